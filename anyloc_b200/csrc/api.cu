@@ -1,0 +1,212 @@
+// C ABI of libanyloc_b200.so: error plumbing, building-block wrappers, GEMM engine dispatch and the
+// DINOv2 forward orchestration (early exit at the hooked module; reference
+// /root/reference/utilities.py:245-252,263-285 + upstream DinoVisionTransformer).
+#include <stdarg.h>
+#include <string.h>
+#include "epilogue.cuh"
+
+namespace anyloc {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+
+int device_sm_count() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else return 148;
+  }
+  return cached;
+}
+
+// engines (defined in gemm_simt.cu / gemm_tc.cu)
+int gemm_simt_launch(const float*, const float*, int, const float*, const float*, int, int, int, int,
+                     const EpiParams&, cudaStream_t);
+int gemm_tc_launch(const float*, const float*, int, const float*, const float*, int, int, int, int,
+                   const EpiParams&, cudaStream_t);
+bool gemm_tc_supported(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo,
+                       int ldb, int M, int N, int K, const EpiParams& ep);
+// vit_ops.cu / attention.cu
+int launch_split(const float*, float*, float*, size_t, cudaStream_t);
+int launch_im2col(const float*, int, int, int, int, int, float*, float*, cudaStream_t);
+int launch_assemble(const float*, const float*, const float*, int, int, int, float*, cudaStream_t);
+int launch_layernorm(const float*, const float*, const float*, int, int, float, float*, float*, cudaStream_t);
+int launch_facet_out(const float*, int, int, int64_t, int, int, int, int, float*, cudaStream_t);
+int launch_l2norm(const float*, int64_t, int, int64_t, float*, cudaStream_t);
+int attention_launch(const float*, int, int, int, int, float*, float*, cudaStream_t);
+
+static int gemm_dispatch(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo,
+                         int ldb, int M, int N, int K, const EpiParams& ep, int engine, cudaStream_t st) {
+  if (M == 0 || N == 0) return ANYLOC_OK;
+  bool tc_ok = gemm_tc_supported(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep);
+  if (engine == ANYLOC_GEMM_TC3 && !tc_ok) {
+    set_error("gemm: tcgen05 engine does not support this shape/alignment (M=%d N=%d K=%d lda=%d ldb=%d)",
+              M, N, K, lda, ldb);
+    return ANYLOC_ERR_UNSUPPORTED;
+  }
+  if (engine == ANYLOC_GEMM_TC3 || (engine == ANYLOC_GEMM_AUTO && tc_ok))
+    return gemm_tc_launch(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st);
+  return gemm_simt_launch(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st);
+}
+
+}  // namespace anyloc
+
+using namespace anyloc;
+
+extern "C" const char* anyloc_last_error(void) { return g_err; }
+extern "C" int anyloc_version(void) { return 100; }
+
+extern "C" int anyloc_device_info(int* sm_count, size_t* smem_optin_bytes) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    set_error("no CUDA device visible (libanyloc_b200 has no CPU fallback)");
+    return ANYLOC_ERR_CUDA;
+  }
+  int dev = 0; cudaDeviceProp p;
+  ANYLOC_CHECK_CUDA(cudaGetDevice(&dev));
+  ANYLOC_CHECK_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (smem_optin_bytes) *smem_optin_bytes = p.sharedMemPerBlockOptin;
+  return p.major * 10 + p.minor;
+}
+
+extern "C" int anyloc_gemm_nt(const float* a_hi, const float* a_lo, int lda, const float* b_hi,
+                              const float* b_lo, int ldb, int M, int N, int K, int epilogue,
+                              const float* bias, const float* gamma, const float* resid, float* out,
+                              float* out_lo, int ldo, int engine, void* stream) {
+  ANYLOC_REQUIRE(a_hi && b_hi && out, "gemm_nt: null pointer");
+  ANYLOC_REQUIRE(M >= 0 && N >= 0 && K > 0, "gemm_nt: bad dims");
+  ANYLOC_REQUIRE(epilogue >= ANYLOC_EPI_BIAS && epilogue <= ANYLOC_EPI_LS_RESID, "gemm_nt: bad epilogue %d", epilogue);
+  if (epilogue == ANYLOC_EPI_BIAS_SPLIT || epilogue == ANYLOC_EPI_GELU_SPLIT || epilogue == ANYLOC_EPI_SWIGLU_SPLIT)
+    ANYLOC_REQUIRE(out_lo, "gemm_nt: split epilogue needs out_lo");
+  if (epilogue == ANYLOC_EPI_SWIGLU_SPLIT) ANYLOC_REQUIRE(N % 2 == 0, "gemm_nt: swiglu needs even N");
+  if (epilogue == ANYLOC_EPI_LS_RESID) ANYLOC_REQUIRE(gamma && resid, "gemm_nt: LS_RESID needs gamma and resid");
+  EpiParams ep{epilogue, bias, gamma, resid, out, out_lo, ldo};
+  return gemm_dispatch(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, engine, (cudaStream_t)stream);
+}
+
+extern "C" int anyloc_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream) {
+  ANYLOC_REQUIRE(x && hi && lo, "split_tf32: null pointer");
+  if (n == 0) return ANYLOC_OK;
+  return launch_split(x, hi, lo, n, (cudaStream_t)stream);
+}
+
+extern "C" int anyloc_layernorm_split(const float* x, const float* w, const float* b, int M, int D,
+                                      float eps, float* y_hi, float* y_lo, void* stream) {
+  ANYLOC_REQUIRE(x && w && b && y_hi && y_lo, "layernorm: null pointer");
+  if (M == 0) return ANYLOC_OK;
+  return launch_layernorm(x, w, b, M, D, eps, y_hi, y_lo, (cudaStream_t)stream);
+}
+
+extern "C" int anyloc_attention(const float* qkv, int B, int T, int D, int heads, float* o_hi, float* o_lo,
+                                void* stream) {
+  ANYLOC_REQUIRE(qkv && o_hi && o_lo, "attention: null pointer");
+  if (B == 0 || T == 0) return ANYLOC_OK;
+  return attention_launch(qkv, B, T, D, heads, o_hi, o_lo, (cudaStream_t)stream);
+}
+
+extern "C" int anyloc_l2_normalize_rows(const float* x, int64_t rows, int D, int64_t ld_in, float* y,
+                                        void* stream) {
+  ANYLOC_REQUIRE(x && y && D % 4 == 0 && ld_in % 4 == 0, "l2_normalize_rows: bad args");
+  if (rows == 0) return ANYLOC_OK;
+  return launch_l2norm(x, rows, D, ld_in, y, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ ViT forward
+extern "C" int anyloc_vit_patch_k(int patch) { return (int)align_up((size_t)3 * patch * patch, 32); }
+
+namespace {
+struct VitBuffers {
+  float *pa_hi, *pa_lo, *ptmp, *x, *y_hi, *y_lo, *qkv, *h_hi, *h_lo;
+};
+size_t vit_carve(const AnylocVitCfg* c, int B, int H, int W, void* ws, size_t ws_bytes, VitBuffers* out) {
+  const int P = c->patch, N = (H / P) * (W / P), T = N + 1, D = c->embed_dim, Kp = anyloc_vit_patch_k(P);
+  const size_t M = (size_t)B * T;
+  Workspace w(ws ? ws : (void*)256, ws ? ws_bytes : (size_t)-1 / 2);
+  VitBuffers b;
+  b.pa_hi = w.take<float>((size_t)B * N * Kp); b.pa_lo = w.take<float>((size_t)B * N * Kp);
+  b.ptmp = w.take<float>((size_t)B * N * D);
+  b.x = w.take<float>(M * D);
+  b.y_hi = w.take<float>(M * D); b.y_lo = w.take<float>(M * D);
+  b.qkv = w.take<float>(M * 3 * D);
+  b.h_hi = w.take<float>(M * c->ffn_hidden); b.h_lo = w.take<float>(M * c->ffn_hidden);
+  if (out) *out = b;
+  if (ws && (!b.pa_hi || !b.pa_lo || !b.ptmp || !b.x || !b.y_hi || !b.y_lo || !b.qkv || !b.h_hi || !b.h_lo)) return 0;
+  return w.off;
+}
+}  // namespace
+
+extern "C" size_t anyloc_vit_workspace_bytes(const AnylocVitCfg* cfg, int B, int H, int W) {
+  if (!cfg || B <= 0 || H < cfg->patch || W < cfg->patch) return 0;
+  return vit_carve(cfg, B, H, W, nullptr, 0, nullptr) + 4096;
+}
+
+static int vit_block(const AnylocVitCfg* c, const AnylocVitBlock& wb, const VitBuffers& bf, int B, int T,
+                     int engine, cudaStream_t st) {
+  const int D = c->embed_dim, M = B * T, Hf = c->ffn_hidden;
+  int rc;
+  if ((rc = launch_layernorm(bf.x, wb.ln1_w, wb.ln1_b, M, D, 1e-6f, bf.y_hi, bf.y_lo, st))) return rc;
+  EpiParams e_qkv{ANYLOC_EPI_BIAS, wb.qkv_b, nullptr, nullptr, bf.qkv, nullptr, 3 * D};
+  if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.qkv_w_hi, wb.qkv_w_lo, D, M, 3 * D, D, e_qkv, engine, st))) return rc;
+  if ((rc = attention_launch(bf.qkv, B, T, D, c->num_heads, bf.y_hi, bf.y_lo, st))) return rc;
+  EpiParams e_proj{ANYLOC_EPI_LS_RESID, wb.proj_b, wb.ls1, bf.x, bf.x, nullptr, D};
+  if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.proj_w_hi, wb.proj_w_lo, D, M, D, D, e_proj, engine, st))) return rc;
+  if ((rc = launch_layernorm(bf.x, wb.ln2_w, wb.ln2_b, M, D, 1e-6f, bf.y_hi, bf.y_lo, st))) return rc;
+  if (c->ffn_kind == ANYLOC_FFN_MLP) {
+    EpiParams e_in{ANYLOC_EPI_GELU_SPLIT, wb.in_b, nullptr, nullptr, bf.h_hi, bf.h_lo, Hf};
+    if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.in_w_hi, wb.in_w_lo, D, M, Hf, D, e_in, engine, st))) return rc;
+  } else {
+    EpiParams e_in{ANYLOC_EPI_SWIGLU_SPLIT, wb.in_b, nullptr, nullptr, bf.h_hi, bf.h_lo, Hf};
+    if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.in_w_hi, wb.in_w_lo, D, M, 2 * Hf, D, e_in, engine, st))) return rc;
+  }
+  EpiParams e_out{ANYLOC_EPI_LS_RESID, wb.out_b, wb.ls2, bf.x, bf.x, nullptr, D};
+  return gemm_dispatch(bf.h_hi, bf.h_lo, Hf, wb.out_w_hi, wb.out_w_lo, Hf, M, D, Hf, e_out, engine, st);
+}
+
+extern "C" int anyloc_vit_extract(const AnylocVitCfg* cfg, const AnylocVitWeights* w, const float* img,
+                                  int B, int H, int W, const float* pos_embed, int layer, int facet,
+                                  int use_cls, int norm_descs, float* out, void* ws, size_t ws_bytes,
+                                  int gemm_engine, void* stream) {
+  ANYLOC_REQUIRE(cfg && w && img && pos_embed && out && ws, "vit_extract: null pointer");
+  ANYLOC_REQUIRE(cfg->patch > 0 && H % cfg->patch == 0 && W % cfg->patch == 0 && H > 0 && W > 0,
+                 "vit_extract: H=%d W=%d must be positive multiples of the patch size %d", H, W, cfg->patch);
+  ANYLOC_REQUIRE(layer >= 0 && layer < cfg->depth, "vit_extract: layer %d out of range [0,%d)", layer, cfg->depth);
+  ANYLOC_REQUIRE(facet >= ANYLOC_FACET_QUERY && facet <= ANYLOC_FACET_TOKEN, "vit_extract: bad facet %d", facet);
+  ANYLOC_REQUIRE(cfg->embed_dim == cfg->num_heads * 64, "vit_extract: head_dim must be 64");
+  ANYLOC_REQUIRE(B > 0, "vit_extract: empty batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = cfg->patch, N = (H / P) * (W / P), T = N + 1, D = cfg->embed_dim, Kp = anyloc_vit_patch_k(P);
+  const int M = B * T;
+  VitBuffers bf;
+  if (!vit_carve(cfg, B, H, W, ws, ws_bytes, &bf)) {
+    set_error("vit_extract: workspace too small (%zu given, %zu needed)", ws_bytes,
+              anyloc_vit_workspace_bytes(cfg, B, H, W));
+    return ANYLOC_ERR_WORKSPACE;
+  }
+  int rc;
+  if ((rc = launch_im2col(img, B, H, W, P, Kp, bf.pa_hi, bf.pa_lo, st))) return rc;
+  EpiParams e_pe{ANYLOC_EPI_BIAS, w->patch_b, nullptr, nullptr, bf.ptmp, nullptr, D};
+  if ((rc = gemm_dispatch(bf.pa_hi, bf.pa_lo, Kp, w->patch_w_hi, w->patch_w_lo, Kp, B * N, D, Kp, e_pe,
+                          gemm_engine, st))) return rc;
+  if ((rc = launch_assemble(bf.ptmp, w->cls_token, pos_embed, B, N, D, bf.x, st))) return rc;
+  for (int l = 0; l < layer; ++l)
+    if ((rc = vit_block(cfg, w->blocks[l], bf, B, T, gemm_engine, st))) return rc;
+  const AnylocVitBlock& wb = w->blocks[layer];
+  if (facet == ANYLOC_FACET_TOKEN) {
+    if ((rc = vit_block(cfg, wb, bf, B, T, gemm_engine, st))) return rc;
+    return launch_facet_out(bf.x, B, T, D, 0, D, use_cls, norm_descs, out, st);
+  }
+  // q/k/v facet: only the requested third of the qkv projection of block `layer`
+  if ((rc = launch_layernorm(bf.x, wb.ln1_w, wb.ln1_b, M, D, 1e-6f, bf.y_hi, bf.y_lo, st))) return rc;
+  const size_t woff = (size_t)facet * D * D;
+  EpiParams e_f{ANYLOC_EPI_BIAS, wb.qkv_b + (size_t)facet * D, nullptr, nullptr, bf.qkv, nullptr, D};
+  if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.qkv_w_hi + woff, wb.qkv_w_lo + woff, D, M, D, D, e_f,
+                          gemm_engine, st))) return rc;
+  return launch_facet_out(bf.qkv, B, T, D, 0, D, use_cls, norm_descs, out, st);
+}

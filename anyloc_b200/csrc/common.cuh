@@ -1,0 +1,69 @@
+// Shared helpers for libanyloc_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/anyloc_b200.h"
+
+namespace anyloc {
+
+void set_error(const char* fmt, ...);
+
+#define ANYLOC_CHECK_CUDA(expr)                                                        \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      anyloc::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__,                 \
+                        cudaGetErrorName(_e), cudaGetErrorString(_e));                 \
+      return ANYLOC_ERR_CUDA;                                                          \
+    }                                                                                  \
+  } while (0)
+
+#define ANYLOC_CHECK_LAUNCH() ANYLOC_CHECK_CUDA(cudaGetLastError())
+
+#define ANYLOC_REQUIRE(cond, ...)                                                      \
+  do {                                                                                 \
+    if (!(cond)) {                                                                     \
+      anyloc::set_error(__VA_ARGS__);                                                  \
+      return ANYLOC_ERR_ARG;                                                           \
+    }                                                                                  \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// bump allocator over a caller-owned workspace
+struct Workspace {
+  char* base; size_t size; size_t off;
+  Workspace(void* p, size_t n) : base((char*)p), size(n), off(0) {}
+  template <typename T> T* take(size_t count) {
+    size_t bytes = align_up(count * sizeof(T), 256);
+    if (off + bytes > size) return nullptr;
+    T* r = (T*)(base + off); off += bytes; return r;
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// fp32 -> (hi, lo): hi = round-to-nearest tf32 (10 explicit mantissa bits, low 13 bits zero),
+// lo = x - hi (exact in fp32).  hi + lo == x exactly.
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  hi = __uint_as_float(u & 0xffffe000u);
+  lo = x - hi;
+}
+
+int device_sm_count();
+
+}  // namespace anyloc

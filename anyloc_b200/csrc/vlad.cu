@@ -1,0 +1,369 @@
+// Hard-assignment VLAD (reference: /root/reference/utilities.py:819-926, residuals :956-962,
+// assignment fpk.KMeans.predict :849).  See include/anyloc_b200.h for the contract.
+//
+// v1 layout (SIMT): three kernels per batch --
+//   centre_prep : c^_k = c_k/(|c_k|+1e-8) (cosine) or c_k with bias -|c_k|^2/2 (euclid)
+//   assign      : one warp per descriptor row: |x|, K dot products against c^ (L1/L2 resident),
+//                 first-max argmax  -> labels, 1/max(|x|,1e-12)
+//   accumulate  : CTA per (image, 128-wide D slice): sum_{label=k}(x^ - c_k) in shared memory,
+//                 per-(image,k,slice) partial sums of squares (deterministic, no atomics)
+//   normalise   : intra + global L2 normalisation, in place on the [B,K*D] output
+#include "common.cuh"
+
+namespace anyloc {
+
+// ------------------------------------------------------------------ centre prep
+__global__ void vlad_centre_prep_kernel(const float* __restrict__ c, int K, int D, int dist_mode,
+                                        float* __restrict__ chat, float* __restrict__ cbias) {
+  int k = blockIdx.x;
+  const float* row = c + (size_t)k * D;
+  float ss = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) { float v = row[d]; ss += v * v; }
+  __shared__ float red[32];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  ss = red[0];
+  if (dist_mode == ANYLOC_DIST_COSINE) {
+    float inv = 1.0f / (sqrtf(ss) + 1e-8f);
+    for (int d = threadIdx.x; d < D; d += blockDim.x) chat[(size_t)k * D + d] = row[d] / (sqrtf(ss) + 1e-8f);
+    (void)inv;
+    if (threadIdx.x == 0) cbias[k] = 0.f;
+  } else {
+    // argmax_k 2 x.c_k - |x|^2 - |c_k|^2  ==  argmax_k (x.c_k - |c_k|^2/2)
+    for (int d = threadIdx.x; d < D; d += blockDim.x) chat[(size_t)k * D + d] = row[d];
+    if (threadIdx.x == 0) cbias[k] = -0.5f * ss;
+  }
+}
+
+// ------------------------------------------------------------------ assign
+// One warp handles ROWS rows at a time; lanes stride the feature dimension in float4.
+template <int ROWS>
+__global__ void __launch_bounds__(256)
+vlad_assign_kernel(const float* __restrict__ x, const int32_t* __restrict__ n_valid, int N_per_img,
+                   int64_t R, int D, int K, const float* __restrict__ chat,
+                   const float* __restrict__ cbias, int32_t* __restrict__ labels,
+                   float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int D4 = D >> 2;
+  for (int64_t r0 = warp * ROWS; r0 < R; r0 += nwarps * ROWS) {
+    const float4* xr[ROWS];
+    bool valid[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+      int64_t r = r0 + i;
+      valid[i] = r < R;
+      if (valid[i] && n_valid) {
+        int b = (int)(r / N_per_img), n = (int)(r % N_per_img);
+        valid[i] = n < n_valid[b];
+      }
+      xr[i] = reinterpret_cast<const float4*>(x + (valid[i] ? r : r0) * (int64_t)D);
+      if (r0 + i >= R) xr[i] = reinterpret_cast<const float4*>(x + r0 * (int64_t)D);
+    }
+    float ss[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) ss[i] = 0.f;
+    for (int d = lane; d < D4; d += 32) {
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i) {
+        float4 v = __ldg(xr[i] + d);
+        ss[i] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+    }
+    float best[ROWS]; int bestk[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) { ss[i] = warp_sum(ss[i]); best[i] = -INFINITY; bestk[i] = 0; }
+    for (int k = 0; k < K; ++k) {
+      const float4* cr = reinterpret_cast<const float4*>(chat + (size_t)k * D);
+      float acc[ROWS];
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i) acc[i] = 0.f;
+      for (int d = lane; d < D4; d += 32) {
+        float4 c = __ldg(cr + d);
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+          float4 v = __ldg(xr[i] + d);     // L1-resident after the norm pass
+          acc[i] = fmaf(v.x, c.x, acc[i]); acc[i] = fmaf(v.y, c.y, acc[i]);
+          acc[i] = fmaf(v.z, c.z, acc[i]); acc[i] = fmaf(v.w, c.w, acc[i]);
+        }
+      }
+      float bk = cbias[k];
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i) {
+        float s = warp_sum(acc[i]) + bk;
+        if (s > best[i]) { best[i] = s; bestk[i] = k; }   // strict >: lowest index wins ties
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i) {
+        int64_t r = r0 + i;
+        if (r < R) {
+          labels[r] = valid[i] ? bestk[i] : -1;
+          if (inv_norm) inv_norm[r] = 1.0f / fmaxf(sqrtf(ss[i]), 1e-12f);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ accumulate
+constexpr int ACC_COLS = 128;
+__global__ void __launch_bounds__(ACC_COLS)
+vlad_accumulate_kernel(const float* __restrict__ x, const int32_t* __restrict__ labels,
+                       const float* __restrict__ inv_norm, const float* __restrict__ centers,
+                       int N, int D, int K, int norm_descs, float* __restrict__ vlad,
+                       float* __restrict__ partial_ss /* [B,K,nslices] */) {
+  extern __shared__ float sm[];
+  float* acc = sm;                    // [K][ACC_COLS]
+  float* cen = sm + (size_t)K * ACC_COLS;  // [K][ACC_COLS]
+  int* lab = reinterpret_cast<int*>(cen + (size_t)K * ACC_COLS);   // [N]
+  float* inv = reinterpret_cast<float*>(lab + N);                  // [N]
+  const int b = blockIdx.y, slice = blockIdx.x, t = threadIdx.x;
+  const int col = slice * ACC_COLS + t;
+  const bool colok = col < D;
+  for (int k = 0; k < K; ++k) {
+    acc[k * ACC_COLS + t] = 0.f;
+    cen[k * ACC_COLS + t] = colok ? centers[(size_t)k * D + col] : 0.f;
+  }
+  for (int n = t; n < N; n += ACC_COLS) {
+    lab[n] = labels[(size_t)b * N + n];
+    inv[n] = norm_descs ? inv_norm[(size_t)b * N + n] : 1.0f;
+  }
+  __syncthreads();
+  const float* xb = x + (size_t)b * N * D + col;
+  if (colok) {
+    int n = 0;
+    for (; n + 4 <= N; n += 4) {
+      float v0 = __ldg(xb + (size_t)(n + 0) * D), v1 = __ldg(xb + (size_t)(n + 1) * D);
+      float v2 = __ldg(xb + (size_t)(n + 2) * D), v3 = __ldg(xb + (size_t)(n + 3) * D);
+      int l0 = lab[n], l1 = lab[n + 1], l2 = lab[n + 2], l3 = lab[n + 3];
+      if (l0 >= 0) acc[l0 * ACC_COLS + t] += v0 * inv[n + 0] - cen[l0 * ACC_COLS + t];
+      if (l1 >= 0) acc[l1 * ACC_COLS + t] += v1 * inv[n + 1] - cen[l1 * ACC_COLS + t];
+      if (l2 >= 0) acc[l2 * ACC_COLS + t] += v2 * inv[n + 2] - cen[l2 * ACC_COLS + t];
+      if (l3 >= 0) acc[l3 * ACC_COLS + t] += v3 * inv[n + 3] - cen[l3 * ACC_COLS + t];
+    }
+    for (; n < N; ++n) {
+      float v = __ldg(xb + (size_t)n * D);
+      int l = lab[n];
+      if (l >= 0) acc[l * ACC_COLS + t] += v * inv[n] - cen[l * ACC_COLS + t];
+    }
+  }
+  __syncthreads();
+  // write un-normalised V and the per-slice sum of squares (warp 0..3 -> fixed order reduce)
+  __shared__ float red[ACC_COLS / 32];
+  const int nslices = gridDim.x;
+  for (int k = 0; k < K; ++k) {
+    float v = acc[k * ACC_COLS + t];
+    if (colok) vlad[((size_t)b * K + k) * D + col] = v;
+    float s = warp_sum(colok ? v * v : 0.f);
+    if ((t & 31) == 0) red[t >> 5] = s;
+    __syncthreads();
+    if (t == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < ACC_COLS / 32; ++w) tot += red[w];
+      partial_ss[((size_t)b * K + k) * nslices + slice] = tot;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ normalise
+__global__ void __launch_bounds__(256)
+vlad_normalize_kernel(float* __restrict__ vlad, const float* __restrict__ partial_ss, int D, int K,
+                      int nslices, int intra_norm) {
+  extern __shared__ float scale[];   // [K]
+  __shared__ float gnorm;
+  const int b = blockIdx.x;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float ss = 0.f;
+    for (int s = 0; s < nslices; ++s) ss += partial_ss[((size_t)b * K + k) * nslices + s];
+    float nk = sqrtf(ss);
+    float sc = intra_norm ? 1.0f / fmaxf(nk, 1e-12f) : 1.0f;
+    scale[k] = sc;
+    // squared norm of the block after intra-normalisation
+    float nb = nk * sc;
+    partial_ss ? (void)0 : (void)0;
+    scale[K + k] = nb * nb;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int k = 0; k < K; ++k) tot += scale[K + k];
+    gnorm = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+  }
+  __syncthreads();
+  float* v = vlad + (size_t)b * K * D;
+  const size_t total = (size_t)K * D;
+  for (size_t i = (size_t)blockIdx.y * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.y * blockDim.x) {
+    int k = (int)(i / D);
+    // two separate multiplications like F.normalize(intra) then F.normalize(global)
+    v[i] = (v[i] * scale[k]) * gnorm;
+  }
+}
+
+// ------------------------------------------------------------------ k-means update
+__global__ void kmeans_accumulate_kernel(const float* __restrict__ x, const int32_t* __restrict__ labels,
+                                         int64_t R, int D, int K, float* __restrict__ sums,
+                                         float* __restrict__ counts) {
+  // grid (D/128 slices, row-chunks); shared [K][128] partial sums, then atomics into sums
+  extern __shared__ float acc[];
+  const int t = threadIdx.x, col = blockIdx.x * ACC_COLS + t;
+  const bool colok = col < D;
+  for (int k = 0; k < K; ++k) acc[k * ACC_COLS + t] = 0.f;
+  float* cnt = acc + (size_t)K * ACC_COLS;
+  for (int k = t; k < K; k += ACC_COLS) cnt[k] = 0.f;
+  __syncthreads();
+  int64_t rows_per = (R + gridDim.y - 1) / gridDim.y;
+  int64_t r0 = (int64_t)blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  for (int64_t r = r0; r < r1; ++r) {
+    int l = labels[r];
+    if (l < 0) continue;
+    if (colok) acc[l * ACC_COLS + t] += __ldg(x + r * D + col);
+    if (blockIdx.x == 0 && t == 0) cnt[l] += 1.f;
+  }
+  __syncthreads();
+  for (int k = 0; k < K; ++k)
+    if (colok && acc[k * ACC_COLS + t] != 0.f) atomicAdd(&sums[(size_t)k * D + col], acc[k * ACC_COLS + t]);
+  if (blockIdx.x == 0)
+    for (int k = t; k < K; k += ACC_COLS) if (cnt[k] != 0.f) atomicAdd(&counts[k], cnt[k]);
+}
+
+__global__ void kmeans_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ counts,
+                                       const float* __restrict__ old_c, int D, int K,
+                                       float* __restrict__ new_c, float* __restrict__ err) {
+  // one block; err = sum((new-old)^2)
+  float e = 0.f;
+  for (size_t i = threadIdx.x; i < (size_t)K * D; i += blockDim.x) {
+    int k = (int)(i / D);
+    float c = counts[k];
+    float v = c > 0.f ? sums[i] / c : 0.f;    // NaN -> 0 for empty clusters (fpk)
+    new_c[i] = v;
+    float d = v - old_c[i];
+    e += d * d;
+  }
+  __shared__ float red[32];
+  e = warp_sum(e);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    err[0] = tot;
+  }
+}
+
+}  // namespace anyloc
+
+using namespace anyloc;
+
+extern "C" size_t anyloc_vlad_workspace_bytes(int B, int N, int D, int K) {
+  size_t R = (size_t)B * N;
+  int nslices = cdiv(D, ACC_COLS);
+  return align_up((size_t)K * D * 4, 256) + align_up((size_t)K * 4, 256) + align_up(R * 4, 256) * 2 +
+         align_up((size_t)B * K * nslices * 4, 256) + align_up(((size_t)K * D + K) * 4, 256) + 4096;
+}
+
+static int launch_assign(const float* feats, const int32_t* n_valid, int N_per_img, int64_t R, int D,
+                         int K, const float* centers, int dist_mode, float* chat, float* cbias,
+                         int32_t* labels, float* inv_norm, cudaStream_t st) {
+  vlad_centre_prep_kernel<<<K, 256, 0, st>>>(centers, K, D, dist_mode, chat, cbias);
+  ANYLOC_CHECK_LAUNCH();
+  int sms = device_sm_count();
+  int64_t warps_needed = (R + 1) / 2;
+  int blocks = (int)std::min<int64_t>((warps_needed + 7) / 8, (int64_t)sms * 8);
+  if (blocks < 1) blocks = 1;
+  vlad_assign_kernel<2><<<blocks, 256, 0, st>>>(feats, n_valid, N_per_img, R, D, K, chat, cbias, labels,
+                                               inv_norm);
+  ANYLOC_CHECK_LAUNCH();
+  return ANYLOC_OK;
+}
+
+extern "C" int anyloc_vlad_assign(const float* feats, const float* centers, int R, int D, int K,
+                                  int dist_mode, int32_t* labels, void* ws, size_t ws_bytes,
+                                  void* stream) {
+  ANYLOC_REQUIRE(feats && centers && labels && ws, "vlad_assign: null pointer");
+  ANYLOC_REQUIRE(R >= 0 && D > 0 && K > 0 && D % 4 == 0, "vlad_assign: bad dims R=%d D=%d K=%d", R, D, K);
+  if (R == 0) return ANYLOC_OK;
+  Workspace w(ws, ws_bytes);
+  float* chat = w.take<float>((size_t)K * D);
+  float* cbias = w.take<float>(K);
+  if (!chat || !cbias) { set_error("vlad_assign: workspace too small"); return ANYLOC_ERR_WORKSPACE; }
+  return launch_assign(feats, nullptr, R, R, D, K, centers, dist_mode, chat, cbias, labels, nullptr,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, const float* centers,
+                                    int B, int N, int D, int K, int dist_mode, int norm_descs,
+                                    int intra_norm, float* vlad, int32_t* labels_out, void* ws,
+                                    size_t ws_bytes, void* stream) {
+  ANYLOC_REQUIRE(feats && centers && vlad && ws, "vlad_generate: null pointer");
+  ANYLOC_REQUIRE(B >= 0 && N >= 0 && D > 0 && K > 0, "vlad_generate: bad dims");
+  ANYLOC_REQUIRE(D % 4 == 0, "vlad_generate: D=%d must be a multiple of 4", D);
+  ANYLOC_REQUIRE(dist_mode == ANYLOC_DIST_COSINE || dist_mode == ANYLOC_DIST_EUCLIDEAN,
+                 "vlad_generate: unknown dist_mode %d", dist_mode);
+  if (B == 0) return ANYLOC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0) { ANYLOC_CHECK_CUDA(cudaMemsetAsync(vlad, 0, (size_t)B * K * D * 4, st)); return ANYLOC_OK; }
+  Workspace w(ws, ws_bytes);
+  const size_t R = (size_t)B * N;
+  const int nslices = cdiv(D, ACC_COLS);
+  float* chat = w.take<float>((size_t)K * D);
+  float* cbias = w.take<float>(K);
+  int32_t* labels = w.take<int32_t>(R);
+  float* inv_norm = w.take<float>(R);
+  float* partial = w.take<float>((size_t)B * K * nslices);
+  if (!chat || !cbias || !labels || !inv_norm || !partial) {
+    set_error("vlad_generate: workspace too small (%zu bytes given)", ws_bytes);
+    return ANYLOC_ERR_WORKSPACE;
+  }
+  int rc = launch_assign(feats, n_valid, N, (int64_t)R, D, K, centers, dist_mode, chat, cbias, labels,
+                         inv_norm, st);
+  if (rc) return rc;
+  size_t smem = ((size_t)2 * K * ACC_COLS + 2 * (size_t)N) * 4;
+  ANYLOC_REQUIRE(smem <= 220 * 1024, "vlad_generate: K=%d N=%d needs %zu B shared memory", K, N, smem);
+  ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(vlad_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+  vlad_accumulate_kernel<<<dim3(nslices, B), ACC_COLS, smem, st>>>(feats, labels, inv_norm, centers, N, D,
+                                                                  K, norm_descs, vlad, partial);
+  ANYLOC_CHECK_LAUNCH();
+  int ysplit = std::max(1, std::min(64, (int)(((size_t)K * D + 256 * 16 - 1) / (256 * 16))));
+  vlad_normalize_kernel<<<dim3(B, ysplit), 256, 2 * K * sizeof(float), st>>>(vlad, partial, D, K, nslices,
+                                                                           intra_norm);
+  ANYLOC_CHECK_LAUNCH();
+  if (labels_out)
+    ANYLOC_CHECK_CUDA(cudaMemcpyAsync(labels_out, labels, R * 4, cudaMemcpyDeviceToDevice, st));
+  return ANYLOC_OK;
+}
+
+extern "C" int anyloc_kmeans_update(const float* x, const int32_t* labels, const float* old_centers,
+                                    int R, int D, int K, float* new_centers, float* err_out, void* ws,
+                                    size_t ws_bytes, void* stream) {
+  ANYLOC_REQUIRE(x && labels && old_centers && new_centers && err_out && ws, "kmeans_update: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w(ws, ws_bytes);
+  float* sums = w.take<float>((size_t)K * D + K);
+  if (!sums) { set_error("kmeans_update: workspace too small"); return ANYLOC_ERR_WORKSPACE; }
+  float* counts = sums + (size_t)K * D;
+  ANYLOC_CHECK_CUDA(cudaMemsetAsync(sums, 0, ((size_t)K * D + K) * 4, st));
+  size_t smem = ((size_t)K * ACC_COLS + K) * 4;
+  ANYLOC_REQUIRE(smem <= 220 * 1024, "kmeans_update: K=%d too large", K);
+  ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(kmeans_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+  int nslices = cdiv(D, ACC_COLS);
+  int chunks = std::max(1, std::min((int)((R + 255) / 256), 4 * device_sm_count() / std::max(1, nslices)));
+  kmeans_accumulate_kernel<<<dim3(nslices, chunks), ACC_COLS, smem, st>>>(x, labels, R, D, K, sums, counts);
+  ANYLOC_CHECK_LAUNCH();
+  kmeans_finalize_kernel<<<1, 1024, 0, st>>>(sums, counts, old_centers, D, K, new_centers, err_out);
+  ANYLOC_CHECK_LAUNCH();
+  return ANYLOC_OK;
+}

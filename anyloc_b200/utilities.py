@@ -1,0 +1,455 @@
+"""Drop-in mirror of the hot-path API of AnyLoc's `utilities.py`
+(/root/reference/utilities.py): `DinoV2ExtractFeatures` (:219-288), `VLAD` (:624-1008),
+`get_top_k_recall` (:390-469) plus the pass-through helpers the callers import from the same
+module (`seed_everything` :505-519, `reduce_pca` :522-586, `CustomDataset` :25-74, `to_np`
+:79-97).  Same names, argument meaning and error behaviour; the arithmetic runs in hand-written
+sm_100a kernels behind the C ABI of include/anyloc_b200.h.  CUDA only -- no CPU fallback.
+
+Put `<repo>/anyloc_b200/dropin` first on PYTHONPATH to make `from utilities import ...` in the
+reference's scripts (scripts/dino_v2_vlad.py:37-38,50) resolve here.
+"""
+import ctypes as C
+import os
+import random
+from typing import List, Literal, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import vit as _vit
+
+_DINO_V2_MODELS = Literal["dinov2_vits14", "dinov2_vitb14", "dinov2_vitl14", "dinov2_vitg14"]
+_DINO_FACETS = Literal["query", "key", "value", "token"]
+
+
+# ------------------------------------------------------------------ helpers (pass-through)
+class CustomDataset:
+    """Abstract parent of the reference's custom datasets (utilities.py:25-74)."""
+
+    def __init__(self) -> None:
+        self.database_num = None
+        self.queries_num = None
+        self.soft_positives_per_query = None
+
+    def get_image_paths(self):
+        if hasattr(self, "images_paths"):
+            return self.images_paths
+        raise NotImplementedError("Not handled!")
+
+    def get_positives(self):
+        if hasattr(self, "soft_positives_per_query"):
+            return self.soft_positives_per_query
+        raise NotImplementedError("Not handled!")
+
+    def get_image_relpaths(self, i: Union[int, List[int]]) -> Union[List[str], str]:
+        single = type(i) == int
+        paths = self.get_image_paths()
+        depth = getattr(self, "_imgs_level", 2)
+        rel = ["/".join(paths[k].split("/")[-depth:]) for k in ([i] if single else i)]
+        return rel[0] if single else rel
+
+    def __getitem__(self, index):
+        raise NotImplementedError("Not created!")
+
+    def __len__(self):
+        if hasattr(self, "images_paths"):
+            return len(self.get_image_paths())
+        raise NotImplementedError("Not handled!")
+
+
+def to_np(x, ret_type=float) -> np.ndarray:
+    """utilities.py:79-97."""
+    arr = x.detach().cpu().numpy() if type(x) == torch.Tensor else np.array(x)
+    return arr.astype(ret_type)
+
+
+def seed_everything(seed=42):
+    """utilities.py:505-519."""
+    random.seed(seed)
+    os.environ["PYTHONHASHSEED"] = str(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    print(f"Seed set to: {seed} (type: {type(seed)})")
+
+
+def reduce_pca(train_descs: np.ndarray, test_descs: np.ndarray, lower_dim: int, low_factor: float = 0.0,
+               fallback: int = 256, svd_solver: str = "full", whitening: bool = False) \
+        -> Tuple[np.ndarray, np.ndarray]:
+    """PCA projection fitted on the training set (utilities.py:522-586); host-side sklearn, not
+    part of the accelerated path."""
+    from sklearn.decomposition import PCA
+    assert 0 <= low_factor <= 1
+    if low_factor == 0.0:
+        pca = PCA(lower_dim, svd_solver=svd_solver, whiten=whitening)
+        return pca.fit_transform(train_descs), pca.transform(test_descs)
+    n_samples, n_components = train_descs.shape
+    if n_samples < n_components:
+        print(f"Too few samples, fallback to {fallback}d first")
+        both = np.concatenate((train_descs.copy(), test_descs.copy()))
+        both = PCA(fallback, svd_solver=svd_solver).fit_transform(both)
+        train_descs, test_descs = both[:n_samples], both[n_samples:]
+    n_low = int(low_factor * lower_dim)
+    n_top = lower_dim - n_low
+    print(f"Up: {n_top}, Down: {n_low}")
+    pca = PCA(train_descs.shape[1], svd_solver=svd_solver)
+    pca.fit(train_descs)
+    basis = np.concatenate((pca.components_[:n_top], pca.components_[-n_low:]))
+    return (train_descs - pca.mean_) @ basis.T, (test_descs - pca.mean_) @ basis.T
+
+
+# ------------------------------------------------------------------ extractor
+class _HookHandle:
+    def remove(self):
+        pass
+
+
+class DinoV2ExtractFeatures:
+    """Extract features from an intermediate layer of DINOv2 (utilities.py:219-288).
+
+    Same constructor and call signature.  The forward stops at the hooked module (blocks
+    0..layer-1, then either the whole block `layer` ("token") or norm1 + the requested third of
+    its qkv projection), which is output-identical to the reference's full forward + hook.
+    Extra keyword-only arguments: `weights` (an upstream state_dict, else see
+    vit.resolve_state_dict) and `gemm_engine` ("auto" | "tc3" | "simt")."""
+
+    def __init__(self, dino_model: _DINO_V2_MODELS, layer: int, facet: _DINO_FACETS = "token",
+                 use_cls=False, norm_descs=True, device: str = "cpu", *, weights=None,
+                 gemm_engine: str = "auto") -> None:
+        self.vit_type: str = dino_model
+        self.device = torch.device(device)
+        dev = _lib.require_cuda(self.device)
+        if facet not in _lib.FACET:
+            raise ValueError(f"facet must be one of {sorted(_lib.FACET)}, got {facet!r}")
+        sd = weights if weights is not None else _vit.resolve_state_dict(dino_model, dev)
+        # only blocks 0..layer are ever executed (early exit), so only those are uploaded
+        self.dino_model = _vit.VitWeights(dino_model, sd, dev, depth=layer + 1)
+        self.layer: int = layer
+        self.facet = facet
+        self.use_cls = use_cls
+        self.norm_descs = norm_descs
+        self.gemm_engine = gemm_engine
+        self.fh_handle = _HookHandle()
+        self._hook_out = None
+
+    def __call__(self, img: torch.Tensor) -> torch.Tensor:
+        with torch.no_grad():
+            return self.dino_model.extract(img, self.layer, self.facet, self.use_cls, self.norm_descs,
+                                           self.gemm_engine)
+
+    def __del__(self):
+        pass
+
+
+# ------------------------------------------------------------------ VLAD
+def _as_device_f32(x, device):
+    if type(x) == np.ndarray:
+        x = torch.from_numpy(x)
+    return x.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class _KMeans:
+    """GPU stand-in for `fast_pytorch_kmeans.KMeans` as the reference uses it (utilities.py:766,
+    :772, :786-787, :849): `.centroids`, `.fit(X)`, `.predict(X)`; cosine / euclidean similarity,
+    numpy-seeded random-choice init, <=100 Lloyd iterations, tol 1e-4."""
+
+    def __init__(self, n_clusters, max_iter=100, tol=1e-4, verbose=0, mode="euclidean", minibatch=None):
+        if mode not in _lib.DIST:
+            raise NotImplementedError(mode)
+        self.n_clusters, self.max_iter, self.tol, self.mode = n_clusters, max_iter, tol, mode
+        self.verbose, self.minibatch = verbose, minibatch
+        self.centroids = None
+
+    def _assign(self, x, centers):
+        lib = _lib.load()
+        R, D = x.shape
+        K = centers.shape[0]
+        labels = torch.empty(R, dtype=torch.int32, device=x.device)
+        with torch.cuda.device(x.device):
+            ws = _lib.workspaces.get(x.device, lib.anyloc_vlad_workspace_bytes(1, 1, D, K), "kmeans")
+            _lib.check(lib.anyloc_vlad_assign(_lib.ptr(x), _lib.ptr(centers), R, D, K, _lib.DIST[self.mode],
+                                              _lib.ptr(labels), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                       "anyloc_vlad_assign")
+        return labels
+
+    def predict(self, X):
+        dev = _lib.require_cuda(X.device if isinstance(X, torch.Tensor) and X.is_cuda else None)
+        was_cpu = not (isinstance(X, torch.Tensor) and X.is_cuda)
+        labels = self._assign(_as_device_f32(X, dev), _as_device_f32(self.centroids, dev)).to(torch.int64)
+        return labels.cpu() if was_cpu else labels
+
+    def fit_predict(self, X, centroids=None):
+        dev = _lib.require_cuda(X.device if X.is_cuda else None)
+        was_cpu = not X.is_cuda
+        x = _as_device_f32(X, dev)
+        n, D = x.shape
+        K = self.n_clusters
+        if centroids is None:
+            init = np.random.choice(n, size=[K], replace=False)      # numpy RNG, as upstream
+            c = x[torch.from_numpy(init).to(dev)].contiguous()
+        else:
+            c = _as_device_f32(centroids, dev)
+        lib = _lib.load()
+        new_c = torch.empty_like(c)
+        err = torch.zeros(1, device=dev)
+        labels = None
+        with torch.cuda.device(dev):
+            ws = _lib.workspaces.get(dev, lib.anyloc_vlad_workspace_bytes(1, 1, D, K), "kmeans_upd")
+            for _ in range(self.max_iter):
+                labels = self._assign(x, c)
+                _lib.check(lib.anyloc_kmeans_update(_lib.ptr(x), _lib.ptr(labels), _lib.ptr(c), n, D, K,
+                                                    _lib.ptr(new_c), _lib.ptr(err), _lib.ptr(ws), ws.numel(),
+                                                    _lib.stream_ptr()), "anyloc_kmeans_update")
+                c, new_c = new_c, c
+                if float(err.item()) <= self.tol:
+                    break
+        self.centroids = c.cpu() if was_cpu else c
+        labels = labels.to(torch.int64)
+        return labels.cpu() if was_cpu else labels
+
+    def fit(self, X, centroids=None):
+        self.fit_predict(X, centroids)
+
+
+class VLAD:
+    """Hard-assignment VLAD with the reference's constructor and methods (utilities.py:624-1008).
+
+    `generate` / `generate_multi` take what the reference takes (CPU tensors / numpy arrays /
+    ragged lists) and return what it returns (CPU tensors); CUDA tensors are also accepted and
+    then stay on the device (the batched fast path).  The on-disk vocabulary cache
+    (`c_centers.pt`) is honoured; the reference's per-image residual cache (`*_r.pt`, >=100 MB per
+    image) is neither read nor written.  `vlad_mode="soft"` is not implemented yet."""
+
+    def __init__(self, num_clusters: int, desc_dim: Union[int, None] = None, intra_norm: bool = True,
+                 norm_descs: bool = True, dist_mode: str = "cosine", vlad_mode: str = "hard",
+                 soft_temp: float = 1.0, cache_dir: Union[str, None] = None) -> None:
+        self.num_clusters = num_clusters
+        self.desc_dim = desc_dim
+        self.intra_norm = intra_norm
+        self.norm_descs = norm_descs
+        self.mode = dist_mode
+        self.vlad_mode = str(vlad_mode).lower()
+        assert self.vlad_mode in ["soft", "hard"]
+        self.soft_temp = soft_temp
+        self.c_centers = None
+        self.kmeans = None
+        self._centers_dev = {}
+        self.cache_dir = cache_dir
+        if self.cache_dir is not None:
+            self.cache_dir = os.path.abspath(os.path.expanduser(self.cache_dir))
+            if not os.path.exists(self.cache_dir):
+                os.makedirs(self.cache_dir)
+                print(f"Created cache directory: {self.cache_dir}")
+            else:
+                print(f"Warning: Cache directory already exists: {self.cache_dir}")
+        else:
+            print("VLAD caching is disabled.")
+
+    # -- cache predicates (utilities.py:688-746)
+    def can_use_cache_vlad(self):
+        if self.cache_dir is None or not os.path.exists(self.cache_dir):
+            return False
+        return os.path.exists(f"{self.cache_dir}/c_centers.pt")
+
+    def can_use_cache_ids(self, cache_ids: Union[List[str], str, None], only_residuals: bool = False) -> bool:
+        if not self.can_use_cache_vlad() or cache_ids is None:
+            return False
+        if isinstance(cache_ids, str):
+            cache_ids = [cache_ids]
+        suffix = "l" if self.vlad_mode == "hard" else "s"
+        for cid in cache_ids:
+            if not os.path.exists(f"{self.cache_dir}/{cid}_r.pt"):
+                return False
+            if not only_residuals and not os.path.exists(f"{self.cache_dir}/{cid}_{suffix}.pt"):
+                return False
+        return True
+
+    # -- vocabulary (utilities.py:749-791)
+    def fit(self, train_descs: Union[np.ndarray, torch.Tensor, None]):
+        self.kmeans = _KMeans(self.num_clusters, mode=self.mode)
+        self._centers_dev = {}
+        if self.can_use_cache_vlad():
+            print("Using cached cluster centers")
+            self.c_centers = torch.load(f"{self.cache_dir}/c_centers.pt")
+            self.kmeans.centroids = self.c_centers
+            if self.desc_dim is None:
+                self.desc_dim = self.c_centers.shape[1]
+                print(f"Desc dim set to {self.desc_dim}")
+            return
+        if train_descs is None:
+            raise ValueError("No training descriptors given")
+        if type(train_descs) == np.ndarray:
+            train_descs = torch.from_numpy(train_descs).to(torch.float32)
+        if self.desc_dim is None:
+            self.desc_dim = train_descs.shape[1]
+        dev = _lib.require_cuda(train_descs.device if train_descs.is_cuda else None)
+        was_cpu = not train_descs.is_cuda
+        x = _as_device_f32(train_descs, dev)
+        if self.norm_descs:
+            y = torch.empty_like(x)
+            with torch.cuda.device(dev):
+                _lib.check(_lib.load().anyloc_l2_normalize_rows(_lib.ptr(x), x.shape[0], x.shape[1], x.shape[1],
+                                                                _lib.ptr(y), _lib.stream_ptr()), "l2_normalize_rows")
+            x = y
+        self.kmeans.fit(x)
+        self.c_centers = self.kmeans.centroids.cpu() if was_cpu else self.kmeans.centroids
+        self.kmeans.centroids = self.c_centers
+        if self.cache_dir is not None:
+            print("Caching cluster centers")
+            torch.save(self.c_centers.cpu(), f"{self.cache_dir}/c_centers.pt")
+
+    def fit_and_generate(self, train_descs: Union[np.ndarray, torch.Tensor]) -> torch.Tensor:
+        if type(train_descs) == np.ndarray:
+            train_descs = torch.from_numpy(train_descs).to(torch.float32)
+        self.fit(train_descs.reshape(-1, train_descs.shape[-1]))
+        return self.generate_multi(train_descs)
+
+    # -- device plumbing
+    def _centers_on(self, dev):
+        key = (dev.index, id(self.c_centers))
+        if key not in self._centers_dev:
+            self._centers_dev = {key: _as_device_f32(self.c_centers, dev)}
+        return self._centers_dev[key]
+
+    def _run(self, feats, n_valid, dev, want_labels=False):
+        """feats [B,N,D] device fp32; n_valid [B] int32 device or None -> ([B,K*D], labels|None)."""
+        assert self.kmeans is not None
+        assert self.c_centers is not None
+        if self.vlad_mode != "hard":
+            raise NotImplementedError("anyloc_b200: soft-assignment VLAD is not implemented (hard only)")
+        lib = _lib.load()
+        B, N, D = feats.shape
+        K = self.num_clusters
+        centers = self._centers_on(dev)
+        if centers.shape != (K, D):
+            raise ValueError(f"cluster centres {tuple(centers.shape)} do not match K={K}, D={D}")
+        out = torch.empty(B, K * D, device=dev, dtype=torch.float32)
+        labels = torch.empty(B, N, device=dev, dtype=torch.int32) if want_labels else None
+        with torch.cuda.device(dev):
+            ws = _lib.workspaces.get(dev, lib.anyloc_vlad_workspace_bytes(B, N, D, K), "vlad")
+            rc = lib.anyloc_vlad_generate(_lib.ptr(feats), _lib.ptr(n_valid), _lib.ptr(centers), B, N, D, K,
+                                          _lib.DIST[self.mode], int(bool(self.norm_descs)),
+                                          int(bool(self.intra_norm)), _lib.ptr(out), _lib.ptr(labels),
+                                          _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, "anyloc_vlad_generate")
+        return out, labels
+
+    # -- descriptors (utilities.py:819-926)
+    def generate(self, query_descs: Union[np.ndarray, torch.Tensor], cache_id: Union[str, None] = None) \
+            -> torch.Tensor:
+        on_dev = isinstance(query_descs, torch.Tensor) and query_descs.is_cuda
+        dev = _lib.require_cuda(query_descs.device if on_dev else None)
+        x = _as_device_f32(query_descs, dev)
+        out, _ = self._run(x.unsqueeze(0), None, dev)
+        return out[0] if on_dev else out[0].cpu()
+
+    def generate_multi(self, multi_query: Union[np.ndarray, torch.Tensor, list],
+                       cache_ids: Union[List[str], None] = None) -> Union[torch.Tensor, list]:
+        if isinstance(multi_query, (list, tuple)):
+            if len(multi_query) == 0:
+                return torch.stack([])      # same failure as the reference on an empty list
+            on_dev = all(isinstance(q, torch.Tensor) and q.is_cuda for q in multi_query)
+            dev = _lib.require_cuda(multi_query[0].device if on_dev else None)
+            qs = [_as_device_f32(q, dev) for q in multi_query]
+            n_max = max(q.shape[0] for q in qs)
+            D = qs[0].shape[1]
+            feats = torch.zeros(len(qs), n_max, D, device=dev, dtype=torch.float32)
+            for i, q in enumerate(qs):
+                feats[i, :q.shape[0]] = q
+            n_valid = torch.tensor([q.shape[0] for q in qs], dtype=torch.int32, device=dev)
+            out, _ = self._run(feats, n_valid, dev)
+            return out if on_dev else out.cpu()
+        was_np = type(multi_query) == np.ndarray
+        on_dev = isinstance(multi_query, torch.Tensor) and multi_query.is_cuda
+        dev = _lib.require_cuda(multi_query.device if on_dev else None)
+        if not on_dev and not was_np and multi_query.numel() * 4 > (1 << 30):
+            # large host batches (the driver hands over [n_imgs, n_patches, D] on the CPU): stream chunks
+            step = max(1, (1 << 30) // (multi_query[0].numel() * 4))
+            return torch.cat([self._run(_as_device_f32(multi_query[i:i + step], dev), None, dev)[0].cpu()
+                              for i in range(0, multi_query.shape[0], step)])
+        out, _ = self._run(_as_device_f32(multi_query, dev), None, dev)
+        return out if on_dev else out.cpu()
+
+    # -- residual tensors (utilities.py:928-1008); off the hot path, plain tensor algebra
+    def generate_res_vec(self, query_descs: Union[np.ndarray, torch.Tensor],
+                         cache_id: Union[str, None] = None) -> torch.Tensor:
+        assert self.kmeans is not None
+        assert self.c_centers is not None
+        if type(query_descs) == np.ndarray:
+            query_descs = torch.from_numpy(query_descs).to(torch.float32)
+        if self.norm_descs:
+            query_descs = torch.nn.functional.normalize(query_descs)
+        return query_descs[:, None, :] - self.c_centers.to(query_descs.device)[None, :, :]
+
+    def generate_multi_res_vec(self, multi_query, cache_ids=None):
+        res = [self.generate_res_vec(q) for q in multi_query]
+        try:
+            return torch.stack(res)
+        except (TypeError, RuntimeError):
+            return res
+
+
+# ------------------------------------------------------------------ retrieval
+def top_k_search(db: torch.Tensor, qu: torch.Tensor, k: int, method: str = "cosine",
+                 norm_descs: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exact k-nearest search on the GPU (the `faiss.IndexFlatIP/L2.search` part of
+    get_top_k_recall, utilities.py:435-450).  Device tensors in, device tensors out."""
+    if method not in _lib.METRIC:
+        raise NotImplementedError(f"Method: {method}")
+    dev = _lib.require_cuda(db.device)
+    lib = _lib.load()
+    n_db, Dv = db.shape
+    n_q = qu.shape[0]
+    pad = (-Dv) % 4
+    if pad:     # zero columns change neither norms nor scores
+        db = torch.nn.functional.pad(db, (0, pad))
+        qu = torch.nn.functional.pad(qu, (0, pad))
+        Dv += pad
+    dist = torch.empty(n_q, k, device=dev, dtype=torch.float32)
+    idx = torch.empty(n_q, k, device=dev, dtype=torch.int64)
+    with torch.cuda.device(dev):
+        ws = _lib.workspaces.get(dev, lib.anyloc_topk_workspace_bytes(n_db, n_q, Dv, k), "topk")
+        rc = lib.anyloc_topk(_lib.ptr(db), _lib.ptr(qu), n_db, n_q, Dv, k, _lib.METRIC[method],
+                             int(bool(norm_descs)), _lib.ptr(dist), _lib.ptr(idx), _lib.ptr(ws), ws.numel(),
+                             _lib.stream_ptr())
+    _lib.check(rc, "anyloc_topk")
+    return dist, idx
+
+
+def get_top_k_recall(top_k: List[int], db: torch.Tensor, qu: torch.Tensor, gt_pos: np.ndarray,
+                     method: str = "cosine", norm_descs: bool = True, use_gpu: bool = False,
+                     use_percentage: bool = True, sub_sample_db: int = 1, sub_sample_qu: int = 1) \
+        -> Tuple[np.ndarray, np.ndarray, dict]:
+    """utilities.py:390-469.  `use_gpu` is accepted for signature compatibility; the search always
+    runs on the GPU.  Host tensors in -> host tensors out (like faiss with torch_utils)."""
+    if method not in _lib.METRIC:
+        raise NotImplementedError(f"Method: {method}")
+    as_numpy = type(db) == np.ndarray
+    if as_numpy:
+        db, qu = torch.from_numpy(db), torch.from_numpy(np.asarray(qu))
+    if len(qu.shape) == 1:
+        qu = qu.unsqueeze(0)
+    on_dev = db.is_cuda
+    dev = _lib.require_cuda(db.device if on_dev else None)
+    distances, indices = top_k_search(_as_device_f32(db, dev), _as_device_f32(qu, dev), max(top_k), method,
+                                      norm_descs)
+    idx_host = indices.cpu().numpy()
+    recalls = dict(zip(top_k, [0] * len(top_k)))
+    for i_qu, qu_retr in enumerate(idx_host):
+        correct_retr = gt_pos[i_qu * sub_sample_qu]
+        for i_rec in top_k:
+            if np.any(np.isin(qu_retr[:i_rec] * sub_sample_db, correct_retr)):
+                recalls[i_rec] += 1
+    if use_percentage:
+        for k in recalls:
+            recalls[k] /= len(idx_host)
+    if not on_dev:
+        distances, indices = distances.cpu(), indices.cpu()
+    if as_numpy:
+        distances, indices = distances.numpy(), indices.numpy()
+    return distances, indices, recalls
+
+
+seed_everything()       # import side effect of the reference module (utilities.py:1011)

@@ -1,0 +1,159 @@
+/*
+ * anyloc_b200.h -- C ABI of libanyloc_b200.so (sm_100a).
+ *
+ * The reference (AnyLoc) is pure Python and has no FFI; the boundary it exposes
+ * for this hot path is the Python class API of /root/reference/utilities.py.
+ * Each entry point below cites the reference interface whose arithmetic it
+ * replaces; the Python mirror of that API (anyloc_b200/utilities.py) binds
+ * these symbols with ctypes.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless the name ends in _host;
+ * every call enqueues work on `stream` (a cudaStream_t passed as void*) and
+ * returns without synchronising; return value 0 = ok, negative = error (text
+ * from anyloc_last_error(), thread-local).  No global state; workspaces are
+ * caller-owned (sizes from the *_workspace_bytes functions).  There is NO CPU
+ * fallback: without a CUDA device the compute calls return ANYLOC_ERR_CUDA.
+ */
+#ifndef ANYLOC_B200_H
+#define ANYLOC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANYLOC_OK 0
+#define ANYLOC_ERR_ARG (-1)
+#define ANYLOC_ERR_CUDA (-2)
+#define ANYLOC_ERR_WORKSPACE (-3)
+#define ANYLOC_ERR_UNSUPPORTED (-4)
+
+/* dist_mode: VLAD(dist_mode=...) utilities.py:660 */
+#define ANYLOC_DIST_COSINE 0
+#define ANYLOC_DIST_EUCLIDEAN 1
+/* metric: get_top_k_recall(method=...) utilities.py:439-444 */
+#define ANYLOC_METRIC_IP 0
+#define ANYLOC_METRIC_L2 1
+/* facet: DinoV2ExtractFeatures(facet=...) utilities.py:245-252,274-281 */
+#define ANYLOC_FACET_QUERY 0
+#define ANYLOC_FACET_KEY 1
+#define ANYLOC_FACET_VALUE 2
+#define ANYLOC_FACET_TOKEN 3
+/* ffn kinds of the DINOv2 family (upstream dinov2/hub/backbones.py) */
+#define ANYLOC_FFN_MLP 0
+#define ANYLOC_FFN_SWIGLU 1
+
+/* GEMM epilogues (internal building blocks, exported for parity tests) */
+#define ANYLOC_EPI_BIAS 0          /* out = acc + bias                                   */
+#define ANYLOC_EPI_BIAS_SPLIT 1    /* v = acc + bias           -> (hi,lo) tf32 pair      */
+#define ANYLOC_EPI_GELU_SPLIT 2    /* v = gelu_erf(acc + bias) -> (hi,lo)                */
+#define ANYLOC_EPI_SWIGLU_SPLIT 3  /* cols (2j,2j+1)=(x1,x2); v=silu(x1)*x2 -> (hi,lo)[j] */
+#define ANYLOC_EPI_LS_RESID 4      /* out = resid + gamma * (acc + bias)                 */
+/* GEMM engines */
+#define ANYLOC_GEMM_AUTO 0
+#define ANYLOC_GEMM_SIMT 1         /* fp32 FFMA (validation / odd shapes)               */
+#define ANYLOC_GEMM_TC3 2          /* tcgen05 kind::tf32, 3-term split (fp32-equivalent) */
+
+const char* anyloc_last_error(void);
+int anyloc_version(void);
+/* >0: compute capability *10 of the current device (100 on B200); <0: no usable device */
+int anyloc_device_info(int* sm_count, size_t* smem_optin_bytes);
+
+/* ------------------------------------------------------------------ VLAD
+ * Replaces VLAD.generate / generate_multi (utilities.py:819-926) incl. the
+ * residuals of generate_res_vec (:956-962) and fpk.KMeans.predict (:849):
+ *   x^ = x / max(|x|,1e-12)                (norm_descs)
+ *   label = argmax_k sim(x, c_k)            (cosine: x.c_k/(|c_k|+1e-8); euclid: 2x.c_k-|c_k|^2;
+ *                                            lowest k wins exact ties)
+ *   V_k = sum_{label=k} (x^ - c_k);  V_k /= max(|V_k|,1e-12) (intra_norm);  V /= max(|V|,1e-12)
+ * feats [B,N,D] fp32 row-major, n_valid [B] (nullable; rows >= n_valid[b] ignored, ragged lists),
+ * centers [K,D], vlad [B,K*D], labels [B,N] int32 (nullable; -1 for ignored rows).
+ */
+size_t anyloc_vlad_workspace_bytes(int B, int N, int D, int K);
+int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, const float* centers,
+                         int B, int N, int D, int K, int dist_mode, int norm_descs, int intra_norm,
+                         float* vlad, int32_t* labels, void* ws, size_t ws_bytes, void* stream);
+/* labels only (fpk.KMeans.predict, utilities.py:849; also one Lloyd assignment step of VLAD.fit :786) */
+int anyloc_vlad_assign(const float* feats, const float* centers, int R, int D, int K, int dist_mode,
+                       int32_t* labels, void* ws, size_t ws_bytes, void* stream);
+/* one Lloyd centroid update of fpk.KMeans.fit (utilities.py:786): new_c[k] = mean of members
+ * (0 for empty clusters); err_out[0] = sum((new_c - old_c)^2).  sums_ws: K*D+K floats. */
+int anyloc_kmeans_update(const float* x, const int32_t* labels, const float* old_centers, int R, int D,
+                         int K, float* new_centers, float* err_out, void* ws, size_t ws_bytes,
+                         void* stream);
+
+/* ------------------------------------------------------------- retrieval
+ * Replaces the faiss part of get_top_k_recall (utilities.py:435-450): optional row
+ * normalisation (F.normalize), exact inner-product / squared-L2 scores, k best per query
+ * sorted best-first, lowest database index first among equal scores.
+ * db [n_db,Dv], qu [n_q,Dv] fp32; dist [n_q,k] fp32; idx [n_q,k] int64.
+ */
+size_t anyloc_topk_workspace_bytes(int n_db, int n_q, int Dv, int k);
+int anyloc_topk(const float* db, const float* qu, int n_db, int n_q, int Dv, int k, int metric,
+                int normalize, float* dist, int64_t* idx, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------- ViT
+ * Replaces DinoV2ExtractFeatures.__call__ (utilities.py:263-285) and the hub model's forward
+ * it triggers (facebookresearch/dinov2 DinoVisionTransformer), with the
+ * early exit at the hooked module (blocks 0..layer-1, then norm1+qkv-third or the whole block).
+ */
+typedef struct {
+  int embed_dim;   /* 384 / 768 / 1024 / 1536 */
+  int depth;       /* number of blocks whose weights are supplied */
+  int num_heads;   /* head_dim must be 64 */
+  int ffn_kind;    /* ANYLOC_FFN_* */
+  int ffn_hidden;  /* 4*D (mlp) or 4096-style fused hidden (swiglu) */
+  int patch;       /* 14 */
+} AnylocVitCfg;
+
+/* Per-block device pointers.  Matrices are [out,in] row-major like nn.Linear.weight, supplied as
+ * tf32 (hi,lo) pairs with hi+lo == fp32 weight (anyloc_split_tf32).  For SwiGLU, w_in rows are
+ * interleaved (row 2j = w12[j], row 2j+1 = w12[hidden+j]) and b_in likewise. */
+typedef struct {
+  const float *ln1_w, *ln1_b;
+  const float *qkv_w_hi, *qkv_w_lo, *qkv_b;     /* [3D,D], [3D] */
+  const float *proj_w_hi, *proj_w_lo, *proj_b;  /* [D,D],  [D]  */
+  const float *ls1;                             /* [D] LayerScale gamma */
+  const float *ln2_w, *ln2_b;
+  const float *in_w_hi, *in_w_lo, *in_b;        /* fc1 [4D,D] or interleaved w12 [2H,D] */
+  const float *out_w_hi, *out_w_lo, *out_b;     /* fc2 [D,4D] or w3 [D,H] */
+  const float *ls2;
+} AnylocVitBlock;
+
+typedef struct {
+  const float *patch_w_hi, *patch_w_lo; /* [D, Kp] conv weight flattened (c,ky,kx), zero padded to Kp */
+  const float *patch_b;                 /* [D] */
+  const float *cls_token;               /* [D] */
+  const AnylocVitBlock* blocks;         /* HOST array [depth] of device pointers */
+} AnylocVitWeights;
+
+/* padded patch-embed reduction length (3*14*14=588 -> multiple of 32) */
+int anyloc_vit_patch_k(int patch);
+size_t anyloc_vit_workspace_bytes(const AnylocVitCfg* cfg, int B, int H, int W);
+/* img [B,3,H,W] fp32 (H,W multiples of 14); pos_embed [1+g_h*g_w, D] already interpolated for this
+ * grid (upstream interpolate_pos_encoding); out [B, N(+1 if use_cls), D]. */
+int anyloc_vit_extract(const AnylocVitCfg* cfg, const AnylocVitWeights* w_host, const float* img,
+                       int B, int H, int W, const float* pos_embed, int layer, int facet,
+                       int use_cls, int norm_descs, float* out, void* ws, size_t ws_bytes,
+                       int gemm_engine, void* stream);
+
+/* ------------------------------------------- building blocks (exported for parity tests)
+ * C[M,N] = (A_hi+A_lo)[M,K] . (B_hi+B_lo)[N,K]^T with epilogue; *_lo nullable (treated as 0).
+ * lda/ldb/ldo in elements.  out_lo/bias/gamma/resid per epilogue. */
+int anyloc_gemm_nt(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo,
+                   int ldb, int M, int N, int K, int epilogue, const float* bias, const float* gamma,
+                   const float* resid, float* out, float* out_lo, int ldo, int engine, void* stream);
+int anyloc_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream);
+int anyloc_layernorm_split(const float* x, const float* w, const float* b, int M, int D, float eps,
+                           float* y_hi, float* y_lo, void* stream);
+/* qkv [B,T,3D] fp32 ([q|k|v] thirds, heads of 64) -> o (hi,lo) [B,T,D] */
+int anyloc_attention(const float* qkv, int B, int T, int D, int heads, float* o_hi, float* o_lo,
+                     void* stream);
+int anyloc_l2_normalize_rows(const float* x, int64_t rows, int D, int64_t ld_in, float* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANYLOC_B200_H */

@@ -1,0 +1,147 @@
+"""TEST INFRASTRUCTURE -- CPU restatement (torch, fp32 with optional fp64) of the
+reference's hot path.  Each function cites the reference lines it follows
+(/root/reference/utilities.py).  Pinned against the verbatim reference import
+through tests/golden/*.npz (see tests/golden/make_golden.py).  Travels to the
+GPU box (the reference tree does not).
+"""
+import numpy as np
+import torch
+from torch.nn import functional as F
+
+
+# ---------------------------------------------------------------- extractor
+def extract_features(model, img, layer, facet="value", use_cls=False, norm_descs=True):
+    """utilities.py:263-285 with the hook of :245-252 evaluated explicitly:
+    facet 'token'   = output of blocks[layer];
+    facet q/k/v     = thirds of blocks[layer].attn.qkv(norm1(x_layer)).
+    Early exit after the hooked module is output-identical to the full forward the
+    reference runs (its result is discarded, utilities.py:269-273)."""
+    with torch.no_grad():
+        x = model.prepare_tokens(img)
+        for blk in model.blocks[:layer]:
+            x = blk(x)
+        blk = model.blocks[layer]
+        if facet == "token":
+            res = blk(x)
+        else:
+            res = blk.attn.qkv(blk.norm1(x))
+        if not use_cls:
+            res = res[:, 1:, ...]
+        if facet in ("query", "key", "value"):
+            d = res.shape[2] // 3
+            i = {"query": 0, "key": 1, "value": 2}[facet]
+            res = res[:, :, i * d:(i + 1) * d]
+    if norm_descs:
+        res = F.normalize(res, dim=-1)
+    return res
+
+
+# --------------------------------------------------------------------- VLAD
+def assign_similarity(x, centers, dist_mode="cosine"):
+    """fpk.KMeans.max_sim as reached from utilities.py:849 (`predict` on the
+    descriptors as passed in, i.e. NOT re-normalised in that scope)."""
+    if dist_mode == "cosine":
+        a = x / (x.norm(dim=-1, keepdim=True) + 1e-8)
+        b = centers / (centers.norm(dim=-1, keepdim=True) + 1e-8)
+        return a @ b.T
+    if dist_mode == "euclidean":
+        return 2 * x @ centers.T - (x ** 2).sum(1)[:, None] - (centers ** 2).sum(1)[None, :]
+    raise NotImplementedError(dist_mode)
+
+
+def vlad_labels(x, centers, dist_mode="cosine"):
+    return assign_similarity(x, centers, dist_mode).max(dim=-1)[1]
+
+
+def vlad_generate(x, centers, intra_norm=True, norm_descs=True, dist_mode="cosine",
+                  labels=None, dtype=None):
+    """utilities.py:819-890 hard branch (:841-861) + residuals (:956-962), without
+    materialising [N,K,D].  `labels` may be forced (margin-aware parity tests);
+    `dtype=torch.float64` gives the high-precision variant."""
+    x = torch.as_tensor(x)
+    centers = torch.as_tensor(centers)
+    if dtype is not None:
+        x, centers = x.to(dtype), centers.to(dtype)
+    K, D = centers.shape
+    if labels is None:
+        labels = vlad_labels(x, centers, dist_mode)          # :849
+    xn = F.normalize(x) if norm_descs else x                  # :959-960
+    out = torch.zeros(K * D, dtype=x.dtype)                   # :840
+    for k in sorted(set(labels.tolist())):                    # :854-855
+        cd = (xn[labels == k] - centers[k][None]).sum(0)      # :858 (residual :961-962)
+        if intra_norm:
+            cd = F.normalize(cd, dim=0)                       # :859-860
+        out[k * D:(k + 1) * D] = cd                           # :861
+    return F.normalize(out, dim=0)                            # :889
+
+
+def vlad_generate_multi(xs, centers, **kw):
+    """utilities.py:892-926."""
+    return torch.stack([vlad_generate(x, centers, **kw) for x in xs])
+
+
+def label_margins(x, centers, dist_mode="cosine"):
+    """fp64 top1-top2 similarity gap per descriptor and fp64 labels."""
+    s = assign_similarity(torch.as_tensor(x).double(), torch.as_tensor(centers).double(), dist_mode)
+    if s.shape[1] == 1:
+        return torch.full((s.shape[0],), float("inf"), dtype=torch.float64), torch.zeros(s.shape[0], dtype=torch.long)
+    top2 = s.topk(2, dim=1)[0]
+    return top2[:, 0] - top2[:, 1], s.max(dim=1)[1]
+
+
+# ---------------------------------------------------------------- retrieval
+def top_k(db, qu, k, method="cosine", norm_descs=True, dtype=None):
+    """utilities.py:433-450 (normalise, exact IP / squared-L2 search, k best, sorted,
+    lowest index first among equals)."""
+    db, qu = torch.as_tensor(db), torch.as_tensor(qu)
+    if dtype is not None:
+        db, qu = db.to(dtype), qu.to(dtype)
+    if qu.dim() == 1:
+        qu = qu.unsqueeze(0)
+    if norm_descs:
+        db, qu = F.normalize(db), F.normalize(qu)
+    if method == "cosine":
+        score, largest = qu @ db.T, True
+    elif method == "l2":
+        score = (qu * qu).sum(1)[:, None] - 2.0 * (qu @ db.T) + (db * db).sum(1)[None, :]
+        largest = False
+    else:
+        raise NotImplementedError(f"Method: {method}")
+    order = torch.sort(-score if largest else score, dim=1, stable=True)[1][:, :k]
+    return torch.gather(score, 1, order), order
+
+
+def recalls_from_indices(indices, top_k_vals, gt_pos, use_percentage=True,
+                         sub_sample_db=1, sub_sample_qu=1):
+    """utilities.py:451-468."""
+    indices = np.asarray(indices)
+    recalls = dict(zip(top_k_vals, [0] * len(top_k_vals)))
+    for i_qu, qu_retr in enumerate(indices):
+        for i_rec in top_k_vals:
+            correct = gt_pos[i_qu * sub_sample_qu]
+            if np.any(np.isin(qu_retr[:i_rec] * sub_sample_db, correct)):
+                recalls[i_rec] += 1
+    if use_percentage:
+        for k in recalls:
+            recalls[k] /= len(indices)
+    return recalls
+
+
+def get_top_k_recall(top_k_vals, db, qu, gt_pos, method="cosine", norm_descs=True,
+                     use_percentage=True, sub_sample_db=1, sub_sample_qu=1):
+    dist, idx = top_k(db, qu, max(top_k_vals), method, norm_descs)
+    return dist, idx, recalls_from_indices(idx, top_k_vals, gt_pos, use_percentage,
+                                           sub_sample_db, sub_sample_qu)
+
+
+# ------------------------------------------------------------ synthetic data
+def clustered_features(n, d, k, seed=0, kappa_noise=0.35, centre_norm=0.8):
+    """K well separated lobes on the sphere (large assignment margins) + the
+    vocabulary that generated them (un-normalised centres, norm<1 like k-means
+    means of unit vectors)."""
+    g = torch.Generator().manual_seed(seed)
+    mu = F.normalize(torch.randn(k, d, generator=g), dim=1)
+    lab = torch.randint(0, k, (n,), generator=g)
+    x = F.normalize(mu[lab] + kappa_noise / d ** 0.5 * torch.randn(n, d, generator=g), dim=1)
+    centres = centre_norm * mu * (1.0 + 0.1 * torch.rand(k, 1, generator=g))
+    return x, centres, lab

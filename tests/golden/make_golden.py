@@ -1,0 +1,145 @@
+"""Generates the committed golden vectors under tests/golden/ by running the
+REFERENCE'S OWN CODE (/root/reference/utilities.py, imported verbatim through
+oracle/reference_import.py) on seeded inputs.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+Third-party arithmetic the reference does not vendor (dinov2 hub model,
+fast_pytorch_kmeans, faiss) is supplied by the restatements in oracle/ -- see
+oracle/__init__.py for what is and is not pinned.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import reference_import as ri           # noqa: E402
+from oracle import anyloc_oracle as ao              # noqa: E402
+from oracle import dinov2_restated as dr            # noqa: E402
+from oracle import fpk_restated as fpk              # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+ref = ri.load_reference_utilities()
+
+
+def ref_vlad(K, centers, **kw):
+    v = ref.VLAD(K, **kw)
+    v.kmeans = fpk.KMeans(K, mode=v.mode)
+    v.kmeans.centroids = centers
+    v.c_centers = centers
+    v.desc_dim = centers.shape[1]
+    return v
+
+
+def make_vlad():
+    cases = {}
+    g = torch.Generator().manual_seed(123)
+    specs = [
+        # name, N, D, K, kind, kwargs
+        ("clustered_n300_d64_k8", 300, 64, 8, "clustered", {}),
+        ("random_n257_d96_k5", 257, 96, 5, "random", {}),
+        ("random_n64_d32_k1", 64, 32, 1, "random", {}),
+        ("nointra_n100_d48_k4", 100, 48, 4, "clustered", {"intra_norm": False}),
+        ("nonorm_n100_d48_k4", 100, 48, 4, "random_unnorm", {"norm_descs": False}),
+        ("euclid_n120_d40_k6", 120, 40, 6, "random_unnorm", {"dist_mode": "euclidean"}),
+        ("emptyclusters_n10_d32_k16", 10, 32, 16, "clustered", {}),
+        ("ties_zero_n40_d32_k4", 40, 32, 4, "ties", {}),
+    ]
+    for name, N, D, K, kind, kw in specs:
+        if kind == "clustered":
+            x, c, _ = ao.clustered_features(N, D, K, seed=len(name))
+        elif kind == "random":
+            x = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=1)
+            c = 0.7 * torch.nn.functional.normalize(torch.randn(K, D, generator=g), dim=1)
+        elif kind == "random_unnorm":
+            x = torch.randn(N, D, generator=g) * (0.5 + torch.rand(N, 1, generator=g))
+            c = torch.randn(K, D, generator=g) * 0.8
+        elif kind == "ties":
+            x, c, _ = ao.clustered_features(N, D, K, seed=5)
+            c[2] = c[1]                      # duplicate centre -> exact tie, lowest index wins
+            x[3] = 0.0                       # all-zero descriptor -> label 0
+            x[7] = 0.0
+        v = ref_vlad(K, c, **kw)
+        out = v.generate(x)
+        labels = v.kmeans.predict(x)
+        cases[name] = dict(x=x.numpy(), centers=c.numpy(), out=out.numpy(),
+                           labels=labels.numpy().astype(np.int64),
+                           kw=np.array(repr(kw)))
+    # generate_multi on a batch and on a ragged list
+    x, c, _ = ao.clustered_features(4 * 50, 32, 6, seed=9)
+    v = ref_vlad(6, c)
+    xb = x.reshape(4, 50, 32)
+    cases["multi_b4_n50_d32_k6"] = dict(x=xb.numpy(), centers=c.numpy(),
+                                        out=v.generate_multi(xb).numpy(), kw=np.array("{}"))
+    flat = {}
+    for n, d in cases.items():
+        for k, a in d.items():
+            flat[f"{n}/{k}"] = a
+    np.savez_compressed(os.path.join(OUT, "vlad.npz"), **flat)
+    print("vlad.npz", len(cases), "cases")
+
+
+def make_fit():
+    # VLAD.fit (utilities.py:749-791) through the restated fpk KMeans; numpy RNG seeded as the
+    # reference does at import / in main (seed_everything -> np.random.seed(42)).
+    x, _, _ = ao.clustered_features(400, 24, 5, seed=3, kappa_noise=0.8)
+    np.random.seed(42)
+    v = ref.VLAD(5)
+    v.fit(x)
+    np.savez_compressed(os.path.join(OUT, "fit.npz"), x=x.numpy(), centers=v.c_centers.numpy())
+    print("fit.npz")
+
+
+def make_topk():
+    g = torch.Generator().manual_seed(7)
+    db = torch.randn(60, 80, generator=g)
+    qu = db[torch.randperm(60, generator=g)[:9]] + 0.3 * torch.randn(9, 80, generator=g)
+    db[11] = db[4]                                   # duplicate rows -> lowest index first
+    gt = np.empty(9, dtype=object)
+    for i in range(9):
+        gt[i] = np.array([(3 * i) % 60, (7 * i + 1) % 60])
+    out = {}
+    for method in ("cosine", "l2"):
+        d, i, r = ref.get_top_k_recall([1, 3, 5], db, qu, gt, method=method)
+        out[f"{method}/dist"], out[f"{method}/idx"] = d.numpy(), i.numpy()
+        out[f"{method}/recalls"] = np.array([r[k] for k in (1, 3, 5)])
+    d, i, r = ref.get_top_k_recall([2], db, qu[0], gt, method="cosine", norm_descs=False,
+                                   use_percentage=False)
+    out["single/dist"], out["single/idx"] = d.numpy(), i.numpy()
+    out["single/recalls"] = np.array([r[2]])
+    gt_obj = np.array([g_.tolist() for g_ in gt], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "topk.npz"), db=db.numpy(), qu=qu.numpy(), gt=gt_obj, **out)
+    print("topk.npz")
+
+
+def make_extract():
+    out = {}
+    cfgs = [
+        # tag, model, depth_override, layer, H, W
+        ("vits14_l9_56x70", "dinov2_vits14", None, 9, 56, 70),
+        ("vitg14_d2_l1_42x42", "dinov2_vitg14", 2, 1, 42, 42),
+    ]
+    for tag, name, depth, layer, H, W in cfgs:
+        factory = lambda n, depth=depth: dr.perturb(dr.build(n, seed=0, depth_override=depth), seed=1)
+        img = torch.randn(2, 3, H, W, generator=torch.Generator().manual_seed(1234))
+        out[f"{tag}/img"] = img.numpy()
+        for facet in ("value", "key", "query", "token"):
+            with ri.hub_patched(factory):
+                ext = ref.DinoV2ExtractFeatures(name, layer, facet, device="cpu")
+            feats = ext(img)
+            out[f"{tag}/{facet}"] = feats.numpy()
+        with ri.hub_patched(factory):
+            ext = ref.DinoV2ExtractFeatures(name, layer, "value", use_cls=True, norm_descs=False, device="cpu")
+        out[f"{tag}/value_cls_nonorm"] = ext(img).numpy()
+    np.savez_compressed(os.path.join(OUT, "extract.npz"), **out)
+    print("extract.npz")
+
+
+if __name__ == "__main__":
+    make_vlad()
+    make_fit()
+    make_topk()
+    make_extract()

@@ -1,0 +1,156 @@
+"""CPU tests: the oracle restatement against the committed golden vectors (generated from the
+reference's own code, tests/golden/make_golden.py), against the verbatim reference import when the
+reference tree is present, and the restated ViT against the independent HuggingFace port."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import anyloc_oracle as ao
+from oracle import dinov2_restated as dr
+from oracle import fpk_restated as fpk
+from oracle import reference_import as ri
+from tests.util import load_cases, case_kwargs
+
+
+@pytest.mark.parametrize("name", sorted(n for n in load_cases("vlad.npz") if not n.startswith("multi")))
+def test_vlad_oracle_matches_golden(name):
+    c = load_cases("vlad.npz")[name]
+    kw = case_kwargs(c)
+    out = ao.vlad_generate(torch.from_numpy(c["x"]), torch.from_numpy(c["centers"]), **kw)
+    lab = ao.vlad_labels(torch.from_numpy(c["x"]), torch.from_numpy(c["centers"]), kw.get("dist_mode", "cosine"))
+    assert torch.equal(lab, torch.from_numpy(c["labels"]))
+    assert torch.equal(out, torch.from_numpy(c["out"]))          # same ops, same order: bit-exact
+
+
+def test_vlad_multi_oracle_matches_golden():
+    c = load_cases("vlad.npz")["multi_b4_n50_d32_k6"]
+    out = ao.vlad_generate_multi(torch.from_numpy(c["x"]), torch.from_numpy(c["centers"]))
+    assert torch.equal(out, torch.from_numpy(c["out"]))
+
+
+def test_vlad_golden_properties():
+    c = load_cases("vlad.npz")["emptyclusters_n10_d32_k16"]
+    out = torch.from_numpy(c["out"]).reshape(16, 32)
+    used = sorted(set(c["labels"].tolist()))
+    for k in range(16):
+        if k in used:
+            assert abs(float(out[k].norm()) - 1 / len(used) ** 0.5) < 1e-6
+        else:
+            assert float(out[k].abs().max()) == 0.0          # utilities.py:840,854-855
+    t = load_cases("vlad.npz")["ties_zero_n40_d32_k4"]
+    assert 2 not in set(t["labels"].tolist())                # duplicate centre: lowest index wins
+    assert t["labels"][3] == 0 and t["labels"][7] == 0       # all-zero descriptor -> label 0
+
+
+def test_topk_oracle_matches_golden():
+    g = load_cases("topk.npz")
+    db, qu = torch.from_numpy(g[""]["db"]), torch.from_numpy(g[""]["qu"])
+    gt = np.empty(len(g[""]["gt"]), dtype=object)
+    for i, row in enumerate(g[""]["gt"]):
+        gt[i] = row
+    for method in ("cosine", "l2"):
+        d, i, r = ao.get_top_k_recall([1, 3, 5], db, qu, gt, method=method)
+        assert torch.equal(i, torch.from_numpy(g[method]["idx"]))
+        assert torch.equal(d, torch.from_numpy(g[method]["dist"]))
+        assert np.allclose([r[k] for k in (1, 3, 5)], g[method]["recalls"])
+    # duplicate DB rows 4 and 11: lowest index first
+    idx = g["cosine"]["idx"]
+    for row in idx:
+        row = row.tolist()
+        if 4 in row and 11 in row:
+            assert row.index(4) < row.index(11)
+    d, i, r = ao.get_top_k_recall([2], db, qu[0], gt, norm_descs=False, use_percentage=False)
+    assert torch.equal(i, torch.from_numpy(g["single"]["idx"]))
+    assert r[2] == g["single"]["recalls"][0]
+
+
+def test_fit_restated_matches_golden():
+    g = load_cases("fit.npz")[""]
+    x = torch.nn.functional.normalize(torch.from_numpy(g["x"]))
+    np.random.seed(42)
+    km = fpk.KMeans(5, mode="cosine")
+    km.fit(x)
+    assert torch.allclose(km.centroids, torch.from_numpy(g["centers"]), atol=0, rtol=0)
+
+
+@pytest.mark.parametrize("tag,name,depth,layer", [("vits14_l9_56x70", "dinov2_vits14", None, 9),
+                                                   ("vitg14_d2_l1_42x42", "dinov2_vitg14", 2, 1)])
+def test_extract_oracle_matches_golden(tag, name, depth, layer):
+    g = load_cases("extract.npz")[tag]
+    model = dr.perturb(dr.build(name, seed=0, depth_override=depth), seed=1)
+    img = torch.from_numpy(g["img"])
+    for facet in ("value", "key", "query", "token"):
+        out = ao.extract_features(model, img, layer, facet)
+        # early exit == full forward + hook: identical ops on the path that matters
+        assert torch.equal(out, torch.from_numpy(g[facet])), facet
+    out = ao.extract_features(model, img, layer, "value", use_cls=True, norm_descs=False)
+    assert torch.equal(out, torch.from_numpy(g["value_cls_nonorm"]))
+
+
+@pytest.mark.skipif(not ri.available(), reason="reference tree only exists in the build container")
+def test_oracle_matches_verbatim_reference():
+    ref = ri.load_reference_utilities()
+    g = torch.Generator().manual_seed(5)
+    for (N, D, K) in [(200, 64, 8), (529, 128, 32), (17, 32, 3)]:
+        x = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=1)
+        c = 0.6 * torch.randn(K, D, generator=g)
+        v = ref.VLAD(K)
+        v.kmeans = fpk.KMeans(K, mode="cosine"); v.kmeans.centroids = c; v.c_centers = c; v.desc_dim = D
+        assert torch.equal(v.generate(x), ao.vlad_generate(x, c))
+    db, qu = torch.randn(40, 64, generator=g), torch.randn(6, 64, generator=g)
+    gt = np.empty(6, dtype=object)
+    for i in range(6):
+        gt[i] = np.array([i, i + 1])
+    d, i, r = ref.get_top_k_recall([1, 4], db, qu, gt)
+    d2, i2, r2 = ao.get_top_k_recall([1, 4], db, qu, gt)
+    assert torch.equal(i, i2) and torch.equal(d, d2) and r == r2
+
+
+def _hf_model_from(model, name, H, W, depth):
+    from transformers import Dinov2Config, Dinov2Model
+    dim, _, heads, ffn = dr.ARCHS[name]
+    cfg = Dinov2Config(hidden_size=dim, num_hidden_layers=depth, num_attention_heads=heads, mlp_ratio=4,
+                       image_size=H, patch_size=14, use_swiglu_ffn=(ffn != "mlp"), layer_norm_eps=1e-6,
+                       hidden_act="gelu", qkv_bias=True, layerscale_value=1.0,
+                       attn_implementation="eager")
+    hf = Dinov2Model(cfg).eval()
+    sd = {k: v for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        e = hf.embeddings
+        e.cls_token.copy_(sd["cls_token"])
+        x = torch.zeros(1, 1 + (H // 14) * (W // 14), dim)
+        e.position_embeddings.copy_(model.interpolate_pos_encoding(x, H, W))
+        e.patch_embeddings.projection.weight.copy_(sd["patch_embed.proj.weight"])
+        e.patch_embeddings.projection.bias.copy_(sd["patch_embed.proj.bias"])
+        for i, layer in enumerate(hf.encoder.layer):
+            p = f"blocks.{i}."
+            layer.norm1.weight.copy_(sd[p + "norm1.weight"]); layer.norm1.bias.copy_(sd[p + "norm1.bias"])
+            layer.norm2.weight.copy_(sd[p + "norm2.weight"]); layer.norm2.bias.copy_(sd[p + "norm2.bias"])
+            w, b = sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"]
+            att = layer.attention.attention
+            for j, lin in enumerate((att.query, att.key, att.value)):
+                lin.weight.copy_(w[j * dim:(j + 1) * dim]); lin.bias.copy_(b[j * dim:(j + 1) * dim])
+            layer.attention.output.dense.weight.copy_(sd[p + "attn.proj.weight"])
+            layer.attention.output.dense.bias.copy_(sd[p + "attn.proj.bias"])
+            layer.layer_scale1.lambda1.copy_(sd[p + "ls1.gamma"])
+            layer.layer_scale2.lambda1.copy_(sd[p + "ls2.gamma"])
+            if ffn == "mlp":
+                layer.mlp.fc1.weight.copy_(sd[p + "mlp.fc1.weight"]); layer.mlp.fc1.bias.copy_(sd[p + "mlp.fc1.bias"])
+                layer.mlp.fc2.weight.copy_(sd[p + "mlp.fc2.weight"]); layer.mlp.fc2.bias.copy_(sd[p + "mlp.fc2.bias"])
+            else:
+                layer.mlp.weights_in.weight.copy_(sd[p + "mlp.w12.weight"]); layer.mlp.weights_in.bias.copy_(sd[p + "mlp.w12.bias"])
+                layer.mlp.weights_out.weight.copy_(sd[p + "mlp.w3.weight"]); layer.mlp.weights_out.bias.copy_(sd[p + "mlp.w3.bias"])
+    return hf
+
+
+@pytest.mark.parametrize("name,depth", [("dinov2_vits14", 3), ("dinov2_vitg14", 2)])
+def test_restated_vit_matches_hf_port(name, depth):
+    """Independent pin of the block arithmetic: HuggingFace's Dinov2Model with remapped weights."""
+    H = W = 56
+    model = dr.perturb(dr.build(name, seed=0, depth_override=depth), seed=1)
+    hf = _hf_model_from(model, name, H, W, depth)
+    img = torch.randn(2, 3, H, W, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        hs = hf(pixel_values=img, output_hidden_states=True).hidden_states   # [emb, blk0, blk1, ...]
+    tok = ao.extract_features(model, img, depth - 1, "token", use_cls=True, norm_descs=False)
+    assert torch.allclose(tok, hs[depth], atol=2e-5, rtol=1e-5)
