@@ -1,0 +1,92 @@
+"""GPU parity of the extractor (anyloc_vit_extract via DinoV2ExtractFeatures) against golden
+features produced by the REFERENCE'S OWN DinoV2ExtractFeatures (utilities.py:223-285, run verbatim
+over the restated hub model, tests/golden/make_golden.py) and against the oracle on more shapes.
+Tolerance 1e-4 relative (north_star); measured error is reported by the assert message."""
+import pytest
+import torch
+
+from oracle import anyloc_oracle as ao
+from oracle import dinov2_restated as dr
+from tests.util import load_cases, rel_inf
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+ENGINES = ["simt", "auto"]
+
+
+@pytest.fixture(scope="module")
+def u(cuda):
+    from anyloc_b200 import utilities
+    return utilities
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("tag,name,depth,layer", [("vits14_l9_56x70", "dinov2_vits14", None, 9),
+                                                   ("vitg14_d2_l1_42x42", "dinov2_vitg14", 2, 1)])
+def test_extract_golden(u, engine, tag, name, depth, layer):
+    g = load_cases("extract.npz")[tag]
+    sd = dr.perturb(dr.build(name, seed=0, depth_override=depth), seed=1).state_dict()
+    img = torch.from_numpy(g["img"]).cuda()
+    for facet in ("value", "key", "query", "token"):
+        ext = u.DinoV2ExtractFeatures(name, layer, facet, device="cuda", weights=sd, gemm_engine=engine)
+        out = ext(img)
+        assert out.is_cuda and out.shape == g[facet].shape
+        err = rel_inf(out.cpu(), g[facet])
+        assert err < TOL, (facet, err)
+    ext = u.DinoV2ExtractFeatures(name, layer, "value", use_cls=True, norm_descs=False, device="cuda", weights=sd,
+                                  gemm_engine=engine)
+    err = rel_inf(ext(img).cpu(), g["value_cls_nonorm"])
+    assert err < TOL, err
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name,depth,layer,H,W,B", [("dinov2_vits14", 4, 3, 224, 224, 3),
+                                                    ("dinov2_vitb14", 2, 1, 98, 154, 2),
+                                                    ("dinov2_vitl14", 3, 2, 518, 518, 1),
+                                                    ("dinov2_vitg14", 3, 2, 322, 322, 2)])
+def test_extract_vs_oracle(u, engine, name, depth, layer, H, W, B):
+    model = dr.perturb(dr.build(name, seed=0, depth_override=depth), seed=2)
+    img = torch.randn(B, 3, H, W, generator=torch.Generator().manual_seed(1234))
+    for facet in ("value", "token"):
+        ref = ao.extract_features(model, img, layer, facet)
+        ext = u.DinoV2ExtractFeatures(name, layer, facet, device="cuda", weights=model.state_dict(),
+                                      gemm_engine=engine)
+        out = ext(img.cuda())
+        err = rel_inf(out.cpu(), ref)
+        assert err < TOL, (name, facet, err)
+    with pytest.raises(ValueError):
+        ext(torch.randn(1, 3, 225, 224, device="cuda"))
+
+
+def test_extractor_errors(u):
+    with pytest.raises(Exception):
+        u.DinoV2ExtractFeatures("dinov2_vits14", 3, "value", device="cpu")       # CUDA only, loud
+    with pytest.raises(ValueError):
+        u.DinoV2ExtractFeatures("dinov2_vits14", 3, "values", device="cuda",
+                                weights=dr.build("dinov2_vits14", depth_override=4).state_dict())
+
+
+def test_pipeline_c1_end_to_end(u):
+    """BASELINE config 1 (ViT-S/14 layer-9 value, 16x224x224, K=8) end to end on the GPU vs the
+    CPU oracle: extractor -> VLAD.fit vocabulary from the oracle -> descriptors -> top-k."""
+    import numpy as np
+    from oracle import fpk_restated as fpk
+    model = dr.build("dinov2_vits14", seed=0, depth_override=10)
+    img = torch.randn(16, 3, 224, 224, generator=torch.Generator().manual_seed(1234))
+    feats_ref = ao.extract_features(model, img, 9, "value")
+    ext = u.DinoV2ExtractFeatures("dinov2_vits14", 9, "value", device="cuda", weights=model.state_dict())
+    feats = ext(img.cuda())
+    assert rel_inf(feats.cpu(), feats_ref) < TOL
+    np.random.seed(42)
+    km = fpk.KMeans(8, mode="cosine"); km.fit(feats_ref.reshape(-1, 384))
+    v = u.VLAD(8); v.kmeans = u._KMeans(8, mode="cosine"); v.kmeans.centroids = km.centroids
+    v.c_centers = km.centroids; v.desc_dim = 384
+    vl = v.generate_multi(feats)
+    lab = torch.stack([v.kmeans.predict(f) for f in feats])
+    ref = torch.stack([ao.vlad_generate(f, km.centroids, labels=l.cpu()) for f, l in zip(feats_ref, lab)])
+    assert rel_inf(vl.cpu(), ref) < 5e-4      # features differ by ~1e-5; residual sums amplify
+    gt = np.empty(4, dtype=object)
+    for i in range(4):
+        gt[i] = np.array([i])
+    d, i, r = u.get_top_k_recall([1, 2], vl[:12].cpu(), vl[:4].cpu() + 0.01 * vl[12:16].cpu(), gt)
+    assert r[1] == 1.0 and i[:, 0].tolist() == [0, 1, 2, 3]
