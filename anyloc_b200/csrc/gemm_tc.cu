@@ -1,11 +1,371 @@
-// placeholder until the tcgen05 engine lands (next commit): reports "unsupported" so AUTO picks SIMT.
+// tcgen05 GEMM engine:  C[M,N] = (A_hi+A_lo)[M,K] . (B_hi+B_lo)[N,K]^T  + fused epilogue,
+// fp32-equivalent accuracy through the 3-term tf32 split
+//      A.B ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo        (all accumulated in fp32 in TMEM)
+// where x_hi = rna_tf32(x), x_lo = x - x_hi are materialised by the producer kernels
+// (LayerNorm / previous epilogue / weight prep), so the tensor core consumes plain fp32 words.
+//
+// Structure (one persistent CTA per SM, 256 threads):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor 2D, 128B-swizzled K-major boxes of 32 floats
+//   warp 1   : MMA issuer    -- one lane issues tcgen05.mma.cta_group::1.kind::tf32 (M128 x BN x K8)
+//   warp 2   : TMEM allocator (2 x BN fp32 columns: double-buffered accumulator)
+//   warps 4-7: epilogue      -- tcgen05.ld 32x32b, bias / GELU / SwiGLU / LayerScale+residual /
+//                               tf32 split, vectorised global stores; overlaps the next tile's MMAs
+// Tiles are rastered n-fastest so that the CTAs resident at any moment share a handful of A row
+// panels and the whole B matrix in L2.
+#include <cuda.h>
 #include "epilogue.cuh"
+
 namespace anyloc {
-bool gemm_tc_supported(const float*, const float*, int, const float*, const float*, int, int, int, int,
-                       const EpiParams&) { return false; }
-int gemm_tc_launch(const float*, const float*, int, const float*, const float*, int, int, int, int,
-                   const EpiParams&, cudaStream_t) {
-  set_error("tcgen05 GEMM engine not built");
-  return ANYLOC_ERR_UNSUPPORTED;
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                    // floats per k-block = 128 B = one swizzle span
+constexpr int UMMA_K = 8;                 // tf32: 32 bytes per instruction
+constexpr int A_BYTES = BM * BK * 4;      // 16 KB
+
+template <int BN> struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 2 : 3;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN;          // 512 or 256: power of two
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0; !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done && (it & 0xfffff) == 0xfffff) {          // watchdog: never hang the GPU
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B swizzle: 8-row x 128 B atoms, 1024 B apart (SBO); LBO unused (1); version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- epilogue on a 32-column chunk held by one thread (row m, columns n..n+31)
+__device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, int N, const float* v) {
+  const bool vec = (n + 32 <= N) && ((ep.ldo & 3) == 0);
+  if (!vec) {
+    if (ep.mode == ANYLOC_EPI_SWIGLU_SPLIT) {
+      for (int j = 0; j < 32; j += 2) if (n + j + 1 < N) epi_store_pair(ep, m, n + j, v[j], v[j + 1]);
+    } else {
+      for (int j = 0; j < 32; ++j) if (n + j < N) epi_store1(ep, m, n + j, v[j]);
+    }
+    return;
+  }
+  float b[32];
+  if (ep.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(ep.bias + n + j));
+      b[j] = t.x; b[j + 1] = t.y; b[j + 2] = t.z; b[j + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) b[j] = 0.f;
+  }
+  if (ep.mode == ANYLOC_EPI_SWIGLU_SPLIT) {
+    float4* oh = reinterpret_cast<float4*>(ep.out + (size_t)m * ep.ldo + (n >> 1));
+    float4* ol = reinterpret_cast<float4*>(ep.out_lo + (size_t)m * ep.ldo + (n >> 1));
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      float h[4], l[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float x1 = v[j + 2 * q] + b[j + 2 * q], x2 = v[j + 2 * q + 1] + b[j + 2 * q + 1];
+        split_tf32(silu(x1) * x2, h[q], l[q]);
+      }
+      oh[j >> 3] = make_float4(h[0], h[1], h[2], h[3]);
+      ol[j >> 3] = make_float4(l[0], l[1], l[2], l[3]);
+    }
+    return;
+  }
+  const size_t o = (size_t)m * ep.ldo + n;
+  if (ep.mode == ANYLOC_EPI_BIAS) {
+    float4* op = reinterpret_cast<float4*>(ep.out + o);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      op[j >> 2] = make_float4(v[j] + b[j], v[j + 1] + b[j + 1], v[j + 2] + b[j + 2], v[j + 3] + b[j + 3]);
+  } else if (ep.mode == ANYLOC_EPI_LS_RESID) {
+    const float4* rp = reinterpret_cast<const float4*>(ep.resid + o);
+    float4* op = reinterpret_cast<float4*>(ep.out + o);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 r = rp[j >> 2];
+      float4 g = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + j));
+      op[j >> 2] = make_float4(r.x + g.x * (v[j] + b[j]), r.y + g.y * (v[j + 1] + b[j + 1]),
+                               r.z + g.z * (v[j + 2] + b[j + 2]), r.w + g.w * (v[j + 3] + b[j + 3]));
+    }
+  } else {   // BIAS_SPLIT / GELU_SPLIT
+    float4* oh = reinterpret_cast<float4*>(ep.out + o);
+    float4* ol = reinterpret_cast<float4*>(ep.out_lo + o);
+    const bool gelu = ep.mode == ANYLOC_EPI_GELU_SPLIT;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float h[4], l[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float x = v[j + q] + b[j + q];
+        if (gelu) x = gelu_erf(x);
+        split_tf32(x, h[q], l[q]);
+      }
+      oh[j >> 2] = make_float4(h[0], h[1], h[2], h[3]);
+      ol[j >> 2] = make_float4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                int M, int N, int K, int has_a_lo, int has_b_lo, EpiParams ep) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* bar_area = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_area);          // [STAGES]
+  uint64_t* empty_bar = full_bar + C::STAGES;                           // [STAGES]
+  uint64_t* tfull_bar = empty_bar + C::STAGES;                          // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_hi) : "memory");
+    if (has_a_lo) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_lo) : "memory");
+    if (has_b_lo) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_lo) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------ TMA producer
+      const uint32_t tx_bytes = A_BYTES * (1 + (has_a_lo ? 1 : 0)) + C::B_BYTES * (1 + (has_b_lo ? 1 : 0));
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+          const uint32_t fb = smem_u32(full_bar + stage);
+          mbar_expect_tx(fb, tx_bytes);
+          const uint32_t sbase = smem_u32(smem + stage * C::STAGE_BYTES);
+          tma_load_2d(sbase, &tm_a_hi, fb, kb * BK, m0);
+          if (has_a_lo) tma_load_2d(sbase + A_BYTES, &tm_a_lo, fb, kb * BK, m0);
+          tma_load_2d(sbase + 2 * A_BYTES, &tm_b_hi, fb, kb * BK, n0);
+          if (has_b_lo) tma_load_2d(sbase + 2 * A_BYTES + C::B_BYTES, &tm_b_lo, fb, kb * BK, n0);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)(BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(smem_u32(full_bar + stage), phase);
+          tc_fence_after();
+          const uint32_t sbase = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint64_t a_hi = make_desc(sbase), a_lo = make_desc(sbase + A_BYTES);
+          const uint64_t b_hi = make_desc(sbase + 2 * A_BYTES), b_lo = make_desc(sbase + 2 * A_BYTES + C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);      // +32 B per k-step inside the atom
+            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+            if (has_a_lo) umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+            if (has_b_lo) umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+          }
+          umma_commit(smem_u32(empty_bar + stage));      // frees the smem stage when these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(tfull_bar + acc));          // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // -------------------------------------------------- epilogue (4 warps; warp%4 selects the TMEM lane quarter)
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+      mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+      tc_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (n0 + c * 32 >= N) break;                   // warp-uniform
+        float v[32];
+        tmem_ld32(trow + (uint32_t)(c * 32), v);
+        if (m < M) epi_chunk32(ep, m, n0 + c * 32, N, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("gemm_tc: cuTensorMapEncodeTiled unavailable"); return ANYLOC_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d", (int)r, rows, K, ld); return ANYLOC_ERR_CUDA; }
+  return ANYLOC_OK;
+}
+
+}  // namespace tc
+
+bool gemm_tc_supported(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo,
+                       int ldb, int M, int N, int K, const EpiParams& ep) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (M < 1 || N < 1 || K < 4) return false;
+  if ((K & 3) || (lda & 3) || (ldb & 3)) return false;
+  if (!al16(a_hi) || !al16(b_hi) || (a_lo && !al16(a_lo)) || (b_lo && !al16(b_lo))) return false;
+  if (!al16(ep.out) || (ep.out_lo && !al16(ep.out_lo)) || (ep.resid && !al16(ep.resid))) return false;
+  if (ep.bias && !al16(ep.bias)) return false;
+  if (ep.gamma && !al16(ep.gamma)) return false;
+  return true;
+}
+
+int gemm_tc_launch(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb,
+                   int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+  using namespace tc;
+  constexpr int BN = 256;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_map(&ma_hi, a_hi, M, K, lda, BM))) return rc;
+  if ((rc = make_map(&ma_lo, a_lo ? a_lo : a_hi, M, K, lda, BM))) return rc;
+  if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, BN))) return rc;
+  if ((rc = make_map(&mb_lo, b_lo ? b_lo : b_hi, N, K, ldb, BN))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg<BN>::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = cdiv(M, BM) * cdiv(N, BN);
+  const int grid = std::min(tiles, device_sm_count());
+  gemm_tc3_kernel<BN><<<grid, 256, Cfg<BN>::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K, a_lo != nullptr,
+                                                             b_lo != nullptr, ep);
+  ANYLOC_CHECK_LAUNCH();
+  return ANYLOC_OK;
+}
+
 }  // namespace anyloc
