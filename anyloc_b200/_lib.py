@@ -43,6 +43,9 @@ class VitWeightsStruct(C.Structure):
 _SIGS = {
     "anyloc_last_error": (C.c_char_p, []),
     "anyloc_version": (C.c_int, []),
+    "anyloc_launch_count": (C.c_longlong, []),
+    "anyloc_profile_enable": (C.c_int, [C.c_int]),
+    "anyloc_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
     "anyloc_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "anyloc_vlad_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "anyloc_vlad_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 7 +
@@ -143,3 +146,21 @@ class _WorkspacePool:
 
 
 workspaces = _WorkspacePool()
+
+PROF_CATEGORIES = ["gemm_tc", "gemm_simt", "attention", "layernorm", "vit_misc", "vlad", "topk"]
+
+
+def profile_enable(on=True):
+    check(load().anyloc_profile_enable(int(bool(on))), "profile_enable")
+
+
+def profile_read():
+    """-> {category: (device_ms, launch_groups, algorithmic_work)} since the last read."""
+    n = len(PROF_CATEGORIES)
+    ms, groups, work = (C.c_double * n)(), (C.c_longlong * n)(), (C.c_double * n)()
+    check(load().anyloc_profile_read(ms, groups, work), "profile_read")
+    return {c: (ms[i], groups[i], work[i]) for i, c in enumerate(PROF_CATEGORIES)}
+
+
+def launch_count():
+    return int(load().anyloc_launch_count())

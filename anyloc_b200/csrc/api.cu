@@ -3,6 +3,8 @@
 // /root/reference/utilities.py:245-252,263-285 + upstream DinoVisionTransformer).
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
+#include <vector>
 #include "epilogue.cuh"
 
 namespace anyloc {
@@ -11,6 +13,28 @@ static thread_local char g_err[1024] = "";
 void set_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+namespace {
+struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+size_t g_prof_used = 0;
+}  // namespace
+ProfScope::ProfScope(int cat, cudaStream_t stream, double work) : slot(-1), st(stream) {
+  if (!g_prof_on) return;
+  if (g_prof_used == g_prof.size()) {
+    ProfRec r{};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    g_prof.push_back(r);
+  }
+  slot = (int)g_prof_used++;
+  g_prof[slot].cat = cat; g_prof[slot].work = work;
+  cudaEventRecord(g_prof[slot].a, st);
+}
+ProfScope::~ProfScope() { if (slot >= 0) cudaEventRecord(g_prof[slot].b, st); }
 
 int device_sm_count() {
   static int cached = -1;
@@ -49,8 +73,12 @@ static int gemm_dispatch(const float* a_hi, const float* a_lo, int lda, const fl
               M, N, K, lda, ldb);
     return ANYLOC_ERR_UNSUPPORTED;
   }
-  if (engine == ANYLOC_GEMM_TC3 || (engine == ANYLOC_GEMM_AUTO && tc_ok))
+  const double flops = 2.0 * M * N * K;
+  if (engine == ANYLOC_GEMM_TC3 || (engine == ANYLOC_GEMM_AUTO && tc_ok && M >= 32)) {
+    ProfScope ps(PC_GEMM_TC, st, flops);
     return gemm_tc_launch(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st);
+  }
+  ProfScope ps(PC_GEMM_SIMT, st, flops);
   return gemm_simt_launch(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st);
 }
 
@@ -60,6 +88,20 @@ using namespace anyloc;
 
 extern "C" const char* anyloc_last_error(void) { return g_err; }
 extern "C" int anyloc_version(void) { return 100; }
+extern "C" long long anyloc_launch_count(void) { return g_launches.load(); }
+extern "C" int anyloc_profile_enable(int on) { g_prof_on = on != 0; g_prof_used = 0; return ANYLOC_OK; }
+extern "C" int anyloc_profile_read(double* ms, long long* groups, double* work) {
+  ANYLOC_REQUIRE(ms && groups && work, "profile_read: null pointer");
+  for (int c = 0; c < PC_COUNT; ++c) { ms[c] = 0.0; groups[c] = 0; work[c] = 0.0; }
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    float t = 0.f;
+    ANYLOC_CHECK_CUDA(cudaEventSynchronize(g_prof[i].b));
+    ANYLOC_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b));
+    ms[g_prof[i].cat] += t; groups[g_prof[i].cat] += 1; work[g_prof[i].cat] += g_prof[i].work;
+  }
+  g_prof_used = 0;
+  return ANYLOC_OK;
+}
 
 extern "C" int anyloc_device_info(int* sm_count, size_t* smem_optin_bytes) {
   int n = 0;
@@ -151,13 +193,17 @@ static int vit_block(const AnylocVitCfg* c, const AnylocVitBlock& wb, const VitB
                      int engine, cudaStream_t st) {
   const int D = c->embed_dim, M = B * T, Hf = c->ffn_hidden;
   int rc;
-  if ((rc = launch_layernorm(bf.x, wb.ln1_w, wb.ln1_b, M, D, 1e-6f, bf.y_hi, bf.y_lo, st))) return rc;
+  const double ln_bytes = 12.0 * M * D;
+  { ProfScope ps(PC_LAYERNORM, st, ln_bytes);
+    if ((rc = launch_layernorm(bf.x, wb.ln1_w, wb.ln1_b, M, D, 1e-6f, bf.y_hi, bf.y_lo, st))) return rc; }
   EpiParams e_qkv{ANYLOC_EPI_BIAS, wb.qkv_b, nullptr, nullptr, bf.qkv, nullptr, 3 * D};
   if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.qkv_w_hi, wb.qkv_w_lo, D, M, 3 * D, D, e_qkv, engine, st))) return rc;
-  if ((rc = attention_launch(bf.qkv, B, T, D, c->num_heads, bf.y_hi, bf.y_lo, st))) return rc;
+  { ProfScope ps(PC_ATTENTION, st, 4.0 * B * (double)T * T * D);
+    if ((rc = attention_launch(bf.qkv, B, T, D, c->num_heads, bf.y_hi, bf.y_lo, st))) return rc; }
   EpiParams e_proj{ANYLOC_EPI_LS_RESID, wb.proj_b, wb.ls1, bf.x, bf.x, nullptr, D};
   if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.proj_w_hi, wb.proj_w_lo, D, M, D, D, e_proj, engine, st))) return rc;
-  if ((rc = launch_layernorm(bf.x, wb.ln2_w, wb.ln2_b, M, D, 1e-6f, bf.y_hi, bf.y_lo, st))) return rc;
+  { ProfScope ps(PC_LAYERNORM, st, ln_bytes);
+    if ((rc = launch_layernorm(bf.x, wb.ln2_w, wb.ln2_b, M, D, 1e-6f, bf.y_hi, bf.y_lo, st))) return rc; }
   if (c->ffn_kind == ANYLOC_FFN_MLP) {
     EpiParams e_in{ANYLOC_EPI_GELU_SPLIT, wb.in_b, nullptr, nullptr, bf.h_hi, bf.h_lo, Hf};
     if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.in_w_hi, wb.in_w_lo, D, M, Hf, D, e_in, engine, st))) return rc;

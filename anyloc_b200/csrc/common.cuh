@@ -20,7 +20,11 @@ void set_error(const char* fmt, ...);
     }                                                                                  \
   } while (0)
 
-#define ANYLOC_CHECK_LAUNCH() ANYLOC_CHECK_CUDA(cudaGetLastError())
+#define ANYLOC_CHECK_LAUNCH()                                                          \
+  do {                                                                                 \
+    anyloc::count_launch();                                                            \
+    ANYLOC_CHECK_CUDA(cudaGetLastError());                                             \
+  } while (0)
 
 #define ANYLOC_REQUIRE(cond, ...)                                                      \
   do {                                                                                 \
@@ -65,5 +69,14 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 }
 
 int device_sm_count();
+void count_launch();
+
+// Optional per-category device timing (cudaEvents on the launching stream), see anyloc_profile_*.
+enum ProfCat { PC_GEMM_TC = 0, PC_GEMM_SIMT, PC_ATTENTION, PC_LAYERNORM, PC_VIT_MISC, PC_VLAD, PC_TOPK, PC_COUNT };
+struct ProfScope {
+  int slot; cudaStream_t st;
+  ProfScope(int cat, cudaStream_t stream, double work);
+  ~ProfScope();
+};
 
 }  // namespace anyloc

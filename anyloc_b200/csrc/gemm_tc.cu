@@ -7,9 +7,16 @@
 // Structure (one persistent CTA per SM, 256 threads):
 //   warp 0   : TMA producer  -- cp.async.bulk.tensor 2D, 128B-swizzled K-major boxes of 32 floats
 //   warp 1   : MMA issuer    -- one lane issues tcgen05.mma.cta_group::1.kind::tf32 (M128 x BN x K8)
-//   warp 2   : TMEM allocator (2 x BN fp32 columns: double-buffered accumulator)
-//   warps 4-7: epilogue      -- tcgen05.ld 32x32b, bias / GELU / SwiGLU / LayerScale+residual /
-//                               tf32 split, vectorised global stores; overlaps the next tile's MMAs
+//   warp 2   : TMEM allocator (2 x BN fp32 columns: double-buffered CHUNK accumulator)
+//   warps 4-19: accumulate + epilogue -- the tensor core adds into its fp32 accumulator with
+//               round-toward-zero, a bias of ~2^-26 per MMA that grows linearly with K (measured:
+//               -9e-6 relative at K=1536, -1e-4 at K=16384).  So the MMA warp only accumulates
+//               CHUNK_KB k-blocks (K=64) in TMEM; these warps drain every chunk with tcgen05.ld and
+//               add it to round-to-nearest fp32 register accumulators (the whole 128xBN tile lives
+//               in registers: 64 columns of one row per thread), which brings the error back to
+//               the level of an fp32 FFMA GEMM.  After the last chunk: bias / GELU / SwiGLU /
+//               LayerScale+residual / tf32 split and vectorised global stores, overlapping the next
+//               tile's MMAs.
 // Tiles are rastered n-fastest so that the CTAs resident at any moment share a handful of A row
 // panels and the whole B matrix in L2.
 #include <cuda.h>
@@ -31,6 +38,9 @@ template <int BN> struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;          // 512 or 256: power of two
 };
+constexpr int CHUNK_KB = 2;               // k-blocks accumulated inside the tensor core before an RN drain
+constexpr int EPI_WARPS = 16;             // 4 TMEM lane quarters x 4 column quarters
+constexpr int THREADS = 128 + EPI_WARPS * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -52,10 +62,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (!done && (it & 0xfffff) == 0xfffff) {          // watchdog: never hang the GPU
-      long long now = clock64();
+    if (!done && (it & 0x3ff) == 0x3ff) {              // watchdog: never hang the GPU (try_wait itself
+      long long now = clock64();                        // suspends for a HW-bounded time per call)
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 20000000000LL) __trap();
+      else if (now - t0 > 8000000000LL) __trap();      // ~4 s
     }
   }
 }
@@ -101,81 +111,71 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// ---- epilogue on a 32-column chunk held by one thread (row m, columns n..n+31)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- epilogue on 32 consecutive columns of one row (row m, columns n..n+31), values in v[]
 __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, int N, const float* v) {
   const bool vec = (n + 32 <= N) && ((ep.ldo & 3) == 0);
   if (!vec) {
     if (ep.mode == ANYLOC_EPI_SWIGLU_SPLIT) {
+#pragma unroll
       for (int j = 0; j < 32; j += 2) if (n + j + 1 < N) epi_store_pair(ep, m, n + j, v[j], v[j + 1]);
     } else {
+#pragma unroll
       for (int j = 0; j < 32; ++j) if (n + j < N) epi_store1(ep, m, n + j, v[j]);
     }
     return;
   }
-  float b[32];
-  if (ep.bias) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      float4 t = __ldg(reinterpret_cast<const float4*>(ep.bias + n + j));
-      b[j] = t.x; b[j + 1] = t.y; b[j + 2] = t.z; b[j + 3] = t.w;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) b[j] = 0.f;
-  }
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (ep.mode == ANYLOC_EPI_SWIGLU_SPLIT) {
     float4* oh = reinterpret_cast<float4*>(ep.out + (size_t)m * ep.ldo + (n >> 1));
     float4* ol = reinterpret_cast<float4*>(ep.out_lo + (size_t)m * ep.ldo + (n >> 1));
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
-      float h[4], l[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float x1 = v[j + 2 * q] + b[j + 2 * q], x2 = v[j + 2 * q + 1] + b[j + 2 * q + 1];
-        split_tf32(silu(x1) * x2, h[q], l[q]);
-      }
-      oh[j >> 3] = make_float4(h[0], h[1], h[2], h[3]);
-      ol[j >> 3] = make_float4(l[0], l[1], l[2], l[3]);
+      float4 b0 = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n + j)) : zero4;
+      float4 b1 = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n + j + 4)) : zero4;
+      float4 h, l;
+      split_tf32(silu(v[j] + b0.x) * (v[j + 1] + b0.y), h.x, l.x);
+      split_tf32(silu(v[j + 2] + b0.z) * (v[j + 3] + b0.w), h.y, l.y);
+      split_tf32(silu(v[j + 4] + b1.x) * (v[j + 5] + b1.y), h.z, l.z);
+      split_tf32(silu(v[j + 6] + b1.z) * (v[j + 7] + b1.w), h.w, l.w);
+      oh[j >> 3] = h; ol[j >> 3] = l;
     }
     return;
   }
   const size_t o = (size_t)m * ep.ldo + n;
-  if (ep.mode == ANYLOC_EPI_BIAS) {
-    float4* op = reinterpret_cast<float4*>(ep.out + o);
 #pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      op[j >> 2] = make_float4(v[j] + b[j], v[j + 1] + b[j + 1], v[j + 2] + b[j + 2], v[j + 3] + b[j + 3]);
-  } else if (ep.mode == ANYLOC_EPI_LS_RESID) {
-    const float4* rp = reinterpret_cast<const float4*>(ep.resid + o);
-    float4* op = reinterpret_cast<float4*>(ep.out + o);
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      float4 r = rp[j >> 2];
+  for (int j = 0; j < 32; j += 4) {
+    float4 b = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n + j)) : zero4;
+    float4 x = make_float4(v[j] + b.x, v[j + 1] + b.y, v[j + 2] + b.z, v[j + 3] + b.w);
+    if (ep.mode == ANYLOC_EPI_BIAS) {
+      reinterpret_cast<float4*>(ep.out + o)[j >> 2] = x;
+    } else if (ep.mode == ANYLOC_EPI_LS_RESID) {
+      float4 r = reinterpret_cast<const float4*>(ep.resid + o)[j >> 2];
       float4 g = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + j));
-      op[j >> 2] = make_float4(r.x + g.x * (v[j] + b[j]), r.y + g.y * (v[j + 1] + b[j + 1]),
-                               r.z + g.z * (v[j + 2] + b[j + 2]), r.w + g.w * (v[j + 3] + b[j + 3]));
-    }
-  } else {   // BIAS_SPLIT / GELU_SPLIT
-    float4* oh = reinterpret_cast<float4*>(ep.out + o);
-    float4* ol = reinterpret_cast<float4*>(ep.out_lo + o);
-    const bool gelu = ep.mode == ANYLOC_EPI_GELU_SPLIT;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      float h[4], l[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float x = v[j + q] + b[j + q];
-        if (gelu) x = gelu_erf(x);
-        split_tf32(x, h[q], l[q]);
-      }
-      oh[j >> 2] = make_float4(h[0], h[1], h[2], h[3]);
-      ol[j >> 2] = make_float4(l[0], l[1], l[2], l[3]);
+      reinterpret_cast<float4*>(ep.out + o)[j >> 2] =
+          make_float4(r.x + g.x * x.x, r.y + g.y * x.y, r.z + g.z * x.z, r.w + g.w * x.w);
+    } else {   // BIAS_SPLIT / GELU_SPLIT
+      if (ep.mode == ANYLOC_EPI_GELU_SPLIT) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+      float4 h, l;
+      split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+      reinterpret_cast<float4*>(ep.out + o)[j >> 2] = h;
+      reinterpret_cast<float4*>(ep.out_lo + o)[j >> 2] = l;
     }
   }
 }
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(THREADS, 1)
 gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                 int M, int N, int K, int has_a_lo, int has_b_lo, EpiParams ep) {
@@ -194,6 +194,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_k = (K + BK - 1) / BK;
+  const int num_chunks = (num_k + CHUNK_KB - 1) / CHUNK_KB;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_hi) : "memory");
@@ -203,7 +204,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -216,8 +217,11 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-  if (warp == 0) {
-    if (lane == 0) {
+  // Register re-balancing inside the CTA's launch-time pool (640 x 96 = 61440):
+  // 128 x 40 + 512 x 104 = 58368 <= 61440, so the blocking setmaxnreg.inc can always be satisfied.
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0 && lane == 0) {
       // ------------------------------------------------ TMA producer
       const uint32_t tx_bytes = A_BYTES * (1 + (has_a_lo ? 1 : 0)) + C::B_BYTES * (1 + (has_b_lo ? 1 : 0));
       int stage = 0; uint32_t phase = 0;
@@ -235,19 +239,20 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
+    } else if (warp == 1 && lane == 0) {
       // ------------------------------------------------ MMA issuer
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                  ((uint32_t)(BM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < num_k; ++kb) {
+          const int in_chunk = kb % CHUNK_KB;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+          if (in_chunk == 0) {                           // chunk accumulator must have been drained
+            mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
+            tc_fence_after();
+          }
           mbar_wait(smem_u32(full_bar + stage), phase);
           tc_fence_after();
           const uint32_t sbase = smem_u32(smem + stage * C::STAGE_BYTES);
@@ -256,38 +261,55 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);      // +32 B per k-step inside the atom
-            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (in_chunk | k) != 0);
             if (has_a_lo) umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
             if (has_b_lo) umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
           }
           umma_commit(smem_u32(empty_bar + stage));      // frees the smem stage when these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          if (in_chunk == CHUNK_KB - 1 || kb == num_k - 1) {
+            umma_commit(smem_u32(tfull_bar + acc));      // chunk complete -> drain
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          }
         }
-        umma_commit(smem_u32(tfull_bar + acc));          // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
-    // -------------------------------------------------- epilogue (4 warps; warp%4 selects the TMEM lane quarter)
-    const int q = warp & 3;
+  } else {
+    // ---------------------------------------- accumulate (RN, registers) + epilogue: 16 warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int q = warp & 3;                  // TMEM lane quarter this warp may read
+    const int cq = (warp - 4) >> 2;          // column quarter: BN/4 columns
+    constexpr int CPT = BN / 4;              // columns per thread
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
-      mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
-      tc_fence_after();
-      const int m = m0 + q * 32 + lane;
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        if (n0 + c * 32 >= N) break;                   // warp-uniform
-        float v[32];
-        tmem_ld32(trow + (uint32_t)(c * 32), v);
-        if (m < M) epi_chunk32(ep, m, n0 + c * 32, N, v);
+      float sum[CPT];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) sum[j] = 0.f;
+      for (int ch = 0; ch < num_chunks; ++ch) {
+        mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cq * CPT);
+#pragma unroll
+        for (int c = 0; c < CPT / 16; ++c) {
+          float v[16];
+          tmem_ld16(trow + (uint32_t)(c * 16), v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sum[c * 16 + j] += v[j];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      const int m = m0 + q * 32 + lane;
+      if (m < M) {
+#pragma unroll
+        for (int c = 0; c < CPT / 32; ++c) {
+          const int n = n0 + cq * CPT + c * 32;
+          if (n < N) epi_chunk32(ep, m, n, N, sum + c * 32);
+        }
+      }
     }
   }
   tc_fence_before();
@@ -362,7 +384,7 @@ int gemm_tc_launch(const float* a_hi, const float* a_lo, int lda, const float* b
   }
   const int tiles = cdiv(M, BM) * cdiv(N, BN);
   const int grid = std::min(tiles, device_sm_count());
-  gemm_tc3_kernel<BN><<<grid, 256, Cfg<BN>::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K, a_lo != nullptr,
+  gemm_tc3_kernel<BN><<<grid, THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K, a_lo != nullptr,
                                                              b_lo != nullptr, ep);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;

@@ -68,7 +68,6 @@ topk_select_kernel(float* __restrict__ scores, int n_db, int64_t ld, int k, int 
       float v = s[j];
       if (v > best || (v == best && j < besti)) { best = v; besti = j; }
     }
-    if (besti == 0x7fffffff && threadIdx.x < n_db) { besti = threadIdx.x; best = s[besti]; }  // all -inf/NaN rows
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       float ov = __shfl_xor_sync(0xffffffffu, best, o);
@@ -92,7 +91,6 @@ topk_select_kernel(float* __restrict__ scores, int n_db, int64_t ld, int k, int 
           dist[(size_t)q * k + r] = metric == ANYLOC_METRIC_L2 ? -best : best;
           idx[(size_t)q * k + r] = besti;
           s[besti] = -INFINITY;      // exclude from later rounds
-          // NaN-safe: mark with a value no comparison selects again
         } else {
           dist[(size_t)q * k + r] = metric == ANYLOC_METRIC_L2 ? INFINITY : -INFINITY;
           idx[(size_t)q * k + r] = -1;   // faiss pads with -1 when k > ntotal
@@ -107,7 +105,6 @@ topk_select_kernel(float* __restrict__ scores, int n_db, int64_t ld, int k, int 
 
 using namespace anyloc;
 
-static const int TOPK_DB_CHUNK = 1 << 30;   // scores for all of n_db are materialised (n_q x n_db fp32)
 
 extern "C" size_t anyloc_topk_workspace_bytes(int n_db, int n_q, int Dv, int k) {
   (void)k;
@@ -139,6 +136,7 @@ extern "C" int anyloc_topk(const float* db, const float* qu, int n_db, int n_q, 
               anyloc_topk_workspace_bytes(n_db, n_q, Dv, k));
     return ANYLOC_ERR_WORKSPACE;
   }
+  ProfScope ps(PC_TOPK, st, 4.0 * ((double)n_db + n_q) * Dv);
   normalize_rows_split_kernel<<<n_db, 256, 0, st>>>(db, Dv, normalize, db_hi, db_lo, dd);
   ANYLOC_CHECK_LAUNCH();
   normalize_rows_split_kernel<<<n_q, 256, 0, st>>>(qu, Dv, normalize, qu_hi, qu_lo, qq);
@@ -148,6 +146,5 @@ extern "C" int anyloc_topk(const float* db, const float* qu, int n_db, int n_q, 
   if (rc) return rc;
   topk_select_kernel<<<n_q, 1024, 0, st>>>(scores, n_db, n_db, k, metric, qq, dd, dist, idx);
   ANYLOC_CHECK_LAUNCH();
-  (void)TOPK_DB_CHUNK;
   return ANYLOC_OK;
 }

@@ -31,9 +31,8 @@ __global__ void vlad_centre_prep_kernel(const float* __restrict__ c, int K, int 
   __syncthreads();
   ss = red[0];
   if (dist_mode == ANYLOC_DIST_COSINE) {
-    float inv = 1.0f / (sqrtf(ss) + 1e-8f);
-    for (int d = threadIdx.x; d < D; d += blockDim.x) chat[(size_t)k * D + d] = row[d] / (sqrtf(ss) + 1e-8f);
-    (void)inv;
+    const float den = sqrtf(ss) + 1e-8f;            // fpk cos_sim: b / (|b| + 1e-8)
+    for (int d = threadIdx.x; d < D; d += blockDim.x) chat[(size_t)k * D + d] = row[d] / den;
     if (threadIdx.x == 0) cbias[k] = 0.f;
   } else {
     // argmax_k 2 x.c_k - |x|^2 - |c_k|^2  ==  argmax_k (x.c_k - |c_k|^2/2)
@@ -191,7 +190,6 @@ vlad_normalize_kernel(float* __restrict__ vlad, const float* __restrict__ partia
     scale[k] = sc;
     // squared norm of the block after intra-normalisation
     float nb = nk * sc;
-    partial_ss ? (void)0 : (void)0;
     scale[K + k] = nb * nb;
   }
   __syncthreads();
@@ -326,6 +324,7 @@ extern "C" int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, 
     set_error("vlad_generate: workspace too small (%zu bytes given)", ws_bytes);
     return ANYLOC_ERR_WORKSPACE;
   }
+  ProfScope ps(PC_VLAD, st, 4.0 * ((double)B * N * D + (double)B * K * D + (double)K * D));
   int rc = launch_assign(feats, n_valid, N, (int64_t)R, D, K, centers, dist_mode, chat, cbias, labels,
                          inv_norm, st);
   if (rc) return rc;

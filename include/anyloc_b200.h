@@ -61,6 +61,18 @@ int anyloc_version(void);
 /* >0: compute capability *10 of the current device (100 on B200); <0: no usable device */
 int anyloc_device_info(int* sm_count, size_t* smem_optin_bytes);
 
+/* ------------------------------------------------------------ instrumentation (bench.py)
+ * anyloc_launch_count: kernels launched by this library since load (all threads).
+ * Profiling (off by default; not thread-safe): when enabled every launch group records a cudaEvent
+ * pair on its stream; anyloc_profile_read synchronises them and returns, per category
+ * (0 gemm_tc, 1 gemm_simt, 2 attention, 3 layernorm, 4 vit_misc, 5 vlad, 6 topk), the summed
+ * device milliseconds, the number of launch groups and the summed algorithmic work
+ * (FLOPs for 0-2, bytes otherwise), then clears the records. */
+#define ANYLOC_PROF_CATEGORIES 7
+long long anyloc_launch_count(void);
+int anyloc_profile_enable(int on);
+int anyloc_profile_read(double* ms, long long* groups, double* work);
+
 /* ------------------------------------------------------------------ VLAD
  * Replaces VLAD.generate / generate_multi (utilities.py:819-926) incl. the
  * residuals of generate_res_vec (:956-962) and fpk.KMeans.predict (:849):

@@ -36,6 +36,30 @@ def extract_features(model, img, layer, facet="value", use_cls=False, norm_descs
     return res
 
 
+def extract_features_full_forward(model, img, layer, facet="value", use_cls=False, norm_descs=True):
+    """The reference's execution strategy (for the CPU-baseline timing): run the WHOLE model with a
+    forward hook on blocks[layer] / blocks[layer].attn.qkv and discard the model output
+    (utilities.py:245-252, :268-273).  Output-identical to extract_features()."""
+    captured = {}
+    mod = model.blocks[layer] if facet == "token" else model.blocks[layer].attn.qkv
+    handle = mod.register_forward_hook(lambda m, i, o: captured.__setitem__("out", o))
+    try:
+        with torch.no_grad():
+            model(img)
+            res = captured["out"]
+            if not use_cls:
+                res = res[:, 1:, ...]
+            if facet in ("query", "key", "value"):
+                d = res.shape[2] // 3
+                i = {"query": 0, "key": 1, "value": 2}[facet]
+                res = res[:, :, i * d:(i + 1) * d]
+    finally:
+        handle.remove()
+    if norm_descs:
+        res = F.normalize(res, dim=-1)
+    return res
+
+
 # --------------------------------------------------------------------- VLAD
 def assign_similarity(x, centers, dist_mode="cosine"):
     """fpk.KMeans.max_sim as reached from utilities.py:849 (`predict` on the
@@ -73,6 +97,22 @@ def vlad_generate(x, centers, intra_norm=True, norm_descs=True, dist_mode="cosin
             cd = F.normalize(cd, dim=0)                       # :859-860
         out[k * D:(k + 1) * D] = cd                           # :861
     return F.normalize(out, dim=0)                            # :889
+
+
+def vlad_generate_faithful(x, centers, intra_norm=True, norm_descs=True, dist_mode="cosine"):
+    """Same result as vlad_generate(), with the reference's memory behaviour (for CPU-baseline timing):
+    the full [N,K,D] residual tensor (utilities.py:961-962) and boolean-mask gathers (:858)."""
+    K, D = centers.shape
+    xn = F.normalize(x) if norm_descs else x
+    residuals = xn[:, None, :] - centers[None, :, :]
+    labels = vlad_labels(x, centers, dist_mode)
+    out = torch.zeros(K * D)
+    for k in set(labels.numpy()):
+        cd = residuals[labels == k, k].sum(dim=0)
+        if intra_norm:
+            cd = F.normalize(cd, dim=0)
+        out[k * D:(k + 1) * D] = cd
+    return F.normalize(out, dim=0)
 
 
 def vlad_generate_multi(xs, centers, **kw):

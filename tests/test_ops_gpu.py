@@ -84,7 +84,8 @@ def test_gemm_epilogues(L, engine, M, N, K, epi):
     resid = torch.randn(M, n_out, device="cuda", generator=g) if epi == "ls_resid" else None
     out = gemm(L, a, b, epi, bias, gamma, resid, engine)
     ref = ref_gemm(a, b, epi, bias, gamma, resid)
-    assert rel_inf(out.cpu(), ref.cpu()) < 2e-6 * max(1.0, (K / 64) ** 0.5), (engine, epi)
+    err = rel_inf(out.cpu(), ref.cpu())
+    assert err < 2e-6 * max(1.0, (K / 64) ** 0.5), (engine, epi, err)
 
 
 @pytest.mark.parametrize("D", [384, 768, 1024, 1536])
