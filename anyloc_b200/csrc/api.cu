@@ -62,7 +62,8 @@ int launch_assemble(const float*, const float*, const float*, int, int, int, flo
 int launch_layernorm(const float*, const float*, const float*, int, int, float, float*, float*, cudaStream_t);
 int launch_facet_out(const float*, int, int, int64_t, int, int, int, int, float*, cudaStream_t);
 int launch_l2norm(const float*, int64_t, int, int64_t, float*, cudaStream_t);
-int attention_launch(const float*, int, int, int, int, float*, float*, cudaStream_t);
+int attention_launch(const float*, const float*, int, int, int, int, float*, float*, cudaStream_t);
+int attention_tc_launch(const float*, const float*, int, int, int, int, float*, float*, cudaStream_t);
 
 static int gemm_dispatch(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo,
                          int ldb, int M, int N, int K, const EpiParams& ep, int engine, cudaStream_t st) {
@@ -146,11 +147,25 @@ extern "C" int anyloc_layernorm_split(const float* x, const float* w, const floa
   return launch_layernorm(x, w, b, M, D, eps, y_hi, y_lo, (cudaStream_t)stream);
 }
 
-extern "C" int anyloc_attention(const float* qkv, int B, int T, int D, int heads, float* o_hi, float* o_lo,
-                                void* stream) {
-  ANYLOC_REQUIRE(qkv && o_hi && o_lo, "attention: null pointer");
+static int attention_dispatch(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads,
+                              float* o_hi, float* o_lo, int engine, cudaStream_t st) {
+  ProfScope ps(PC_ATTENTION, st, 4.0 * B * (double)T * T * D);
+  const bool tc_ok = qkv_lo != nullptr && (D % 4) == 0 &&
+                     (reinterpret_cast<uintptr_t>(qkv_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(qkv_lo) & 15) == 0;
+  if (engine == ANYLOC_GEMM_TC3 && !tc_ok) {
+    set_error("attention: the tcgen05 engine needs the (hi,lo) qkv pair, 16-byte aligned");
+    return ANYLOC_ERR_UNSUPPORTED;
+  }
+  if (engine == ANYLOC_GEMM_SIMT || !tc_ok) return attention_launch(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, st);
+  return attention_tc_launch(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, st);
+}
+
+extern "C" int anyloc_attention(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads,
+                                float* o_hi, float* o_lo, int engine, void* stream) {
+  ANYLOC_REQUIRE(qkv_hi && o_hi && o_lo, "attention: null pointer");
+  ANYLOC_REQUIRE(D == heads * 64, "attention: head_dim must be 64 (D=%d heads=%d)", D, heads);
   if (B == 0 || T == 0) return ANYLOC_OK;
-  return attention_launch(qkv, B, T, D, heads, o_hi, o_lo, (cudaStream_t)stream);
+  return attention_dispatch(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, engine, (cudaStream_t)stream);
 }
 
 extern "C" int anyloc_l2_normalize_rows(const float* x, int64_t rows, int D, int64_t ld_in, float* y,
@@ -165,7 +180,7 @@ extern "C" int anyloc_vit_patch_k(int patch) { return (int)align_up((size_t)3 * 
 
 namespace {
 struct VitBuffers {
-  float *pa_hi, *pa_lo, *ptmp, *x, *y_hi, *y_lo, *qkv, *h_hi, *h_lo;
+  float *pa_hi, *pa_lo, *ptmp, *x, *y_hi, *y_lo, *qkv, *qkv_lo, *h_hi, *h_lo;
 };
 size_t vit_carve(const AnylocVitCfg* c, int B, int H, int W, void* ws, size_t ws_bytes, VitBuffers* out) {
   const int P = c->patch, N = (H / P) * (W / P), T = N + 1, D = c->embed_dim, Kp = anyloc_vit_patch_k(P);
@@ -176,10 +191,10 @@ size_t vit_carve(const AnylocVitCfg* c, int B, int H, int W, void* ws, size_t ws
   b.ptmp = w.take<float>((size_t)B * N * D);
   b.x = w.take<float>(M * D);
   b.y_hi = w.take<float>(M * D); b.y_lo = w.take<float>(M * D);
-  b.qkv = w.take<float>(M * 3 * D);
+  b.qkv = w.take<float>(M * 3 * D); b.qkv_lo = w.take<float>(M * 3 * D);
   b.h_hi = w.take<float>(M * c->ffn_hidden); b.h_lo = w.take<float>(M * c->ffn_hidden);
   if (out) *out = b;
-  if (ws && (!b.pa_hi || !b.pa_lo || !b.ptmp || !b.x || !b.y_hi || !b.y_lo || !b.qkv || !b.h_hi || !b.h_lo)) return 0;
+  if (ws && (!b.pa_hi || !b.pa_lo || !b.ptmp || !b.x || !b.y_hi || !b.y_lo || !b.qkv || !b.qkv_lo || !b.h_hi || !b.h_lo)) return 0;
   return w.off;
 }
 }  // namespace
@@ -196,10 +211,9 @@ static int vit_block(const AnylocVitCfg* c, const AnylocVitBlock& wb, const VitB
   const double ln_bytes = 12.0 * M * D;
   { ProfScope ps(PC_LAYERNORM, st, ln_bytes);
     if ((rc = launch_layernorm(bf.x, wb.ln1_w, wb.ln1_b, M, D, 1e-6f, bf.y_hi, bf.y_lo, st))) return rc; }
-  EpiParams e_qkv{ANYLOC_EPI_BIAS, wb.qkv_b, nullptr, nullptr, bf.qkv, nullptr, 3 * D};
+  EpiParams e_qkv{ANYLOC_EPI_BIAS_SPLIT, wb.qkv_b, nullptr, nullptr, bf.qkv, bf.qkv_lo, 3 * D};
   if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.qkv_w_hi, wb.qkv_w_lo, D, M, 3 * D, D, e_qkv, engine, st))) return rc;
-  { ProfScope ps(PC_ATTENTION, st, 4.0 * B * (double)T * T * D);
-    if ((rc = attention_launch(bf.qkv, B, T, D, c->num_heads, bf.y_hi, bf.y_lo, st))) return rc; }
+  if ((rc = attention_dispatch(bf.qkv, bf.qkv_lo, B, T, D, c->num_heads, bf.y_hi, bf.y_lo, engine, st))) return rc;
   EpiParams e_proj{ANYLOC_EPI_LS_RESID, wb.proj_b, wb.ls1, bf.x, bf.x, nullptr, D};
   if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.proj_w_hi, wb.proj_w_lo, D, M, D, D, e_proj, engine, st))) return rc;
   { ProfScope ps(PC_LAYERNORM, st, ln_bytes);

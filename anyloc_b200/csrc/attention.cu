@@ -10,8 +10,8 @@ constexpr int AT = 64;          // query tile = key tile = head_dim
 constexpr int ATP = AT + 4;     // padded row
 
 __global__ void __launch_bounds__(256)
-attention_simt_kernel(const float* __restrict__ qkv, int T, int D, float* __restrict__ o_hi,
-                      float* __restrict__ o_lo) {
+attention_simt_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_lo, int T, int D,
+                      float* __restrict__ o_hi, float* __restrict__ o_lo) {
   extern __shared__ float sm[];
   float* Qt = sm;                 // [d][row]
   float* Kt = Qt + AT * ATP;      // [d][key]
@@ -21,6 +21,15 @@ attention_simt_kernel(const float* __restrict__ qkv, int T, int D, float* __rest
   const int q0 = blockIdx.x * AT, h = blockIdx.y, b = blockIdx.z;
   const size_t ld = (size_t)3 * D;
   const float* base = qkv + (size_t)b * T * ld + (size_t)h * AT;
+  const float* base_lo = qkv_lo ? qkv_lo + (size_t)b * T * ld + (size_t)h * AT : nullptr;
+  auto ld4 = [&](size_t off) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(base + off));
+    if (base_lo) {
+      float4 w = __ldg(reinterpret_cast<const float4*>(base_lo + off));
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    return v;
+  };
   const int lrow = tid >> 4, lc = (tid & 15) * 4;
 
   // Q tile (transposed)
@@ -28,7 +37,7 @@ attention_simt_kernel(const float* __restrict__ qkv, int T, int D, float* __rest
   for (int p = 0; p < 4; ++p) {
     int r = lrow + p * 16, t = q0 + r;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t < T) v = __ldg(reinterpret_cast<const float4*>(base + (size_t)t * ld + lc));
+    if (t < T) v = ld4((size_t)t * ld + lc);
     Qt[(lc + 0) * ATP + r] = v.x; Qt[(lc + 1) * ATP + r] = v.y;
     Qt[(lc + 2) * ATP + r] = v.z; Qt[(lc + 3) * ATP + r] = v.w;
   }
@@ -45,8 +54,8 @@ attention_simt_kernel(const float* __restrict__ qkv, int T, int D, float* __rest
       int r = lrow + p * 16, t = k0 + r;
       float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
       if (t < T) {
-        kv = __ldg(reinterpret_cast<const float4*>(base + (size_t)t * ld + D + lc));
-        vv = __ldg(reinterpret_cast<const float4*>(base + (size_t)t * ld + 2 * D + lc));
+        kv = ld4((size_t)t * ld + D + lc);
+        vv = ld4((size_t)t * ld + 2 * D + lc);
       }
       Kt[(lc + 0) * ATP + r] = kv.x; Kt[(lc + 1) * ATP + r] = kv.y;
       Kt[(lc + 2) * ATP + r] = kv.z; Kt[(lc + 3) * ATP + r] = kv.w;
@@ -117,13 +126,13 @@ attention_simt_kernel(const float* __restrict__ qkv, int T, int D, float* __rest
   }
 }
 
-int attention_launch(const float* qkv, int B, int T, int D, int heads, float* o_hi, float* o_lo,
-                     cudaStream_t st) {
+int attention_launch(const float* qkv, const float* qkv_lo, int B, int T, int D, int heads, float* o_hi,
+                     float* o_lo, cudaStream_t st) {
   ANYLOC_REQUIRE(D == heads * AT, "attention: head_dim must be 64 (D=%d heads=%d)", D, heads);
   size_t smem = (size_t)4 * AT * ATP * sizeof(float);
   ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
-  attention_simt_kernel<<<dim3(cdiv(T, AT), heads, B), 256, smem, st>>>(qkv, T, D, o_hi, o_lo);
+  attention_simt_kernel<<<dim3(cdiv(T, AT), heads, B), 256, smem, st>>>(qkv, qkv_lo, T, D, o_hi, o_lo);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }

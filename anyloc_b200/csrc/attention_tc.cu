@@ -1,0 +1,404 @@
+// tcgen05 flash attention for the DINOv2 blocks (upstream dinov2/layers/attention.py via
+// /root/reference/utilities.py:269): O = softmax(Q K^T / 8) V per head (head_dim 64), fp32-equivalent
+// accuracy through the 3-term tf32 split on both GEMMs.
+//
+// Inputs are the (hi,lo) tf32 pairs of the fused qkv projection, [B*T, 3D] each (written by the qkv
+// GEMM's BIAS_SPLIT epilogue); output is the (hi,lo) pair [B*T, D] that feeds the `proj` GEMM.
+// One CTA per (128-query tile, head, image), 256 threads:
+//   warp 0   : TMA producer -- Q tile once, then a 2-stage ring of 64-key blocks {K_hi,K_lo,V_hi,V_lo}
+//   warp 1   : MMA issuer   -- S_j = Q K_j^T  (A,B from smem, K-major, M128 x N64 x K8, 24 UMMAs)
+//                              O_j = P_j V_j  (A = P from TMEM, B = V from smem MN-major, 24 UMMAs)
+//   warp 2   : TMEM allocator (S double-buffered 2x64, P_hi 64, P_lo 64, O chunk 64 columns)
+//   warps 4-7: softmax      -- thread = query row: tcgen05.ld S, online softmax in fp32 registers,
+//                              tcgen05.st P (hi,lo), and round-to-nearest accumulation of the per-block
+//                              O_j chunks into register accumulators (the tensor core's accumulator
+//                              rounds toward zero, see gemm_tc.cu), final 1/l scaling, (hi,lo) stores.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace anyloc {
+namespace atc {
+
+constexpr int BQ = 128;        // queries per CTA
+constexpr int BKV = 64;        // keys per block
+constexpr int HD = 64;         // head dim
+constexpr int STAGES = 2;
+constexpr int Q_HALF = BQ * 32 * 4;           // one [128 x 32] fp32 k-block: 16 KB
+constexpr int Q_BYTES = 4 * Q_HALF;           // hi(2 k-blocks) + lo(2 k-blocks): 64 KB
+constexpr int KV_BOX = BKV * 32 * 4;          // one [64 x 32] fp32 box: 8 KB
+constexpr int STAGE_BYTES = 8 * KV_BOX;       // K_hi(2) K_lo(2) V_hi(2) V_lo(2): 64 KB
+constexpr int SMEM_BYTES = Q_BYTES + STAGES * STAGE_BYTES + 1024 + 256;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t COL_S = 0;       // 2 x 64
+constexpr uint32_t COL_PHI = 128;   // 64
+constexpr uint32_t COL_PLO = 192;   // 64
+constexpr uint32_t COL_O = 256;     // 64
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0; !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done && (it & 0x3ff) == 0x3ff) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand, 128B swizzle (8-row atoms 1024 B apart)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// MN-major operand, 128B swizzle: 32-element (128 B) MN blocks `lbo_bytes` apart, 8-row K groups 1024 B apart
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_constant__ CUtensorMap tm_lo_q,
+                    const __grid_constant__ CUtensorMap tm_hi_kv, const __grid_constant__ CUtensorMap tm_lo_kv,
+                    int T, int D, float* __restrict__ o_hi, float* __restrict__ o_lo) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                                  // [hi kb0][hi kb1][lo kb0][lo kb1], 16 KB each
+  uint8_t* sKV = smem + Q_BYTES;                       // STAGES x {K_hi0,K_hi1,K_lo0,K_lo1,V_hi0,V_hi1,V_lo0,V_lo1}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + STAGES * STAGE_BYTES);
+  uint64_t* q_full = bars;             // 1
+  uint64_t* kv_full = bars + 1;        // [STAGES]
+  uint64_t* kv_empty = kv_full + STAGES;   // [STAGES]
+  uint64_t* s_full = kv_empty + STAGES;    // [2]
+  uint64_t* p_full = s_full + 2;       // 1
+  uint64_t* o_full = p_full + 1;       // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int nblk = (T + BKV - 1) / BKV;
+  const int row0 = b * T;                    // first token row of this image in the [B*T, 3D] matrices
+  const int colq = h * HD, colk = D + h * HD, colv = 2 * D + h * HD;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi_kv) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo_kv) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(smem_u32(q_full), 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(kv_full + s), 1); mbar_init(smem_u32(kv_empty + s), 1); }
+    mbar_init(smem_u32(s_full), 1); mbar_init(smem_u32(s_full + 1), 1);
+    mbar_init(smem_u32(p_full), 4);          // one arrive per softmax warp
+    mbar_init(smem_u32(o_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------ TMA producer
+      const uint32_t qb = smem_u32(q_full);
+      mbar_expect_tx(qb, Q_BYTES);
+      tma_load_2d(smem_u32(sQ + 0 * Q_HALF), &tm_hi_q, qb, colq, row0 + q0);
+      tma_load_2d(smem_u32(sQ + 1 * Q_HALF), &tm_hi_q, qb, colq + 32, row0 + q0);
+      tma_load_2d(smem_u32(sQ + 2 * Q_HALF), &tm_lo_q, qb, colq, row0 + q0);
+      tma_load_2d(smem_u32(sQ + 3 * Q_HALF), &tm_lo_q, qb, colq + 32, row0 + q0);
+      int stage = 0; uint32_t phase = 0;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(smem_u32(kv_empty + stage), phase ^ 1);
+        const uint32_t fb = smem_u32(kv_full + stage);
+        mbar_expect_tx(fb, STAGE_BYTES);
+        const uint32_t sb = smem_u32(sKV + stage * STAGE_BYTES);
+        const int r = row0 + j * BKV;
+        tma_load_2d(sb + 0 * KV_BOX, &tm_hi_kv, fb, colk, r);
+        tma_load_2d(sb + 1 * KV_BOX, &tm_hi_kv, fb, colk + 32, r);
+        tma_load_2d(sb + 2 * KV_BOX, &tm_lo_kv, fb, colk, r);
+        tma_load_2d(sb + 3 * KV_BOX, &tm_lo_kv, fb, colk + 32, r);
+        tma_load_2d(sb + 4 * KV_BOX, &tm_hi_kv, fb, colv, r);
+        tma_load_2d(sb + 5 * KV_BOX, &tm_hi_kv, fb, colv + 32, r);
+        tma_load_2d(sb + 6 * KV_BOX, &tm_lo_kv, fb, colv, r);
+        tma_load_2d(sb + 7 * KV_BOX, &tm_lo_kv, fb, colv + 32, r);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------ MMA issuer
+      // S: M128 x N64, A/B K-major.  PV: M128 x N64, A from TMEM, B (=V) MN-major.
+      constexpr uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BKV >> 3) << 17) |
+                                   ((uint32_t)(BQ >> 4) << 24);
+      constexpr uint32_t idesc_pv = idesc_s | (1u << 16);       // b_major = MN
+      const uint32_t q_base = smem_u32(sQ);
+      auto issue_s = [&](int j) {
+        const int st = j % STAGES;
+        const uint32_t kb = smem_u32(sKV + st * STAGE_BYTES);
+        const uint32_t d = tmem_base + COL_S + (uint32_t)((j & 1) * BKV);
+#pragma unroll
+        for (int k = 0; k < HD / 8; ++k) {                   // 8 k-steps over the head dim
+          const uint32_t off = (uint32_t)((k >> 2) * Q_HALF + (k & 3) * 32);
+          const uint32_t koff = (uint32_t)((k >> 2) * KV_BOX + (k & 3) * 32);
+          const uint64_t a_hi = desc_kmajor(q_base + off), a_lo = desc_kmajor(q_base + 2 * Q_HALF + off);
+          const uint64_t b_hi = desc_kmajor(kb + koff), b_lo = desc_kmajor(kb + 2 * KV_BOX + koff);
+          umma_ss(d, a_hi, b_hi, idesc_s, k != 0);
+          umma_ss(d, a_lo, b_hi, idesc_s, 1u);
+          umma_ss(d, a_hi, b_lo, idesc_s, 1u);
+        }
+        umma_commit(smem_u32(s_full + (j & 1)));
+      };
+      mbar_wait(smem_u32(q_full), 0);
+      mbar_wait(smem_u32(kv_full + 0), 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j % STAGES;
+        if (j + 1 < nblk) {
+          mbar_wait(smem_u32(kv_full + ((j + 1) % STAGES)), (uint32_t)(((j + 1) / STAGES) & 1));
+          tc_fence_after();
+          issue_s(j + 1);          // S buffer (j+1)&1 was consumed before P_{j-1} was published (program order)
+        }
+        mbar_wait(smem_u32(p_full), (uint32_t)(j & 1));
+        tc_fence_after();
+        const uint32_t vb = smem_u32(sKV + st * STAGE_BYTES) + 4 * KV_BOX;
+        const uint32_t d = tmem_base + COL_O;
+#pragma unroll
+        for (int k = 0; k < BKV / 8; ++k) {                   // 8 k-steps over the 64 keys
+          const uint64_t v_hi = desc_mnmajor(vb + (uint32_t)(k * 1024), KV_BOX);
+          const uint64_t v_lo = desc_mnmajor(vb + 2 * KV_BOX + (uint32_t)(k * 1024), KV_BOX);
+          const uint32_t p_hi = tmem_base + COL_PHI + (uint32_t)(k * 8), p_lo = tmem_base + COL_PLO + (uint32_t)(k * 8);
+          umma_ts(d, p_hi, v_hi, idesc_pv, k != 0);
+          umma_ts(d, p_lo, v_hi, idesc_pv, 1u);
+          umma_ts(d, p_hi, v_lo, idesc_pv, 1u);
+        }
+        umma_commit(smem_u32(o_full));
+        umma_commit(smem_u32(kv_empty + st));     // K_j / V_j no longer needed once these MMAs retire
+      }
+    }
+  } else if (warp >= 4) {
+    // -------------------------------------------------- softmax + RN accumulation (thread = query row)
+    const int qd = warp & 3;
+    const int qrow = q0 + qd * 32 + lane;             // token index inside the image
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
+    const float kScale = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
+    float m = -INFINITY, l = 0.f;
+    float o[HD];
+#pragma unroll
+    for (int c = 0; c < HD; ++c) o[c] = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(smem_u32(s_full + (j & 1)), (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      float s[BKV];
+      tmem_ld32(lane_addr + COL_S + (uint32_t)((j & 1) * BKV), s);
+      tmem_ld32(lane_addr + COL_S + (uint32_t)((j & 1) * BKV + 32), s + 32);
+      float mx = m;
+#pragma unroll
+      for (int c = 0; c < BKV; ++c) {
+        s[c] = (j * BKV + c < T) ? s[c] * kScale : -INFINITY;
+        mx = fmaxf(mx, s[c]);
+      }
+      const float alpha = exp2f(m - mx);                // 0 on the first block (m = -inf, mx finite)
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < BKV; ++c) { s[c] = exp2f(s[c] - mx); rs += s[c]; }
+      l = l * alpha + rs;
+      m = mx;
+      if (j > 0) {                                      // fold in O_{j-1} (RN), frees the P and O buffers
+        mbar_wait(smem_u32(o_full), (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+        float t[32];
+        tmem_ld32(lane_addr + COL_O, t);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) o[c] += t[c];
+        tmem_ld32(lane_addr + COL_O + 32, t);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) o[32 + c] += t[c];
+      }
+#pragma unroll
+      for (int c = 0; c < HD; ++c) o[c] *= alpha;
+      // publish P_j = (hi, lo)
+      {
+        float t[32];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) { float hh, ll; split_tf32(s[half * 32 + c], hh, ll); t[c] = hh; s[half * 32 + c] = ll; }
+          tmem_st32(lane_addr + COL_PHI + (uint32_t)(half * 32), t);
+        }
+        tmem_st32(lane_addr + COL_PLO, s);
+        tmem_st32(lane_addr + COL_PLO + 32, s + 32);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(p_full));
+    }
+    // last chunk
+    mbar_wait(smem_u32(o_full), (uint32_t)((nblk - 1) & 1));
+    tc_fence_after();
+    {
+      float t[32];
+      tmem_ld32(lane_addr + COL_O, t);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) o[c] += t[c];
+      tmem_ld32(lane_addr + COL_O + 32, t);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) o[32 + c] += t[c];
+    }
+    if (qrow < T) {
+      const float inv = 1.0f / l;
+      const size_t off = ((size_t)row0 + qrow) * D + (size_t)h * HD;
+      float4* ph = reinterpret_cast<float4*>(o_hi + off);
+      float4* pl = reinterpret_cast<float4*>(o_lo + off);
+#pragma unroll
+      for (int c = 0; c < HD; c += 4) {
+        float4 hh, ll;
+        split_tf32(o[c] * inv, hh.x, ll.x); split_tf32(o[c + 1] * inv, hh.y, ll.y);
+        split_tf32(o[c + 2] * inv, hh.z, ll.z); split_tf32(o[c + 3] * inv, hh.w, ll.w);
+        ph[c >> 2] = hh; pl[c >> 2] = ll;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("attention_tc: cuTensorMapEncodeTiled unavailable"); return ANYLOC_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("attention_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return ANYLOC_ERR_CUDA; }
+  return ANYLOC_OK;
+}
+
+}  // namespace atc
+
+int attention_tc_launch(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads, float* o_hi,
+                        float* o_lo, cudaStream_t st) {
+  using namespace atc;
+  ANYLOC_REQUIRE(D == heads * HD, "attention_tc: head_dim must be 64 (D=%d heads=%d)", D, heads);
+  CUtensorMap hq, lq, hkv, lkv;
+  int rc;
+  const int64_t rows = (int64_t)B * T;
+  if ((rc = make_map(&hq, qkv_hi, rows, 3 * D, BQ))) return rc;
+  if ((rc = make_map(&lq, qkv_lo, rows, 3 * D, BQ))) return rc;
+  if ((rc = make_map(&hkv, qkv_hi, rows, 3 * D, BKV))) return rc;
+  if ((rc = make_map(&lkv, qkv_lo, rows, 3 * D, BKV))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  attention_tc_kernel<<<dim3(cdiv(T, BQ), heads, B), 256, SMEM_BYTES, st>>>(hq, lq, hkv, lkv, T, D, o_hi, o_lo);
+  ANYLOC_CHECK_LAUNCH();
+  return ANYLOC_OK;
+}
+
+}  // namespace anyloc

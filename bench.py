@@ -56,6 +56,25 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
 
 
+def usable_cores():
+    """Host threads this process can really use: min(affinity, cgroup CPU quota).  (On the GPU boxes
+    os.cpu_count() says 128 while cpu.max grants 16 CPUs; 128 threads then run 40x slower.)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // p))
+        except Exception:
+            pass
+    return n
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -106,7 +125,7 @@ def cpu_reference(wl, n_images, steps, warmup, seed=0):
     import torch
     from oracle import anyloc_oracle as ao
     from oracle import dinov2_restated as dr
-    cores = os.cpu_count()
+    cores = usable_cores()
     torch.set_num_threads(cores)
     model = dr.build(wl["model"], seed=seed)                 # all blocks: the reference runs them all
     D = model.embed_dim
@@ -175,7 +194,13 @@ def run_ours(args, wl):
     feats = ext(img_dev)
     np.random.seed(42)
     vlad = u.VLAD(K)
-    vlad.fit(feats.reshape(-1, D))          # vocabulary on this batch's features (GPU k-means)
+    if args.vocab == "fit":
+        vlad.fit(feats.reshape(-1, D))      # vocabulary on this batch's features (GPU k-means)
+    else:                                   # profiling runs: skip the k-means launches
+        vlad.kmeans = u._KMeans(K, mode="cosine")
+        idx = torch.randperm(feats.shape[0] * feats.shape[1], device=dev, generator=g)[:K]
+        vlad.c_centers = vlad.kmeans.centroids = 0.7 * feats.reshape(-1, D)[idx].contiguous()
+        vlad.desc_dim = D
     out_host = [torch.empty(B, K * D, dtype=torch.float32).pin_memory() for _ in range(2)]
 
     def step_device():
@@ -289,6 +314,7 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "tc3", "simt"])
     ap.add_argument("--ref-images", type=int, default=2, help="images per CPU-reference step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--vocab", default="fit", choices=["fit", "random"])
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

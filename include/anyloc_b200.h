@@ -160,9 +160,10 @@ int anyloc_gemm_nt(const float* a_hi, const float* a_lo, int lda, const float* b
 int anyloc_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream);
 int anyloc_layernorm_split(const float* x, const float* w, const float* b, int M, int D, float eps,
                            float* y_hi, float* y_lo, void* stream);
-/* qkv [B,T,3D] fp32 ([q|k|v] thirds, heads of 64) -> o (hi,lo) [B,T,D] */
-int anyloc_attention(const float* qkv, int B, int T, int D, int heads, float* o_hi, float* o_lo,
-                     void* stream);
+/* softmax(q k^T / 8) v per head (head_dim 64).  qkv (hi,lo) pairs [B,T,3D] ([q|k|v] thirds); qkv_lo may
+ * be NULL for the SIMT engine (plain fp32 input).  -> o (hi,lo) [B,T,D].  engine: ANYLOC_GEMM_*. */
+int anyloc_attention(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads,
+                     float* o_hi, float* o_lo, int engine, void* stream);
 int anyloc_l2_normalize_rows(const float* x, int64_t rows, int D, int64_t ld_in, float* y, void* stream);
 
 #ifdef __cplusplus

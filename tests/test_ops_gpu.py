@@ -100,13 +100,17 @@ def test_layernorm_split(L, D):
     assert rel_inf((hi + lo).cpu(), ref.cpu()) < 2e-6
 
 
-@pytest.mark.parametrize("B,T,heads", [(2, 257, 6), (1, 530, 24), (3, 64, 2), (1, 1370, 16), (2, 65, 1)])
-def test_attention(L, B, T, heads):
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("B,T,heads", [(2, 257, 6), (1, 530, 24), (3, 64, 2), (1, 1370, 16), (2, 65, 1), (2, 129, 2)])
+def test_attention(L, engine, B, T, heads):
     D = heads * 64
     g = torch.Generator(device="cuda").manual_seed(T)
-    qkv = torch.randn(B, T, 3 * D, device="cuda", generator=g)
+    qkv = torch.randn(B, T, 3 * D, device="cuda", generator=g) * 1.5
+    q_hi, q_lo = split(L, qkv)
     hi, lo = torch.empty(B, T, D, device="cuda"), torch.empty(B, T, D, device="cuda")
-    L.check(L.load().anyloc_attention(L.ptr(qkv), B, T, D, heads, L.ptr(hi), L.ptr(lo), L.stream_ptr()), "attn")
+    L.check(L.load().anyloc_attention(L.ptr(q_hi), L.ptr(q_lo), B, T, D, heads, L.ptr(hi), L.ptr(lo),
+                                      L.ENGINE[engine], L.stream_ptr()), "attn")
+    torch.cuda.synchronize()
     q, k, v = (t.reshape(B, T, heads, 64).transpose(1, 2).double() for t in qkv.chunk(3, dim=-1))
     ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1) @ v).transpose(1, 2).reshape(B, T, D)
     assert rel_inf((hi + lo).cpu(), ref.cpu()) < 5e-6
