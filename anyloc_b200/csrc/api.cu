@@ -63,7 +63,10 @@ int launch_layernorm(const float*, const float*, const float*, int, int, float, 
 int launch_facet_out(const float*, int, int, int64_t, int, int, int, int, float*, cudaStream_t);
 int launch_l2norm(const float*, int64_t, int, int64_t, float*, cudaStream_t);
 int attention_launch(const float*, const float*, int, int, int, int, float*, float*, cudaStream_t);
-int attention_tc_launch(const float*, const float*, int, int, int, int, float*, float*, cudaStream_t);
+int attention_tc_launch(const float*, const float*, const float*, const float*, int, int, int, int, float*, float*,
+                        float*, cudaStream_t);
+int attention_tc_standalone(const float*, const float*, int, int, int, int, float*, float*, float*, cudaStream_t);
+int attention_vt_pitch(int T);
 
 static int gemm_dispatch(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo,
                          int ldb, int M, int N, int K, const EpiParams& ep, int engine, cudaStream_t st) {
@@ -147,8 +150,9 @@ extern "C" int anyloc_layernorm_split(const float* x, const float* w, const floa
   return launch_layernorm(x, w, b, M, D, eps, y_hi, y_lo, (cudaStream_t)stream);
 }
 
-static int attention_dispatch(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads,
-                              float* o_hi, float* o_lo, int engine, cudaStream_t st) {
+static int attention_dispatch(const float* qkv_hi, const float* qkv_lo, const float* vt_hi, const float* vt_lo,
+                              int B, int T, int D, int heads, float* o_hi, float* o_lo, int engine,
+                              cudaStream_t st) {
   ProfScope ps(PC_ATTENTION, st, 4.0 * B * (double)T * T * D);
   const bool tc_ok = qkv_lo != nullptr && (D % 4) == 0 &&
                      (reinterpret_cast<uintptr_t>(qkv_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(qkv_lo) & 15) == 0;
@@ -157,7 +161,8 @@ static int attention_dispatch(const float* qkv_hi, const float* qkv_lo, int B, i
     return ANYLOC_ERR_UNSUPPORTED;
   }
   if (engine == ANYLOC_GEMM_SIMT || !tc_ok) return attention_launch(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, st);
-  return attention_tc_launch(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, st);
+  if (vt_hi) return attention_tc_launch(qkv_hi, qkv_lo, vt_hi, vt_lo, B, T, D, heads, o_hi, o_lo, nullptr, st);
+  return attention_tc_standalone(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, nullptr, st);
 }
 
 extern "C" int anyloc_attention(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads,
@@ -165,7 +170,7 @@ extern "C" int anyloc_attention(const float* qkv_hi, const float* qkv_lo, int B,
   ANYLOC_REQUIRE(qkv_hi && o_hi && o_lo, "attention: null pointer");
   ANYLOC_REQUIRE(D == heads * 64, "attention: head_dim must be 64 (D=%d heads=%d)", D, heads);
   if (B == 0 || T == 0) return ANYLOC_OK;
-  return attention_dispatch(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, engine, (cudaStream_t)stream);
+  return attention_dispatch(qkv_hi, qkv_lo, nullptr, nullptr, B, T, D, heads, o_hi, o_lo, engine, (cudaStream_t)stream);
 }
 
 extern "C" int anyloc_l2_normalize_rows(const float* x, int64_t rows, int D, int64_t ld_in, float* y,
@@ -180,7 +185,8 @@ extern "C" int anyloc_vit_patch_k(int patch) { return (int)align_up((size_t)3 * 
 
 namespace {
 struct VitBuffers {
-  float *pa_hi, *pa_lo, *ptmp, *x, *y_hi, *y_lo, *qkv, *qkv_lo, *h_hi, *h_lo;
+  float *pa_hi, *pa_lo, *ptmp, *x, *y_hi, *y_lo, *qkv, *qkv_lo, *vt_hi, *vt_lo, *h_hi, *h_lo;
+  size_t vt_elems;
 };
 size_t vit_carve(const AnylocVitCfg* c, int B, int H, int W, void* ws, size_t ws_bytes, VitBuffers* out) {
   const int P = c->patch, N = (H / P) * (W / P), T = N + 1, D = c->embed_dim, Kp = anyloc_vit_patch_k(P);
@@ -192,9 +198,11 @@ size_t vit_carve(const AnylocVitCfg* c, int B, int H, int W, void* ws, size_t ws
   b.x = w.take<float>(M * D);
   b.y_hi = w.take<float>(M * D); b.y_lo = w.take<float>(M * D);
   b.qkv = w.take<float>(M * 3 * D); b.qkv_lo = w.take<float>(M * 3 * D);
+  b.vt_elems = (size_t)B * D * attention_vt_pitch(T);
+  b.vt_hi = w.take<float>(b.vt_elems); b.vt_lo = w.take<float>(b.vt_elems);
   b.h_hi = w.take<float>(M * c->ffn_hidden); b.h_lo = w.take<float>(M * c->ffn_hidden);
   if (out) *out = b;
-  if (ws && (!b.pa_hi || !b.pa_lo || !b.ptmp || !b.x || !b.y_hi || !b.y_lo || !b.qkv || !b.qkv_lo || !b.h_hi || !b.h_lo)) return 0;
+  if (ws && (!b.pa_hi || !b.pa_lo || !b.ptmp || !b.x || !b.y_hi || !b.y_lo || !b.qkv || !b.qkv_lo || !b.vt_hi || !b.vt_lo || !b.h_hi || !b.h_lo)) return 0;
   return w.off;
 }
 }  // namespace
@@ -211,9 +219,14 @@ static int vit_block(const AnylocVitCfg* c, const AnylocVitBlock& wb, const VitB
   const double ln_bytes = 12.0 * M * D;
   { ProfScope ps(PC_LAYERNORM, st, ln_bytes);
     if ((rc = launch_layernorm(bf.x, wb.ln1_w, wb.ln1_b, M, D, 1e-6f, bf.y_hi, bf.y_lo, st))) return rc; }
-  EpiParams e_qkv{ANYLOC_EPI_BIAS_SPLIT, wb.qkv_b, nullptr, nullptr, bf.qkv, bf.qkv_lo, 3 * D};
+  const bool tc_attn = engine != ANYLOC_GEMM_SIMT;
+  EpiParams e_qkv{tc_attn ? ANYLOC_EPI_QKV_SPLIT : ANYLOC_EPI_BIAS_SPLIT, wb.qkv_b, nullptr, nullptr, bf.qkv,
+                  bf.qkv_lo, 3 * D};
+  e_qkv.vt_hi = bf.vt_hi; e_qkv.vt_lo = bf.vt_lo;
+  e_qkv.qkv_T = T; e_qkv.qkv_Tp = attention_vt_pitch(T); e_qkv.qkv_D = D;
   if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.qkv_w_hi, wb.qkv_w_lo, D, M, 3 * D, D, e_qkv, engine, st))) return rc;
-  if ((rc = attention_dispatch(bf.qkv, bf.qkv_lo, B, T, D, c->num_heads, bf.y_hi, bf.y_lo, engine, st))) return rc;
+  if ((rc = attention_dispatch(bf.qkv, bf.qkv_lo, tc_attn ? bf.vt_hi : nullptr, tc_attn ? bf.vt_lo : nullptr, B, T, D,
+                               c->num_heads, bf.y_hi, bf.y_lo, engine, st))) return rc;
   EpiParams e_proj{ANYLOC_EPI_LS_RESID, wb.proj_b, wb.ls1, bf.x, bf.x, nullptr, D};
   if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.proj_w_hi, wb.proj_w_lo, D, M, D, D, e_proj, engine, st))) return rc;
   { ProfScope ps(PC_LAYERNORM, st, ln_bytes);
@@ -250,6 +263,11 @@ extern "C" int anyloc_vit_extract(const AnylocVitCfg* cfg, const AnylocVitWeight
     return ANYLOC_ERR_WORKSPACE;
   }
   int rc;
+  if (gemm_engine != ANYLOC_GEMM_SIMT && (attention_vt_pitch(T) != T)) {
+    // pad columns [T, Tp) of the transposed-V buffers are read by TMA but never written: keep them finite (zero)
+    ANYLOC_CHECK_CUDA(cudaMemsetAsync(bf.vt_hi, 0, bf.vt_elems * sizeof(float), st));
+    ANYLOC_CHECK_CUDA(cudaMemsetAsync(bf.vt_lo, 0, bf.vt_elems * sizeof(float), st));
+  }
   if ((rc = launch_im2col(img, B, H, W, P, Kp, bf.pa_hi, bf.pa_lo, st))) return rc;
   EpiParams e_pe{ANYLOC_EPI_BIAS, w->patch_b, nullptr, nullptr, bf.ptmp, nullptr, D};
   if ((rc = gemm_dispatch(bf.pa_hi, bf.pa_lo, Kp, w->patch_w_hi, w->patch_w_lo, Kp, B * N, D, Kp, e_pe,

@@ -2,12 +2,15 @@
 // /root/reference/utilities.py:269): O = softmax(Q K^T / 8) V per head (head_dim 64), fp32-equivalent
 // accuracy through the 3-term tf32 split on both GEMMs.
 //
-// Inputs are the (hi,lo) tf32 pairs of the fused qkv projection, [B*T, 3D] each (written by the qkv
-// GEMM's BIAS_SPLIT epilogue); output is the (hi,lo) pair [B*T, D] that feeds the `proj` GEMM.
+// Inputs are the (hi,lo) tf32 pairs of the fused qkv projection: q,k thirds in [B*T, 3D], and V stored
+// per-head TRANSPOSED, vt[(b*heads+h)*64 + d][t] (row pitch Tp), both written by the qkv GEMM's QKV_SPLIT
+// epilogue.  (tcgen05 MN-major B operands need the 32B-atom swizzle for 32-bit types -- measured: an
+// MN-major tf32 operand in the plain 128B swizzle yields zeros -- so V is made K-major at the source.)
+// Output is the (hi,lo) pair [B*T, D] that feeds the `proj` GEMM.
 // One CTA per (128-query tile, head, image), 256 threads:
 //   warp 0   : TMA producer -- Q tile once, then a 2-stage ring of 64-key blocks {K_hi,K_lo,V_hi,V_lo}
 //   warp 1   : MMA issuer   -- S_j = Q K_j^T  (A,B from smem, K-major, M128 x N64 x K8, 24 UMMAs)
-//                              O_j = P_j V_j  (A = P from TMEM, B = V from smem MN-major, 24 UMMAs)
+//                              O_j = P_j V_j  (A = P from TMEM, B = V^T tile from smem K-major, 24 UMMAs)
 //   warp 2   : TMEM allocator (S double-buffered 2x64, P_hi 64, P_lo 64, O chunk 64 columns)
 //   warps 4-7: softmax      -- thread = query row: tcgen05.ld S, online softmax in fp32 registers,
 //                              tcgen05.st P (hi,lo), and round-to-nearest accumulation of the per-block
@@ -78,16 +81,6 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// MN-major operand, 128B swizzle: 32-element (128 B) MN blocks `lbo_bytes` apart, 8-row K groups 1024 B apart
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -133,7 +126,8 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
 __global__ void __launch_bounds__(256, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_constant__ CUtensorMap tm_lo_q,
                     const __grid_constant__ CUtensorMap tm_hi_kv, const __grid_constant__ CUtensorMap tm_lo_kv,
-                    int T, int D, float* __restrict__ o_hi, float* __restrict__ o_lo) {
+                    const __grid_constant__ CUtensorMap tm_hi_vt, const __grid_constant__ CUtensorMap tm_lo_vt,
+                    int T, int D, float* __restrict__ o_hi, float* __restrict__ o_lo, float* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                                  // [hi kb0][hi kb1][lo kb0][lo kb1], 16 KB each
@@ -145,20 +139,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_co
   uint64_t* s_full = kv_empty + STAGES;    // [2]
   uint64_t* p_full = s_full + 2;       // 1
   uint64_t* o_full = p_full + 1;       // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* dbg_full = o_full + 1;     // debug only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dbg_full + 1);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const int nblk = (T + BKV - 1) / BKV;
   const int row0 = b * T;                    // first token row of this image in the [B*T, 3D] matrices
-  const int colq = h * HD, colk = D + h * HD, colv = 2 * D + h * HD;
+  const int colq = h * HD, colk = D + h * HD;
+  const int vrow = (b * (D / HD) + h) * HD;  // first row of this head's V^T in vt[(b*heads+h)*64 + d][t]
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi_kv) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo_kv) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi_vt) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo_vt) : "memory");
   }
   if (warp == 1 && lane == 0) {
     mbar_init(smem_u32(q_full), 1);
@@ -166,6 +164,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_co
     mbar_init(smem_u32(s_full), 1); mbar_init(smem_u32(s_full + 1), 1);
     mbar_init(smem_u32(p_full), 4);          // one arrive per softmax warp
     mbar_init(smem_u32(o_full), 1);
+    mbar_init(smem_u32(dbg_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -198,20 +197,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_co
         tma_load_2d(sb + 1 * KV_BOX, &tm_hi_kv, fb, colk + 32, r);
         tma_load_2d(sb + 2 * KV_BOX, &tm_lo_kv, fb, colk, r);
         tma_load_2d(sb + 3 * KV_BOX, &tm_lo_kv, fb, colk + 32, r);
-        tma_load_2d(sb + 4 * KV_BOX, &tm_hi_kv, fb, colv, r);
-        tma_load_2d(sb + 5 * KV_BOX, &tm_hi_kv, fb, colv + 32, r);
-        tma_load_2d(sb + 6 * KV_BOX, &tm_lo_kv, fb, colv, r);
-        tma_load_2d(sb + 7 * KV_BOX, &tm_lo_kv, fb, colv + 32, r);
+        tma_load_2d(sb + 4 * KV_BOX, &tm_hi_vt, fb, j * BKV, vrow);         // V^T [64 d x 32 keys] k-block 0
+        tma_load_2d(sb + 5 * KV_BOX, &tm_hi_vt, fb, j * BKV + 32, vrow);    //                      k-block 1
+        tma_load_2d(sb + 6 * KV_BOX, &tm_lo_vt, fb, j * BKV, vrow);
+        tma_load_2d(sb + 7 * KV_BOX, &tm_lo_vt, fb, j * BKV + 32, vrow);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------------------------ MMA issuer
-      // S: M128 x N64, A/B K-major.  PV: M128 x N64, A from TMEM, B (=V) MN-major.
+      // S: M128 x N64 (keys), A/B K-major.  PV: M128 x N64 (head dim), A = P from TMEM, B = V^T K-major.
       constexpr uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BKV >> 3) << 17) |
                                    ((uint32_t)(BQ >> 4) << 24);
-      constexpr uint32_t idesc_pv = idesc_s | (1u << 16);       // b_major = MN
+      constexpr uint32_t idesc_pv = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HD >> 3) << 17) |
+                                    ((uint32_t)(BQ >> 4) << 24);
       const uint32_t q_base = smem_u32(sQ);
       auto issue_s = [&](int j) {
         const int st = j % STAGES;
@@ -246,8 +246,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_co
         const uint32_t d = tmem_base + COL_O;
 #pragma unroll
         for (int k = 0; k < BKV / 8; ++k) {                   // 8 k-steps over the 64 keys
-          const uint64_t v_hi = desc_mnmajor(vb + (uint32_t)(k * 1024), KV_BOX);
-          const uint64_t v_lo = desc_mnmajor(vb + 2 * KV_BOX + (uint32_t)(k * 1024), KV_BOX);
+          const uint32_t voff = (uint32_t)((k >> 2) * KV_BOX + (k & 3) * 32);
+          const uint64_t v_hi = desc_kmajor(vb + voff), v_lo = desc_kmajor(vb + 2 * KV_BOX + voff);
           const uint32_t p_hi = tmem_base + COL_PHI + (uint32_t)(k * 8), p_lo = tmem_base + COL_PLO + (uint32_t)(k * 8);
           umma_ts(d, p_hi, v_hi, idesc_pv, k != 0);
           umma_ts(d, p_lo, v_hi, idesc_pv, 1u);
@@ -279,20 +279,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_co
         s[c] = (j * BKV + c < T) ? s[c] * kScale : -INFINITY;
         mx = fmaxf(mx, s[c]);
       }
+      const bool dump = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      if (dump && j == 0) for (int c = 0; c < BKV; ++c) dbg[(qd * 32 + lane) * 64 + c] = s[c];
       const float alpha = exp2f(m - mx);                // 0 on the first block (m = -inf, mx finite)
       float rs = 0.f;
 #pragma unroll
       for (int c = 0; c < BKV; ++c) { s[c] = exp2f(s[c] - mx); rs += s[c]; }
       l = l * alpha + rs;
       m = mx;
+      if (dump && j == 0) for (int c = 0; c < BKV; ++c) dbg[8192 + (qd * 32 + lane) * 64 + c] = s[c];
       if (j > 0) {                                      // fold in O_{j-1} (RN), frees the P and O buffers
         mbar_wait(smem_u32(o_full), (uint32_t)((j - 1) & 1));
         tc_fence_after();
         float t[32];
         tmem_ld32(lane_addr + COL_O, t);
+        if (dump && j == 1) for (int c = 0; c < 32; ++c) dbg[16384 + (qd * 32 + lane) * 64 + c] = t[c];
 #pragma unroll
         for (int c = 0; c < 32; ++c) o[c] += t[c];
         tmem_ld32(lane_addr + COL_O + 32, t);
+        if (dump && j == 1) for (int c = 0; c < 32; ++c) dbg[16384 + (qd * 32 + lane) * 64 + 32 + c] = t[c];
 #pragma unroll
         for (int c = 0; c < 32; ++c) o[32 + c] += t[c];
       }
@@ -378,27 +383,75 @@ static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int cols, 
   return ANYLOC_OK;
 }
 
+// V third of qkv -> per-head transposed (hi,lo): vt[(b*heads+h)*64 + d][t], row pitch Tp.  (Standalone
+// building-block path only; inside the ViT the qkv GEMM epilogue writes this layout directly.)
+__global__ void __launch_bounds__(128)
+v_transpose_kernel(const float* __restrict__ qkv_hi, const float* __restrict__ qkv_lo, int T, int Tp, int D,
+                   float* __restrict__ vt_hi, float* __restrict__ vt_lo) {
+  const int t = blockIdx.x * 128 + threadIdx.x, h = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  const size_t src = ((size_t)b * T + t) * 3 * D + 2 * D + (size_t)h * HD;
+  const size_t dst = ((size_t)b * D + (size_t)h * HD) * Tp + t;
+#pragma unroll 4
+  for (int d = 0; d < HD; d += 4) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(qkv_hi + src + d));
+    float4 c = __ldg(reinterpret_cast<const float4*>(qkv_lo + src + d));
+    vt_hi[dst + (size_t)(d + 0) * Tp] = a.x; vt_hi[dst + (size_t)(d + 1) * Tp] = a.y;
+    vt_hi[dst + (size_t)(d + 2) * Tp] = a.z; vt_hi[dst + (size_t)(d + 3) * Tp] = a.w;
+    vt_lo[dst + (size_t)(d + 0) * Tp] = c.x; vt_lo[dst + (size_t)(d + 1) * Tp] = c.y;
+    vt_lo[dst + (size_t)(d + 2) * Tp] = c.z; vt_lo[dst + (size_t)(d + 3) * Tp] = c.w;
+  }
+}
+
 }  // namespace atc
 
-int attention_tc_launch(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads, float* o_hi,
-                        float* o_lo, cudaStream_t st) {
+int attention_vt_pitch(int T) { return (T + 3) & ~3; }     // TMA row pitch must be a multiple of 16 bytes
+
+// vt_{hi,lo}: [B*D, Tp] with columns [T, Tp) zero (cudaMemset once; never written afterwards)
+int attention_tc_launch(const float* qkv_hi, const float* qkv_lo, const float* vt_hi, const float* vt_lo, int B, int T,
+                        int D, int heads, float* o_hi, float* o_lo, float* dbg, cudaStream_t st) {
   using namespace atc;
   ANYLOC_REQUIRE(D == heads * HD, "attention_tc: head_dim must be 64 (D=%d heads=%d)", D, heads);
-  CUtensorMap hq, lq, hkv, lkv;
+  CUtensorMap hq, lq, hkv, lkv, hvt, lvt;
   int rc;
   const int64_t rows = (int64_t)B * T;
+  const int Tp = attention_vt_pitch(T);
   if ((rc = make_map(&hq, qkv_hi, rows, 3 * D, BQ))) return rc;
   if ((rc = make_map(&lq, qkv_lo, rows, 3 * D, BQ))) return rc;
   if ((rc = make_map(&hkv, qkv_hi, rows, 3 * D, BKV))) return rc;
   if ((rc = make_map(&lkv, qkv_lo, rows, 3 * D, BKV))) return rc;
+  if ((rc = make_map(&hvt, vt_hi, (int64_t)B * D, Tp, HD))) return rc;
+  if ((rc = make_map(&lvt, vt_lo, (int64_t)B * D, Tp, HD))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-  attention_tc_kernel<<<dim3(cdiv(T, BQ), heads, B), 256, SMEM_BYTES, st>>>(hq, lq, hkv, lkv, T, D, o_hi, o_lo);
+  attention_tc_kernel<<<dim3(cdiv(T, BQ), heads, B), 256, SMEM_BYTES, st>>>(hq, lq, hkv, lkv, hvt, lvt, T, D, o_hi,
+                                                                             o_lo, dbg);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }
 
+// standalone: transposes V into a stream-ordered temporary first
+int attention_tc_standalone(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads, float* o_hi,
+                            float* o_lo, float* dbg, cudaStream_t st) {
+  const int Tp = attention_vt_pitch(T);
+  const size_t n = (size_t)B * D * Tp;
+  float* vt = nullptr;
+  ANYLOC_CHECK_CUDA(cudaMallocAsync((void**)&vt, 2 * n * sizeof(float), st));
+  ANYLOC_CHECK_CUDA(cudaMemsetAsync(vt, 0, 2 * n * sizeof(float), st));
+  atc::v_transpose_kernel<<<dim3(cdiv(T, 128), heads, B), 128, 0, st>>>(qkv_hi, qkv_lo, T, Tp, D, vt, vt + n);
+  ANYLOC_CHECK_LAUNCH();
+  int rc = attention_tc_launch(qkv_hi, qkv_lo, vt, vt + n, B, T, D, heads, o_hi, o_lo, dbg, st);
+  cudaFreeAsync(vt, st);
+  return rc;
+}
+
 }  // namespace anyloc
+
+// debug entry (not part of the public ABI): dumps S/P/O-chunk of block 0 of CTA (0,0,0) into dbg[3*8192]
+extern "C" int anyloc_attention_tc_debug(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads,
+                                         float* o_hi, float* o_lo, float* dbg, void* stream) {
+  return anyloc::attention_tc_standalone(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, dbg, (cudaStream_t)stream);
+}

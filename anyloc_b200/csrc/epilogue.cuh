@@ -12,7 +12,20 @@ struct EpiParams {
   float* out;           // [M,ldo]
   float* out_lo;        // [M,ldo] (SPLIT modes)
   int ldo;
+  // QKV_SPLIT only: columns >= 2*qkv_D (the V third) are written TRANSPOSED per head into
+  // vt_{hi,lo}[(b*heads + h)*64 + d][t] (row pitch qkv_Tp) so the attention kernel can use V as a K-major operand
+  float* vt_hi = nullptr;
+  float* vt_lo = nullptr;
+  int qkv_T = 0, qkv_Tp = 0, qkv_D = 0;
 };
+
+__device__ __forceinline__ void epi_store_vt(const EpiParams& p, int m, int n, float v) {
+  // n in [2D, 3D): head h = (n-2D)/64, dim d = (n-2D)%64; row m = b*T + t
+  const int c = n - 2 * p.qkv_D, b = m / p.qkv_T, t = m - b * p.qkv_T;
+  const size_t o = ((size_t)b * p.qkv_D + c) * p.qkv_Tp + t;      // (b*heads + h)*64 + d == b*D + c
+  float h, l; split_tf32(v, h, l);
+  p.vt_hi[o] = h; p.vt_lo[o] = l;
+}
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
@@ -27,6 +40,10 @@ __device__ __forceinline__ void epi_store1(const EpiParams& p, int m, int n, flo
     case ANYLOC_EPI_BIAS_SPLIT: { float h, l; split_tf32(v, h, l); p.out[o] = h; p.out_lo[o] = l; } break;
     case ANYLOC_EPI_GELU_SPLIT: { float h, l; split_tf32(gelu_erf(v), h, l); p.out[o] = h; p.out_lo[o] = l; } break;
     case ANYLOC_EPI_LS_RESID: p.out[o] = p.resid[o] + __ldg(p.gamma + n) * v; break;
+    case ANYLOC_EPI_QKV_SPLIT:
+      if (n >= 2 * p.qkv_D) epi_store_vt(p, m, n, v);
+      else { float h, l; split_tf32(v, h, l); p.out[o] = h; p.out_lo[o] = l; }
+      break;
     default: break;
   }
 }

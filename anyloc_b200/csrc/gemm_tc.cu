@@ -136,6 +136,19 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, i
     return;
   }
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ep.mode == ANYLOC_EPI_QKV_SPLIT && n >= 2 * ep.qkv_D) {
+    // V third: transposed per-head store; lanes of a warp hold consecutive rows -> coalesced along t
+    const int c0 = n - 2 * ep.qkv_D, b = m / ep.qkv_T, t = m - b * ep.qkv_T;
+    const size_t o0 = ((size_t)b * ep.qkv_D + c0) * ep.qkv_Tp + t;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float h, l;
+      split_tf32(v[j] + (ep.bias ? __ldg(ep.bias + n + j) : 0.f), h, l);
+      ep.vt_hi[o0 + (size_t)j * ep.qkv_Tp] = h;
+      ep.vt_lo[o0 + (size_t)j * ep.qkv_Tp] = l;
+    }
+    return;
+  }
   if (ep.mode == ANYLOC_EPI_SWIGLU_SPLIT) {
     float4* oh = reinterpret_cast<float4*>(ep.out + (size_t)m * ep.ldo + (n >> 1));
     float4* ol = reinterpret_cast<float4*>(ep.out_lo + (size_t)m * ep.ldo + (n >> 1));
@@ -164,7 +177,7 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, i
       float4 g = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + j));
       reinterpret_cast<float4*>(ep.out + o)[j >> 2] =
           make_float4(r.x + g.x * x.x, r.y + g.y * x.y, r.z + g.z * x.z, r.w + g.w * x.w);
-    } else {   // BIAS_SPLIT / GELU_SPLIT
+    } else {   // BIAS_SPLIT / GELU_SPLIT / QKV_SPLIT (q,k thirds)
       if (ep.mode == ANYLOC_EPI_GELU_SPLIT) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
       float4 h, l;
       split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);

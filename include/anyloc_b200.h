@@ -51,6 +51,7 @@ extern "C" {
 #define ANYLOC_EPI_GELU_SPLIT 2    /* v = gelu_erf(acc + bias) -> (hi,lo)                */
 #define ANYLOC_EPI_SWIGLU_SPLIT 3  /* cols (2j,2j+1)=(x1,x2); v=silu(x1)*x2 -> (hi,lo)[j] */
 #define ANYLOC_EPI_LS_RESID 4      /* out = resid + gamma * (acc + bias)                 */
+#define ANYLOC_EPI_QKV_SPLIT 5     /* internal (ViT): q,k thirds -> (hi,lo); v third -> per-head transposed (hi,lo) */
 /* GEMM engines */
 #define ANYLOC_GEMM_AUTO 0
 #define ANYLOC_GEMM_SIMT 1         /* fp32 FFMA (validation / odd shapes)               */

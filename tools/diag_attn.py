@@ -1,0 +1,34 @@
+import sys, os, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from anyloc_b200 import _lib as L
+lib = L.load()
+def split(x):
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    L.check(lib.anyloc_split_tf32(L.ptr(x), L.ptr(hi), L.ptr(lo), x.numel(), L.stream_ptr()), "split"); return hi, lo
+fn = lib.anyloc_attention_tc_debug
+fn.restype = C.c_int
+fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+B, T, heads = 1, 257, 2
+D = heads * 64
+g = torch.Generator(device="cuda").manual_seed(1)
+qkv = torch.randn(B, T, 3 * D, device="cuda", generator=g) * 1.5
+qh, ql = split(qkv)
+oh, ol = torch.zeros(B, T, D, device="cuda"), torch.zeros(B, T, D, device="cuda")
+dbg = torch.full((5 * 8192,), float("nan"), device="cuda")
+rc = fn(L.ptr(qh), L.ptr(ql), B, T, D, heads, L.ptr(oh), L.ptr(ol), L.ptr(dbg), L.stream_ptr())
+torch.cuda.synchronize()
+print("rc", rc)
+q, k, v = (t.reshape(B, T, heads, 64).transpose(1, 2).double() for t in qkv.chunk(3, dim=-1))
+S = (q[0, 0, :128] @ k[0, 0, :64].T) * 0.125 * 1.4426950408889634          # block 0, log2 units
+s_d = dbg[:8192].reshape(128, 64).double().cpu(); p_d = dbg[8192:16384].reshape(128, 64).double().cpu(); o_d = dbg[16384:24576].reshape(128, 64).double().cpu()
+print("S err", float((s_d - S.cpu()).abs().max()), "S ref max", float(S.abs().max()))
+P = torch.exp2(S - S.max(dim=1, keepdim=True).values).cpu()
+print("P err", float((p_d - P).abs().max()))
+O0 = P @ v[0, 0, :64].cpu()
+print("O0 err", float((o_d - O0).abs().max()), "O0 ref max", float(O0.abs().max()), "dbg O max", float(o_d.abs().max()))
+print("O0 dbg sample", o_d[0, :6].tolist(), "ref", O0[0, :6].tolist())
+# is it a transposed/permuted version?  correlate rows/cols
+ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1) @ v).transpose(1, 2).reshape(B, T, D)
+out = (oh + ol).double()
+print("final err", float((out - ref).abs().max()), "out max", float(out.abs().max()))
