@@ -1,6 +1,7 @@
 // Shared helpers for libanyloc_b200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
@@ -66,6 +67,16 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   hi = __uint_as_float(u & 0xffffe000u);
   lo = x - hi;
+}
+
+// fp16 pair format (engine TC3H): a GEMM input x is stored as (hi, lo) = (fp16(s*x), fp16(s*x - hi)), s a power
+// of two; hi+lo carries ~22 significant bits of s*x like the tf32 pair, at half the bytes and on the 2x faster
+// kind::f16 tensor path.  Activations use the fixed scale kActScale, weights a per-tensor scale (see vit.py);
+// the GEMM epilogue multiplies the accumulator by alpha = 1/(s_A*s_B) (exact).
+constexpr float kActScale = 8.0f;
+__device__ __forceinline__ void split_f16(float xs, __half& hi, __half& lo) {
+  hi = __float2half_rn(xs);
+  lo = __float2half_rn(xs - __half2float(hi));
 }
 
 int device_sm_count();

@@ -17,7 +17,18 @@ struct EpiParams {
   float* vt_hi = nullptr;
   float* vt_lo = nullptr;
   int qkv_T = 0, qkv_Tp = 0, qkv_D = 0;
+  float alpha = 1.0f;   // accumulator scale (1/(s_A*s_B) for fp16-pair inputs, else 1)
+  int out_f16 = 0;      // SPLIT outputs as fp16 pairs of kActScale*v (out/out_lo then point to __half)
 };
+
+__device__ __forceinline__ void epi_store_split(const EpiParams& p, size_t o, float v) {
+  if (p.out_f16) {
+    __half h, l; split_f16(v * kActScale, h, l);
+    reinterpret_cast<__half*>(p.out)[o] = h; reinterpret_cast<__half*>(p.out_lo)[o] = l;
+  } else {
+    float h, l; split_tf32(v, h, l); p.out[o] = h; p.out_lo[o] = l;
+  }
+}
 
 __device__ __forceinline__ void epi_store_vt(const EpiParams& p, int m, int n, float v) {
   // n in [2D, 3D): head h = (n-2D)/64, dim d = (n-2D)%64; row m = b*T + t
@@ -33,12 +44,12 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 // Apply the epilogue to one accumulator element (m, n).  For SWIGLU the caller passes the PAIR
 // (acc0 at column n even, acc1 at column n+1) and the result lands in column n/2.
 __device__ __forceinline__ void epi_store1(const EpiParams& p, int m, int n, float acc) {
-  float v = acc + (p.bias ? __ldg(p.bias + n) : 0.f);
+  float v = acc * p.alpha + (p.bias ? __ldg(p.bias + n) : 0.f);
   size_t o = (size_t)m * p.ldo + n;
   switch (p.mode) {
     case ANYLOC_EPI_BIAS: p.out[o] = v; break;
-    case ANYLOC_EPI_BIAS_SPLIT: { float h, l; split_tf32(v, h, l); p.out[o] = h; p.out_lo[o] = l; } break;
-    case ANYLOC_EPI_GELU_SPLIT: { float h, l; split_tf32(gelu_erf(v), h, l); p.out[o] = h; p.out_lo[o] = l; } break;
+    case ANYLOC_EPI_BIAS_SPLIT: epi_store_split(p, o, v); break;
+    case ANYLOC_EPI_GELU_SPLIT: epi_store_split(p, o, gelu_erf(v)); break;
     case ANYLOC_EPI_LS_RESID: p.out[o] = p.resid[o] + __ldg(p.gamma + n) * v; break;
     case ANYLOC_EPI_QKV_SPLIT:
       if (n >= 2 * p.qkv_D) epi_store_vt(p, m, n, v);
@@ -49,12 +60,9 @@ __device__ __forceinline__ void epi_store1(const EpiParams& p, int m, int n, flo
 }
 __device__ __forceinline__ void epi_store_pair(const EpiParams& p, int m, int n_even, float acc0, float acc1) {
   // SWIGLU: columns (n_even, n_even+1) = (x1_j, x2_j), j = n_even/2
-  float x1 = acc0 + (p.bias ? __ldg(p.bias + n_even) : 0.f);
-  float x2 = acc1 + (p.bias ? __ldg(p.bias + n_even + 1) : 0.f);
-  float v = silu(x1) * x2, h, l;
-  split_tf32(v, h, l);
-  size_t o = (size_t)m * p.ldo + (n_even >> 1);
-  p.out[o] = h; p.out_lo[o] = l;
+  float x1 = acc0 * p.alpha + (p.bias ? __ldg(p.bias + n_even) : 0.f);
+  float x2 = acc1 * p.alpha + (p.bias ? __ldg(p.bias + n_even + 1) : 0.f);
+  epi_store_split(p, (size_t)m * p.ldo + (n_even >> 1), silu(x1) * x2);
 }
 
 }  // namespace anyloc

@@ -27,12 +27,11 @@ namespace anyloc {
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int BK = 32;                    // floats per k-block = 128 B = one swizzle span
-constexpr int UMMA_K = 8;                 // tf32: 32 bytes per instruction
-constexpr int A_BYTES = BM * BK * 4;      // 16 KB
+constexpr int KSTEPS = 4;                  // UMMA k-steps per 128-byte k-block (32 B each: 8 tf32 or 16 fp16)
+constexpr int A_BYTES = BM * 128;         // 16 KB: 128 rows x 128 B
 
 template <int BN> struct Cfg {
-  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 2 : 3;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -87,12 +86,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+template <bool F16>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                     uint32_t accumulate) {
+  if constexpr (F16)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -122,7 +128,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// ---- epilogue on 32 consecutive columns of one row (row m, columns n..n+31), values in v[]
+// ---- epilogue on 32 consecutive columns of one row (row m, columns n..n+31), raw accumulators in v[]
+__device__ __forceinline__ void store_split4(const EpiParams& ep, size_t o, float4 x) {
+  if (ep.out_f16) {      // fp16 pair of kActScale*x: 4 halves = 8 bytes per array
+    __half h[4], l[4];
+    split_f16(x.x * kActScale, h[0], l[0]); split_f16(x.y * kActScale, h[1], l[1]);
+    split_f16(x.z * kActScale, h[2], l[2]); split_f16(x.w * kActScale, h[3], l[3]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out) + o) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out_lo) + o) = *reinterpret_cast<uint2*>(l);
+  } else {
+    float4 h, l;
+    split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+    *reinterpret_cast<float4*>(ep.out + o) = h;
+    *reinterpret_cast<float4*>(ep.out_lo + o) = l;
+  }
+}
+
 __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, int N, const float* v) {
   const bool vec = (n + 32 <= N) && ((ep.ldo & 3) == 0);
   if (!vec) {
@@ -136,6 +157,7 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, i
     return;
   }
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float al = ep.alpha;
   if (ep.mode == ANYLOC_EPI_QKV_SPLIT && n >= 2 * ep.qkv_D) {
     // V third: transposed per-head store; lanes of a warp hold consecutive rows -> coalesced along t
     const int c0 = n - 2 * ep.qkv_D, b = m / ep.qkv_T, t = m - b * ep.qkv_T;
@@ -143,33 +165,33 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, i
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       float h, l;
-      split_tf32(v[j] + (ep.bias ? __ldg(ep.bias + n + j) : 0.f), h, l);
+      split_tf32(v[j] * al + (ep.bias ? __ldg(ep.bias + n + j) : 0.f), h, l);
       ep.vt_hi[o0 + (size_t)j * ep.qkv_Tp] = h;
       ep.vt_lo[o0 + (size_t)j * ep.qkv_Tp] = l;
     }
     return;
   }
   if (ep.mode == ANYLOC_EPI_SWIGLU_SPLIT) {
-    float4* oh = reinterpret_cast<float4*>(ep.out + (size_t)m * ep.ldo + (n >> 1));
-    float4* ol = reinterpret_cast<float4*>(ep.out_lo + (size_t)m * ep.ldo + (n >> 1));
+    const size_t o = (size_t)m * ep.ldo + (n >> 1);
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
       float4 b0 = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n + j)) : zero4;
       float4 b1 = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n + j + 4)) : zero4;
-      float4 h, l;
-      split_tf32(silu(v[j] + b0.x) * (v[j + 1] + b0.y), h.x, l.x);
-      split_tf32(silu(v[j + 2] + b0.z) * (v[j + 3] + b0.w), h.y, l.y);
-      split_tf32(silu(v[j + 4] + b1.x) * (v[j + 5] + b1.y), h.z, l.z);
-      split_tf32(silu(v[j + 6] + b1.z) * (v[j + 7] + b1.w), h.w, l.w);
-      oh[j >> 3] = h; ol[j >> 3] = l;
+      float4 x;
+      x.x = silu(v[j] * al + b0.x) * (v[j + 1] * al + b0.y);
+      x.y = silu(v[j + 2] * al + b0.z) * (v[j + 3] * al + b0.w);
+      x.z = silu(v[j + 4] * al + b1.x) * (v[j + 5] * al + b1.y);
+      x.w = silu(v[j + 6] * al + b1.z) * (v[j + 7] * al + b1.w);
+      store_split4(ep, o + (j >> 1), x);
     }
     return;
   }
   const size_t o = (size_t)m * ep.ldo + n;
+  const bool qkv = ep.mode == ANYLOC_EPI_QKV_SPLIT;
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     float4 b = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n + j)) : zero4;
-    float4 x = make_float4(v[j] + b.x, v[j + 1] + b.y, v[j + 2] + b.z, v[j + 3] + b.w);
+    float4 x = make_float4(v[j] * al + b.x, v[j + 1] * al + b.y, v[j + 2] * al + b.z, v[j + 3] * al + b.w);
     if (ep.mode == ANYLOC_EPI_BIAS) {
       reinterpret_cast<float4*>(ep.out + o)[j >> 2] = x;
     } else if (ep.mode == ANYLOC_EPI_LS_RESID) {
@@ -177,17 +199,21 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, i
       float4 g = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + j));
       reinterpret_cast<float4*>(ep.out + o)[j >> 2] =
           make_float4(r.x + g.x * x.x, r.y + g.y * x.y, r.z + g.z * x.z, r.w + g.w * x.w);
-    } else {   // BIAS_SPLIT / GELU_SPLIT / QKV_SPLIT (q,k thirds)
-      if (ep.mode == ANYLOC_EPI_GELU_SPLIT) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+    } else if (qkv) {   // q,k thirds: always tf32 pairs (attention input)
       float4 h, l;
       split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
       reinterpret_cast<float4*>(ep.out + o)[j >> 2] = h;
       reinterpret_cast<float4*>(ep.out_lo + o)[j >> 2] = l;
+    } else {            // BIAS_SPLIT / GELU_SPLIT
+      if (ep.mode == ANYLOC_EPI_GELU_SPLIT) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+      store_split4(ep, o + j, x);
     }
   }
 }
 
-template <int BN>
+// F16 = false: operands are fp32 words read as tf32 (32 elements per 128 B k-block, UMMA K=8, kind::tf32)
+// F16 = true : operands are fp16            (64 elements per 128 B k-block, UMMA K=16, kind::f16, 2x rate)
+template <int BN, bool F16>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -206,7 +232,8 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
-  const int num_k = (K + BK - 1) / BK;
+  constexpr int BKE = F16 ? 64 : 32;         // elements per k-block (128 bytes)
+  const int num_k = (K + BKE - 1) / BKE;
   const int num_chunks = (num_k + CHUNK_KB - 1) / CHUNK_KB;
 
   if (warp == 0 && lane == 0) {
@@ -245,16 +272,17 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           const uint32_t fb = smem_u32(full_bar + stage);
           mbar_expect_tx(fb, tx_bytes);
           const uint32_t sbase = smem_u32(smem + stage * C::STAGE_BYTES);
-          tma_load_2d(sbase, &tm_a_hi, fb, kb * BK, m0);
-          if (has_a_lo) tma_load_2d(sbase + A_BYTES, &tm_a_lo, fb, kb * BK, m0);
-          tma_load_2d(sbase + 2 * A_BYTES, &tm_b_hi, fb, kb * BK, n0);
-          if (has_b_lo) tma_load_2d(sbase + 2 * A_BYTES + C::B_BYTES, &tm_b_lo, fb, kb * BK, n0);
+          tma_load_2d(sbase, &tm_a_hi, fb, kb * BKE, m0);
+          if (has_a_lo) tma_load_2d(sbase + A_BYTES, &tm_a_lo, fb, kb * BKE, m0);
+          tma_load_2d(sbase + 2 * A_BYTES, &tm_b_hi, fb, kb * BKE, n0);
+          if (has_b_lo) tma_load_2d(sbase + 2 * A_BYTES + C::B_BYTES, &tm_b_lo, fb, kb * BKE, n0);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     } else if (warp == 1 && lane == 0) {
       // ------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+      constexpr uint32_t fmt = F16 ? 0u : 2u;          // a/b format: 0 = F16, 2 = TF32; c format 1 = F32
+      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
                                  ((uint32_t)(BM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -272,11 +300,11 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           const uint64_t a_hi = make_desc(sbase), a_lo = make_desc(sbase + A_BYTES);
           const uint64_t b_hi = make_desc(sbase + 2 * A_BYTES), b_lo = make_desc(sbase + 2 * A_BYTES + C::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);      // +32 B per k-step inside the atom
-            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (in_chunk | k) != 0);
-            if (has_a_lo) umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-            if (has_b_lo) umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+          for (int k = 0; k < KSTEPS; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);      // +32 B per k-step inside the atom (both types)
+            umma<F16>(d_tmem, a_hi + adv, b_hi + adv, idesc, (in_chunk | k) != 0);
+            if (has_a_lo) umma<F16>(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+            if (has_b_lo) umma<F16>(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
           }
           umma_commit(smem_u32(empty_bar + stage));      // frees the smem stage when these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -351,27 +379,29 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld, int box_rows) {
+static int make_map(CUtensorMap* map, const void* ptr, int rows, int K, int ld, int box_rows, bool f16) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("gemm_tc: cuTensorMapEncodeTiled unavailable"); return ANYLOC_ERR_CUDA; }
+  const int esz = f16 ? 2 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d", (int)r, rows, K, ld); return ANYLOC_ERR_CUDA; }
   return ANYLOC_OK;
 }
 
 }  // namespace tc
 
-bool gemm_tc_supported(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo,
-                       int ldb, int M, int N, int K, const EpiParams& ep) {
+bool gemm_tc_supported(const void* a_hi, const void* a_lo, int lda, const void* b_hi, const void* b_lo, int ldb,
+                       int M, int N, int K, const EpiParams& ep, bool f16) {
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (M < 1 || N < 1 || K < 4) return false;
-  if ((K & 3) || (lda & 3) || (ldb & 3)) return false;
+  const int q = f16 ? 8 : 4;                 // elements per 16 bytes
+  if (M < 1 || N < 1 || K < q) return false;
+  if ((K % q) || (lda % q) || (ldb % q)) return false;
   if (!al16(a_hi) || !al16(b_hi) || (a_lo && !al16(a_lo)) || (b_lo && !al16(b_lo))) return false;
   if (!al16(ep.out) || (ep.out_lo && !al16(ep.out_lo)) || (ep.resid && !al16(ep.resid))) return false;
   if (ep.bias && !al16(ep.bias)) return false;
@@ -379,28 +409,35 @@ bool gemm_tc_supported(const float* a_hi, const float* a_lo, int lda, const floa
   return true;
 }
 
-int gemm_tc_launch(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb,
-                   int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+template <bool F16>
+static int launch_impl(const void* a_hi, const void* a_lo, int lda, const void* b_hi, const void* b_lo, int ldb, int M,
+                       int N, int K, const EpiParams& ep, cudaStream_t st) {
   using namespace tc;
   constexpr int BN = 256;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
-  if ((rc = make_map(&ma_hi, a_hi, M, K, lda, BM))) return rc;
-  if ((rc = make_map(&ma_lo, a_lo ? a_lo : a_hi, M, K, lda, BM))) return rc;
-  if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, BN))) return rc;
-  if ((rc = make_map(&mb_lo, b_lo ? b_lo : b_hi, N, K, ldb, BN))) return rc;
+  if ((rc = make_map(&ma_hi, a_hi, M, K, lda, BM, F16))) return rc;
+  if ((rc = make_map(&ma_lo, a_lo ? a_lo : a_hi, M, K, lda, BM, F16))) return rc;
+  if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, BN, F16))) return rc;
+  if ((rc = make_map(&mb_lo, b_lo ? b_lo : b_hi, N, K, ldb, BN, F16))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg<BN>::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles = cdiv(M, BM) * cdiv(N, BN);
   const int grid = std::min(tiles, device_sm_count());
-  gemm_tc3_kernel<BN><<<grid, THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K, a_lo != nullptr,
-                                                             b_lo != nullptr, ep);
+  gemm_tc3_kernel<BN, F16><<<grid, THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K,
+                                                                       a_lo != nullptr, b_lo != nullptr, ep);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
+}
+
+int gemm_tc_launch(const void* a_hi, const void* a_lo, int lda, const void* b_hi, const void* b_lo, int ldb, int M,
+                   int N, int K, const EpiParams& ep, bool f16, cudaStream_t st) {
+  return f16 ? launch_impl<true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st)
+             : launch_impl<false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st);
 }
 
 }  // namespace anyloc
