@@ -17,6 +17,8 @@ FACET = {"query": 0, "key": 1, "value": 2, "token": 3}
 FFN = {"mlp": 0, "swiglufused": 1}
 EPI = {"bias": 0, "bias_split": 1, "gelu_split": 2, "swiglu_split": 3, "ls_resid": 4}
 ENGINE = {"auto": 0, "simt": 1, "tc3": 2}
+PAIR = {"tf32": 0, "f16": 1}
+ACT_SCALE = 8.0     # kActScale in csrc/common.cuh
 
 
 class AnylocError(RuntimeError):
@@ -24,7 +26,8 @@ class AnylocError(RuntimeError):
 
 
 class VitCfg(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("embed_dim", "depth", "num_heads", "ffn_kind", "ffn_hidden", "patch")]
+    _fields_ = [(n, C.c_int) for n in ("embed_dim", "depth", "num_heads", "ffn_kind", "ffn_hidden", "patch",
+                                       "pair_dtype")]
 
 
 _BLOCK_FIELDS = ["ln1_w", "ln1_b", "qkv_w_hi", "qkv_w_lo", "qkv_b", "proj_w_hi", "proj_w_lo", "proj_b",
@@ -32,12 +35,13 @@ _BLOCK_FIELDS = ["ln1_w", "ln1_b", "qkv_w_hi", "qkv_w_lo", "qkv_b", "proj_w_hi",
 
 
 class VitBlock(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in _BLOCK_FIELDS]
+    _fields_ = [(n, C.c_void_p) for n in _BLOCK_FIELDS] + \
+               [(n, C.c_float) for n in ("qkv_alpha", "proj_alpha", "in_alpha", "out_alpha")]
 
 
 class VitWeightsStruct(C.Structure):
     _fields_ = [("patch_w_hi", C.c_void_p), ("patch_w_lo", C.c_void_p), ("patch_b", C.c_void_p),
-                ("cls_token", C.c_void_p), ("blocks", C.POINTER(VitBlock))]
+                ("cls_token", C.c_void_p), ("blocks", C.POINTER(VitBlock)), ("patch_alpha", C.c_float)]
 
 
 _SIGS = {
@@ -63,13 +67,14 @@ _SIGS = {
                                      C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "anyloc_gemm_nt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
-                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "anyloc_split_tf32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "anyloc_split_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_void_p]),
     "anyloc_layernorm_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
-                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+                                         C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "anyloc_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                   C.c_void_p, C.c_int, C.c_void_p]),
+                                   C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "anyloc_l2_normalize_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
 }
 EXPORTS = sorted(_SIGS)

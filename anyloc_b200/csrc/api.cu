@@ -49,41 +49,42 @@ int device_sm_count() {
 }
 
 // engines (defined in gemm_simt.cu / gemm_tc.cu)
-int gemm_simt_launch(const float*, const float*, int, const float*, const float*, int, int, int, int,
-                     const EpiParams&, cudaStream_t);
-int gemm_tc_launch(const float*, const float*, int, const float*, const float*, int, int, int, int,
-                   const EpiParams&, cudaStream_t);
-bool gemm_tc_supported(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo,
-                       int ldb, int M, int N, int K, const EpiParams& ep);
+int gemm_simt_launch(const void*, const void*, int, const void*, const void*, int, int, int, int,
+                     const EpiParams&, bool f16, cudaStream_t);
+int gemm_tc_launch(const void*, const void*, int, const void*, const void*, int, int, int, int,
+                   const EpiParams&, bool f16, cudaStream_t);
+bool gemm_tc_supported(const void* a_hi, const void* a_lo, int lda, const void* b_hi, const void* b_lo,
+                       int ldb, int M, int N, int K, const EpiParams& ep, bool f16);
 // vit_ops.cu / attention.cu
 int launch_split(const float*, float*, float*, size_t, cudaStream_t);
-int launch_im2col(const float*, int, int, int, int, int, float*, float*, cudaStream_t);
+int launch_split_f16(const float*, void*, void*, size_t, float, cudaStream_t);
+int launch_im2col(const float*, int, int, int, int, int, void*, void*, bool, cudaStream_t);
 int launch_assemble(const float*, const float*, const float*, int, int, int, float*, cudaStream_t);
-int launch_layernorm(const float*, const float*, const float*, int, int, float, float*, float*, cudaStream_t);
+int launch_layernorm(const float*, const float*, const float*, int, int, float, void*, void*, bool, cudaStream_t);
 int launch_facet_out(const float*, int, int, int64_t, int, int, int, int, float*, cudaStream_t);
 int launch_l2norm(const float*, int64_t, int, int64_t, float*, cudaStream_t);
-int attention_launch(const float*, const float*, int, int, int, int, float*, float*, cudaStream_t);
-int attention_tc_launch(const float*, const float*, const float*, const float*, int, int, int, int, float*, float*,
+int attention_launch(const float*, const float*, int, int, int, int, void*, void*, bool, cudaStream_t);
+int attention_tc_launch(const float*, const float*, const float*, const float*, int, int, int, int, void*, void*, bool,
                         float*, cudaStream_t);
-int attention_tc_standalone(const float*, const float*, int, int, int, int, float*, float*, float*, cudaStream_t);
+int attention_tc_standalone(const float*, const float*, int, int, int, int, void*, void*, bool, float*, cudaStream_t);
 int attention_vt_pitch(int T);
 
-static int gemm_dispatch(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo,
-                         int ldb, int M, int N, int K, const EpiParams& ep, int engine, cudaStream_t st) {
+static int gemm_dispatch(const void* a_hi, const void* a_lo, int lda, const void* b_hi, const void* b_lo,
+                         int ldb, int M, int N, int K, const EpiParams& ep, int engine, bool f16, cudaStream_t st) {
   if (M == 0 || N == 0) return ANYLOC_OK;
-  bool tc_ok = gemm_tc_supported(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep);
+  bool tc_ok = gemm_tc_supported(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, f16);
   if (engine == ANYLOC_GEMM_TC3 && !tc_ok) {
-    set_error("gemm: tcgen05 engine does not support this shape/alignment (M=%d N=%d K=%d lda=%d ldb=%d)",
-              M, N, K, lda, ldb);
+    set_error("gemm: tcgen05 engine does not support this shape/alignment (M=%d N=%d K=%d lda=%d ldb=%d f16=%d)",
+              M, N, K, lda, ldb, (int)f16);
     return ANYLOC_ERR_UNSUPPORTED;
   }
   const double flops = 2.0 * M * N * K;
   if (engine == ANYLOC_GEMM_TC3 || (engine == ANYLOC_GEMM_AUTO && tc_ok && M >= 32)) {
     ProfScope ps(PC_GEMM_TC, st, flops);
-    return gemm_tc_launch(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st);
+    return gemm_tc_launch(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, f16, st);
   }
   ProfScope ps(PC_GEMM_SIMT, st, flops);
-  return gemm_simt_launch(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st);
+  return gemm_simt_launch(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, f16, st);
 }
 
 }  // namespace anyloc
@@ -122,19 +123,24 @@ extern "C" int anyloc_device_info(int* sm_count, size_t* smem_optin_bytes) {
   return p.major * 10 + p.minor;
 }
 
-extern "C" int anyloc_gemm_nt(const float* a_hi, const float* a_lo, int lda, const float* b_hi,
-                              const float* b_lo, int ldb, int M, int N, int K, int epilogue,
-                              const float* bias, const float* gamma, const float* resid, float* out,
-                              float* out_lo, int ldo, int engine, void* stream) {
+extern "C" int anyloc_gemm_nt(const void* a_hi, const void* a_lo, int lda, const void* b_hi, const void* b_lo,
+                              int ldb, int M, int N, int K, int in_dtype, float alpha, int epilogue,
+                              const float* bias, const float* gamma, const float* resid, void* out, void* out_lo,
+                              int ldo, int out_dtype, int engine, void* stream) {
   ANYLOC_REQUIRE(a_hi && b_hi && out, "gemm_nt: null pointer");
   ANYLOC_REQUIRE(M >= 0 && N >= 0 && K > 0, "gemm_nt: bad dims");
+  ANYLOC_REQUIRE(in_dtype == ANYLOC_PAIR_TF32 || in_dtype == ANYLOC_PAIR_F16, "gemm_nt: bad in_dtype %d", in_dtype);
+  ANYLOC_REQUIRE(out_dtype == ANYLOC_PAIR_TF32 || out_dtype == ANYLOC_PAIR_F16, "gemm_nt: bad out_dtype %d", out_dtype);
   ANYLOC_REQUIRE(epilogue >= ANYLOC_EPI_BIAS && epilogue <= ANYLOC_EPI_LS_RESID, "gemm_nt: bad epilogue %d", epilogue);
   if (epilogue == ANYLOC_EPI_BIAS_SPLIT || epilogue == ANYLOC_EPI_GELU_SPLIT || epilogue == ANYLOC_EPI_SWIGLU_SPLIT)
     ANYLOC_REQUIRE(out_lo, "gemm_nt: split epilogue needs out_lo");
   if (epilogue == ANYLOC_EPI_SWIGLU_SPLIT) ANYLOC_REQUIRE(N % 2 == 0, "gemm_nt: swiglu needs even N");
   if (epilogue == ANYLOC_EPI_LS_RESID) ANYLOC_REQUIRE(gamma && resid, "gemm_nt: LS_RESID needs gamma and resid");
-  EpiParams ep{epilogue, bias, gamma, resid, out, out_lo, ldo};
-  return gemm_dispatch(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, engine, (cudaStream_t)stream);
+  EpiParams ep{epilogue, bias, gamma, resid, (float*)out, (float*)out_lo, ldo};
+  ep.alpha = alpha;
+  ep.out_f16 = out_dtype == ANYLOC_PAIR_F16;
+  return gemm_dispatch(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, engine, in_dtype == ANYLOC_PAIR_F16,
+                       (cudaStream_t)stream);
 }
 
 extern "C" int anyloc_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream) {
@@ -143,15 +149,21 @@ extern "C" int anyloc_split_tf32(const float* x, float* hi, float* lo, size_t n,
   return launch_split(x, hi, lo, n, (cudaStream_t)stream);
 }
 
+extern "C" int anyloc_split_f16(const float* x, void* hi, void* lo, size_t n, float scale, void* stream) {
+  ANYLOC_REQUIRE(x && hi && lo, "split_f16: null pointer");
+  if (n == 0) return ANYLOC_OK;
+  return launch_split_f16(x, hi, lo, n, scale, (cudaStream_t)stream);
+}
+
 extern "C" int anyloc_layernorm_split(const float* x, const float* w, const float* b, int M, int D,
-                                      float eps, float* y_hi, float* y_lo, void* stream) {
+                                      float eps, void* y_hi, void* y_lo, int out_dtype, void* stream) {
   ANYLOC_REQUIRE(x && w && b && y_hi && y_lo, "layernorm: null pointer");
   if (M == 0) return ANYLOC_OK;
-  return launch_layernorm(x, w, b, M, D, eps, y_hi, y_lo, (cudaStream_t)stream);
+  return launch_layernorm(x, w, b, M, D, eps, y_hi, y_lo, out_dtype == ANYLOC_PAIR_F16, (cudaStream_t)stream);
 }
 
 static int attention_dispatch(const float* qkv_hi, const float* qkv_lo, const float* vt_hi, const float* vt_lo,
-                              int B, int T, int D, int heads, float* o_hi, float* o_lo, int engine,
+                              int B, int T, int D, int heads, void* o_hi, void* o_lo, bool out_f16, int engine,
                               cudaStream_t st) {
   ProfScope ps(PC_ATTENTION, st, 4.0 * B * (double)T * T * D);
   const bool tc_ok = qkv_lo != nullptr && (D % 4) == 0 &&
@@ -160,17 +172,19 @@ static int attention_dispatch(const float* qkv_hi, const float* qkv_lo, const fl
     set_error("attention: the tcgen05 engine needs the (hi,lo) qkv pair, 16-byte aligned");
     return ANYLOC_ERR_UNSUPPORTED;
   }
-  if (engine == ANYLOC_GEMM_SIMT || !tc_ok) return attention_launch(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, st);
-  if (vt_hi) return attention_tc_launch(qkv_hi, qkv_lo, vt_hi, vt_lo, B, T, D, heads, o_hi, o_lo, nullptr, st);
-  return attention_tc_standalone(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, nullptr, st);
+  if (engine == ANYLOC_GEMM_SIMT || !tc_ok)
+    return attention_launch(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, out_f16, st);
+  if (vt_hi) return attention_tc_launch(qkv_hi, qkv_lo, vt_hi, vt_lo, B, T, D, heads, o_hi, o_lo, out_f16, nullptr, st);
+  return attention_tc_standalone(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, out_f16, nullptr, st);
 }
 
 extern "C" int anyloc_attention(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads,
-                                float* o_hi, float* o_lo, int engine, void* stream) {
+                                void* o_hi, void* o_lo, int out_dtype, int engine, void* stream) {
   ANYLOC_REQUIRE(qkv_hi && o_hi && o_lo, "attention: null pointer");
   ANYLOC_REQUIRE(D == heads * 64, "attention: head_dim must be 64 (D=%d heads=%d)", D, heads);
   if (B == 0 || T == 0) return ANYLOC_OK;
-  return attention_dispatch(qkv_hi, qkv_lo, nullptr, nullptr, B, T, D, heads, o_hi, o_lo, engine, (cudaStream_t)stream);
+  return attention_dispatch(qkv_hi, qkv_lo, nullptr, nullptr, B, T, D, heads, o_hi, o_lo,
+                            out_dtype == ANYLOC_PAIR_F16, engine, (cudaStream_t)stream);
 }
 
 extern "C" int anyloc_l2_normalize_rows(const float* x, int64_t rows, int D, int64_t ld_in, float* y,
@@ -215,31 +229,33 @@ extern "C" size_t anyloc_vit_workspace_bytes(const AnylocVitCfg* cfg, int B, int
 static int vit_block(const AnylocVitCfg* c, const AnylocVitBlock& wb, const VitBuffers& bf, int B, int T,
                      int engine, cudaStream_t st) {
   const int D = c->embed_dim, M = B * T, Hf = c->ffn_hidden;
+  const bool f16 = c->pair_dtype == ANYLOC_PAIR_F16;
   int rc;
-  const double ln_bytes = 12.0 * M * D;
+  const double ln_bytes = (f16 ? 8.0 : 12.0) * M * D;
   { ProfScope ps(PC_LAYERNORM, st, ln_bytes);
-    if ((rc = launch_layernorm(bf.x, wb.ln1_w, wb.ln1_b, M, D, 1e-6f, bf.y_hi, bf.y_lo, st))) return rc; }
+    if ((rc = launch_layernorm(bf.x, wb.ln1_w, wb.ln1_b, M, D, 1e-6f, bf.y_hi, bf.y_lo, f16, st))) return rc; }
   const bool tc_attn = engine != ANYLOC_GEMM_SIMT;
   EpiParams e_qkv{tc_attn ? ANYLOC_EPI_QKV_SPLIT : ANYLOC_EPI_BIAS_SPLIT, wb.qkv_b, nullptr, nullptr, bf.qkv,
                   bf.qkv_lo, 3 * D};
   e_qkv.vt_hi = bf.vt_hi; e_qkv.vt_lo = bf.vt_lo;
   e_qkv.qkv_T = T; e_qkv.qkv_Tp = attention_vt_pitch(T); e_qkv.qkv_D = D;
-  if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.qkv_w_hi, wb.qkv_w_lo, D, M, 3 * D, D, e_qkv, engine, st))) return rc;
+  e_qkv.alpha = wb.qkv_alpha;          // q,k,v always leave as tf32 pairs (attention input)
+  if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.qkv_w_hi, wb.qkv_w_lo, D, M, 3 * D, D, e_qkv, engine, f16, st))) return rc;
   if ((rc = attention_dispatch(bf.qkv, bf.qkv_lo, tc_attn ? bf.vt_hi : nullptr, tc_attn ? bf.vt_lo : nullptr, B, T, D,
-                               c->num_heads, bf.y_hi, bf.y_lo, engine, st))) return rc;
+                               c->num_heads, bf.y_hi, bf.y_lo, f16, engine, st))) return rc;
   EpiParams e_proj{ANYLOC_EPI_LS_RESID, wb.proj_b, wb.ls1, bf.x, bf.x, nullptr, D};
-  if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.proj_w_hi, wb.proj_w_lo, D, M, D, D, e_proj, engine, st))) return rc;
+  e_proj.alpha = wb.proj_alpha;
+  if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.proj_w_hi, wb.proj_w_lo, D, M, D, D, e_proj, engine, f16, st))) return rc;
   { ProfScope ps(PC_LAYERNORM, st, ln_bytes);
-    if ((rc = launch_layernorm(bf.x, wb.ln2_w, wb.ln2_b, M, D, 1e-6f, bf.y_hi, bf.y_lo, st))) return rc; }
-  if (c->ffn_kind == ANYLOC_FFN_MLP) {
-    EpiParams e_in{ANYLOC_EPI_GELU_SPLIT, wb.in_b, nullptr, nullptr, bf.h_hi, bf.h_lo, Hf};
-    if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.in_w_hi, wb.in_w_lo, D, M, Hf, D, e_in, engine, st))) return rc;
-  } else {
-    EpiParams e_in{ANYLOC_EPI_SWIGLU_SPLIT, wb.in_b, nullptr, nullptr, bf.h_hi, bf.h_lo, Hf};
-    if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.in_w_hi, wb.in_w_lo, D, M, 2 * Hf, D, e_in, engine, st))) return rc;
-  }
+    if ((rc = launch_layernorm(bf.x, wb.ln2_w, wb.ln2_b, M, D, 1e-6f, bf.y_hi, bf.y_lo, f16, st))) return rc; }
+  EpiParams e_in{c->ffn_kind == ANYLOC_FFN_MLP ? ANYLOC_EPI_GELU_SPLIT : ANYLOC_EPI_SWIGLU_SPLIT, wb.in_b, nullptr,
+                 nullptr, bf.h_hi, bf.h_lo, Hf};
+  e_in.alpha = wb.in_alpha; e_in.out_f16 = f16;
+  const int n_in = c->ffn_kind == ANYLOC_FFN_MLP ? Hf : 2 * Hf;
+  if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.in_w_hi, wb.in_w_lo, D, M, n_in, D, e_in, engine, f16, st))) return rc;
   EpiParams e_out{ANYLOC_EPI_LS_RESID, wb.out_b, wb.ls2, bf.x, bf.x, nullptr, D};
-  return gemm_dispatch(bf.h_hi, bf.h_lo, Hf, wb.out_w_hi, wb.out_w_lo, Hf, M, D, Hf, e_out, engine, st);
+  e_out.alpha = wb.out_alpha;
+  return gemm_dispatch(bf.h_hi, bf.h_lo, Hf, wb.out_w_hi, wb.out_w_lo, Hf, M, D, Hf, e_out, engine, f16, st);
 }
 
 extern "C" int anyloc_vit_extract(const AnylocVitCfg* cfg, const AnylocVitWeights* w, const float* img,
@@ -268,10 +284,12 @@ extern "C" int anyloc_vit_extract(const AnylocVitCfg* cfg, const AnylocVitWeight
     ANYLOC_CHECK_CUDA(cudaMemsetAsync(bf.vt_hi, 0, bf.vt_elems * sizeof(float), st));
     ANYLOC_CHECK_CUDA(cudaMemsetAsync(bf.vt_lo, 0, bf.vt_elems * sizeof(float), st));
   }
-  if ((rc = launch_im2col(img, B, H, W, P, Kp, bf.pa_hi, bf.pa_lo, st))) return rc;
+  const bool f16 = cfg->pair_dtype == ANYLOC_PAIR_F16;
+  if ((rc = launch_im2col(img, B, H, W, P, Kp, bf.pa_hi, bf.pa_lo, f16, st))) return rc;
   EpiParams e_pe{ANYLOC_EPI_BIAS, w->patch_b, nullptr, nullptr, bf.ptmp, nullptr, D};
+  e_pe.alpha = w->patch_alpha;
   if ((rc = gemm_dispatch(bf.pa_hi, bf.pa_lo, Kp, w->patch_w_hi, w->patch_w_lo, Kp, B * N, D, Kp, e_pe,
-                          gemm_engine, st))) return rc;
+                          gemm_engine, f16, st))) return rc;
   if ((rc = launch_assemble(bf.ptmp, w->cls_token, pos_embed, B, N, D, bf.x, st))) return rc;
   for (int l = 0; l < layer; ++l)
     if ((rc = vit_block(cfg, w->blocks[l], bf, B, T, gemm_engine, st))) return rc;
@@ -281,10 +299,11 @@ extern "C" int anyloc_vit_extract(const AnylocVitCfg* cfg, const AnylocVitWeight
     return launch_facet_out(bf.x, B, T, D, 0, D, use_cls, norm_descs, out, st);
   }
   // q/k/v facet: only the requested third of the qkv projection of block `layer`
-  if ((rc = launch_layernorm(bf.x, wb.ln1_w, wb.ln1_b, M, D, 1e-6f, bf.y_hi, bf.y_lo, st))) return rc;
-  const size_t woff = (size_t)facet * D * D;
+  if ((rc = launch_layernorm(bf.x, wb.ln1_w, wb.ln1_b, M, D, 1e-6f, bf.y_hi, bf.y_lo, f16, st))) return rc;
+  const size_t woff = (size_t)facet * D * D * (f16 ? 2 : 4);      // bytes: weights are __half or float
   EpiParams e_f{ANYLOC_EPI_BIAS, wb.qkv_b + (size_t)facet * D, nullptr, nullptr, bf.qkv, nullptr, D};
-  if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.qkv_w_hi + woff, wb.qkv_w_lo + woff, D, M, D, D, e_f,
-                          gemm_engine, st))) return rc;
+  e_f.alpha = wb.qkv_alpha;
+  if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, (const char*)wb.qkv_w_hi + woff,
+                          (const char*)wb.qkv_w_lo + woff, D, M, D, D, e_f, gemm_engine, f16, st))) return rc;
   return launch_facet_out(bf.qkv, B, T, D, 0, D, use_cls, norm_descs, out, st);
 }

@@ -11,7 +11,7 @@ constexpr int ATP = AT + 4;     // padded row
 
 __global__ void __launch_bounds__(256)
 attention_simt_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_lo, int T, int D,
-                      float* __restrict__ o_hi, float* __restrict__ o_lo) {
+                      float* __restrict__ o_hi, float* __restrict__ o_lo, int out_f16) {
   extern __shared__ float sm[];
   float* Qt = sm;                 // [d][row]
   float* Kt = Qt + AT * ATP;      // [d][key]
@@ -117,22 +117,30 @@ attention_simt_kernel(const float* __restrict__ qkv, const float* __restrict__ q
     int t = q0 + ty * 4 + i;
     if (t >= T) continue;
     float inv = 1.0f / l[i];
-    float4 hh, ll;
-    split_tf32(o[i][0] * inv, hh.x, ll.x); split_tf32(o[i][1] * inv, hh.y, ll.y);
-    split_tf32(o[i][2] * inv, hh.z, ll.z); split_tf32(o[i][3] * inv, hh.w, ll.w);
     size_t off = ((size_t)b * T + t) * D + (size_t)h * AT + tx * 4;
-    *reinterpret_cast<float4*>(o_hi + off) = hh;
-    *reinterpret_cast<float4*>(o_lo + off) = ll;
+    if (out_f16) {
+      __half hh[4], ll[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split_f16(o[i][j] * inv * kActScale, hh[j], ll[j]);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(o_hi) + off) = *reinterpret_cast<uint2*>(hh);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(o_lo) + off) = *reinterpret_cast<uint2*>(ll);
+    } else {
+      float4 hh, ll;
+      split_tf32(o[i][0] * inv, hh.x, ll.x); split_tf32(o[i][1] * inv, hh.y, ll.y);
+      split_tf32(o[i][2] * inv, hh.z, ll.z); split_tf32(o[i][3] * inv, hh.w, ll.w);
+      *reinterpret_cast<float4*>(o_hi + off) = hh;
+      *reinterpret_cast<float4*>(o_lo + off) = ll;
+    }
   }
 }
 
-int attention_launch(const float* qkv, const float* qkv_lo, int B, int T, int D, int heads, float* o_hi,
-                     float* o_lo, cudaStream_t st) {
+int attention_launch(const float* qkv, const float* qkv_lo, int B, int T, int D, int heads, void* o_hi,
+                     void* o_lo, bool out_f16, cudaStream_t st) {
   ANYLOC_REQUIRE(D == heads * AT, "attention: head_dim must be 64 (D=%d heads=%d)", D, heads);
   size_t smem = (size_t)4 * AT * ATP * sizeof(float);
   ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
-  attention_simt_kernel<<<dim3(cdiv(T, AT), heads, B), 256, smem, st>>>(qkv, qkv_lo, T, D, o_hi, o_lo);
+  attention_simt_kernel<<<dim3(cdiv(T, AT), heads, B), 256, smem, st>>>(qkv, qkv_lo, T, D, (float*)o_hi, (float*)o_lo, out_f16 ? 1 : 0);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }

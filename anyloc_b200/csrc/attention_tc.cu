@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(256, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_constant__ CUtensorMap tm_lo_q,
                     const __grid_constant__ CUtensorMap tm_hi_kv, const __grid_constant__ CUtensorMap tm_lo_kv,
                     const __grid_constant__ CUtensorMap tm_hi_vt, const __grid_constant__ CUtensorMap tm_lo_vt,
-                    int T, int D, float* __restrict__ o_hi, float* __restrict__ o_lo, float* __restrict__ dbg) {
+                    int T, int D, float* __restrict__ o_hi, float* __restrict__ o_lo, int out_f16,
+                    float* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                                  // [hi kb0][hi kb1][lo kb0][lo kb1], 16 KB each
@@ -335,14 +336,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_co
     if (qrow < T) {
       const float inv = 1.0f / l;
       const size_t off = ((size_t)row0 + qrow) * D + (size_t)h * HD;
-      float4* ph = reinterpret_cast<float4*>(o_hi + off);
-      float4* pl = reinterpret_cast<float4*>(o_lo + off);
+      if (out_f16) {
+        uint4* ph = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(o_hi) + off);
+        uint4* pl = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(o_lo) + off);
 #pragma unroll
-      for (int c = 0; c < HD; c += 4) {
-        float4 hh, ll;
-        split_tf32(o[c] * inv, hh.x, ll.x); split_tf32(o[c + 1] * inv, hh.y, ll.y);
-        split_tf32(o[c + 2] * inv, hh.z, ll.z); split_tf32(o[c + 3] * inv, hh.w, ll.w);
-        ph[c >> 2] = hh; pl[c >> 2] = ll;
+        for (int c = 0; c < HD; c += 8) {
+          __half hh[8], ll[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) split_f16(o[c + j] * inv * kActScale, hh[j], ll[j]);
+          ph[c >> 3] = *reinterpret_cast<uint4*>(hh); pl[c >> 3] = *reinterpret_cast<uint4*>(ll);
+        }
+      } else {
+        float4* ph = reinterpret_cast<float4*>(o_hi + off);
+        float4* pl = reinterpret_cast<float4*>(o_lo + off);
+#pragma unroll
+        for (int c = 0; c < HD; c += 4) {
+          float4 hh, ll;
+          split_tf32(o[c] * inv, hh.x, ll.x); split_tf32(o[c + 1] * inv, hh.y, ll.y);
+          split_tf32(o[c + 2] * inv, hh.z, ll.z); split_tf32(o[c + 3] * inv, hh.w, ll.w);
+          ph[c >> 2] = hh; pl[c >> 2] = ll;
+        }
       }
     }
   }
@@ -409,7 +422,7 @@ int attention_vt_pitch(int T) { return (T + 3) & ~3; }     // TMA row pitch must
 
 // vt_{hi,lo}: [B*D, Tp] with columns [T, Tp) zero (cudaMemset once; never written afterwards)
 int attention_tc_launch(const float* qkv_hi, const float* qkv_lo, const float* vt_hi, const float* vt_lo, int B, int T,
-                        int D, int heads, float* o_hi, float* o_lo, float* dbg, cudaStream_t st) {
+                        int D, int heads, void* o_hi, void* o_lo, bool out_f16, float* dbg, cudaStream_t st) {
   using namespace atc;
   ANYLOC_REQUIRE(D == heads * HD, "attention_tc: head_dim must be 64 (D=%d heads=%d)", D, heads);
   CUtensorMap hq, lq, hkv, lkv, hvt, lvt;
@@ -427,15 +440,15 @@ int attention_tc_launch(const float* qkv_hi, const float* qkv_lo, const float* v
     ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-  attention_tc_kernel<<<dim3(cdiv(T, BQ), heads, B), 256, SMEM_BYTES, st>>>(hq, lq, hkv, lkv, hvt, lvt, T, D, o_hi,
-                                                                             o_lo, dbg);
+  attention_tc_kernel<<<dim3(cdiv(T, BQ), heads, B), 256, SMEM_BYTES, st>>>(hq, lq, hkv, lkv, hvt, lvt, T, D, (float*)o_hi,
+                                                                             (float*)o_lo, out_f16 ? 1 : 0, dbg);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }
 
 // standalone: transposes V into a stream-ordered temporary first
-int attention_tc_standalone(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads, float* o_hi,
-                            float* o_lo, float* dbg, cudaStream_t st) {
+int attention_tc_standalone(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads, void* o_hi,
+                            void* o_lo, bool out_f16, float* dbg, cudaStream_t st) {
   const int Tp = attention_vt_pitch(T);
   const size_t n = (size_t)B * D * Tp;
   float* vt = nullptr;
@@ -443,7 +456,7 @@ int attention_tc_standalone(const float* qkv_hi, const float* qkv_lo, int B, int
   ANYLOC_CHECK_CUDA(cudaMemsetAsync(vt, 0, 2 * n * sizeof(float), st));
   atc::v_transpose_kernel<<<dim3(cdiv(T, 128), heads, B), 128, 0, st>>>(qkv_hi, qkv_lo, T, Tp, D, vt, vt + n);
   ANYLOC_CHECK_LAUNCH();
-  int rc = attention_tc_launch(qkv_hi, qkv_lo, vt, vt + n, B, T, D, heads, o_hi, o_lo, dbg, st);
+  int rc = attention_tc_launch(qkv_hi, qkv_lo, vt, vt + n, B, T, D, heads, o_hi, o_lo, out_f16, dbg, st);
   cudaFreeAsync(vt, st);
   return rc;
 }
@@ -453,5 +466,5 @@ int attention_tc_standalone(const float* qkv_hi, const float* qkv_lo, int B, int
 // debug entry (not part of the public ABI): dumps S/P/O-chunk of block 0 of CTA (0,0,0) into dbg[3*8192]
 extern "C" int anyloc_attention_tc_debug(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads,
                                          float* o_hi, float* o_lo, float* dbg, void* stream) {
-  return anyloc::attention_tc_standalone(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, dbg, (cudaStream_t)stream);
+  return anyloc::attention_tc_standalone(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, false, dbg, (cudaStream_t)stream);
 }

@@ -7,9 +7,22 @@ namespace anyloc {
 
 constexpr int BM = 128, BN = 128, BK = 16;
 
+template <typename T> __device__ __forceinline__ float4 load4(const T* p);
+template <> __device__ __forceinline__ float4 load4<float>(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <> __device__ __forceinline__ float4 load4<__half>(const __half* p) {
+  uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
+  float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// T = float: (hi,lo) tf32 pairs; T = __half: fp16 pairs (scaled; ep.alpha undoes the scale)
+template <typename T>
 __global__ void __launch_bounds__(256)
-gemm_simt_kernel(const float* __restrict__ a_hi, const float* __restrict__ a_lo, int lda,
-                 const float* __restrict__ b_hi, const float* __restrict__ b_lo, int ldb,
+gemm_simt_kernel(const T* __restrict__ a_hi, const T* __restrict__ a_lo, int lda,
+                 const T* __restrict__ b_hi, const T* __restrict__ b_lo, int ldb,
                  int M, int N, int K, EpiParams ep) {
   __shared__ float As[2][BK][BM + 4];
   __shared__ float Bs[2][BK][BN + 4];
@@ -33,13 +46,13 @@ gemm_simt_kernel(const float* __restrict__ a_hi, const float* __restrict__ a_lo,
       int gm = m0 + r, gn = n0 + r, gk = k0 + lk;
       float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
       if (gm < M && gk < K) {
-        va = __ldg(reinterpret_cast<const float4*>(a_hi + (size_t)gm * lda + gk));
-        if (a_lo) { float4 l = __ldg(reinterpret_cast<const float4*>(a_lo + (size_t)gm * lda + gk));
+        va = load4<T>(a_hi + (size_t)gm * lda + gk);
+        if (a_lo) { float4 l = load4<T>(a_lo + (size_t)gm * lda + gk);
                     va.x += l.x; va.y += l.y; va.z += l.z; va.w += l.w; }
       }
       if (gn < N && gk < K) {
-        vb = __ldg(reinterpret_cast<const float4*>(b_hi + (size_t)gn * ldb + gk));
-        if (b_lo) { float4 l = __ldg(reinterpret_cast<const float4*>(b_lo + (size_t)gn * ldb + gk));
+        vb = load4<T>(b_hi + (size_t)gn * ldb + gk);
+        if (b_lo) { float4 l = load4<T>(b_lo + (size_t)gn * ldb + gk);
                     vb.x += l.x; vb.y += l.y; vb.z += l.z; vb.w += l.w; }
       }
       ra[h] = va; rb[h] = vb;
@@ -98,11 +111,16 @@ gemm_simt_kernel(const float* __restrict__ a_hi, const float* __restrict__ a_lo,
   }
 }
 
-int gemm_simt_launch(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo,
-                     int ldb, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+int gemm_simt_launch(const void* a_hi, const void* a_lo, int lda, const void* b_hi, const void* b_lo,
+                     int ldb, int M, int N, int K, const EpiParams& ep, bool f16, cudaStream_t st) {
   ANYLOC_REQUIRE(K % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0, "gemm_simt: K/lda/ldb must be multiples of 4");
   dim3 grid(cdiv(N, BN), cdiv(M, BM));
-  gemm_simt_kernel<<<grid, 256, 0, st>>>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep);
+  if (f16)
+    gemm_simt_kernel<__half><<<grid, 256, 0, st>>>((const __half*)a_hi, (const __half*)a_lo, lda, (const __half*)b_hi,
+                                                   (const __half*)b_lo, ldb, M, N, K, ep);
+  else
+    gemm_simt_kernel<float><<<grid, 256, 0, st>>>((const float*)a_hi, (const float*)a_lo, lda, (const float*)b_hi,
+                                                  (const float*)b_lo, ldb, M, N, K, ep);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }

@@ -141,8 +141,8 @@ extern "C" int anyloc_topk(const float* db, const float* qu, int n_db, int n_q, 
   ANYLOC_CHECK_LAUNCH();
   normalize_rows_split_kernel<<<n_q, 256, 0, st>>>(qu, Dv, normalize, qu_hi, qu_lo, qq);
   ANYLOC_CHECK_LAUNCH();
-  int rc = anyloc_gemm_nt(qu_hi, qu_lo, Dv, db_hi, db_lo, Dv, n_q, n_db, Dv, ANYLOC_EPI_BIAS, nullptr,
-                          nullptr, nullptr, scores, nullptr, n_db, ANYLOC_GEMM_AUTO, stream);
+  int rc = anyloc_gemm_nt(qu_hi, qu_lo, Dv, db_hi, db_lo, Dv, n_q, n_db, Dv, ANYLOC_PAIR_TF32, 1.0f, ANYLOC_EPI_BIAS,
+                          nullptr, nullptr, nullptr, scores, nullptr, n_db, ANYLOC_PAIR_TF32, ANYLOC_GEMM_AUTO, stream);
   if (rc) return rc;
   topk_select_kernel<<<n_q, 1024, 0, st>>>(scores, n_db, n_db, k, metric, qq, dd, dist, idx);
   ANYLOC_CHECK_LAUNCH();

@@ -14,9 +14,28 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
   for (; i < n; i += stride) { float h, l; split_tf32(x[i], h, l); hi[i] = h; lo[i] = l; }
 }
 
+// x -> fp16 pair of scale*x
+__global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
+                                 size_t n, float scale) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) { __half h, l; split_f16(x[i] * scale, h, l); hi[i] = h; lo[i] = l; }
+}
+
+template <bool F16> struct PairOut;
+template <> struct PairOut<false> {
+  typedef float T;
+  static __device__ __forceinline__ void put(float* hi, float* lo, size_t i, float v) { float h, l; split_tf32(v, h, l); hi[i] = h; lo[i] = l; }
+};
+template <> struct PairOut<true> {
+  typedef __half T;
+  static __device__ __forceinline__ void put(__half* hi, __half* lo, size_t i, float v) { __half h, l; split_f16(v * kActScale, h, l); hi[i] = h; lo[i] = l; }
+};
+
 // img [B,3,H,W] -> patches (hi,lo) [B*gh*gw, Kp], column order (c, ky, kx) like conv weight.flatten(1)
+template <bool F16>
 __global__ void im2col_split_kernel(const float* __restrict__ img, int B, int H, int W, int P, int Kp,
-                                    float* __restrict__ hi, float* __restrict__ lo) {
+                                    typename PairOut<F16>::T* __restrict__ hi, typename PairOut<F16>::T* __restrict__ lo) {
   const int gh = H / P, gw = W / P;
   const size_t row = blockIdx.x;               // patch index
   const int b = (int)(row / (gh * gw)), pi = (int)(row % (gh * gw));
@@ -28,8 +47,7 @@ __global__ void im2col_split_kernel(const float* __restrict__ img, int B, int H,
       int ch = c / (P * P), rem = c % (P * P), ky = rem / P, kx = rem % P;
       v = __ldg(img + (((size_t)b * 3 + ch) * H + (py * P + ky)) * W + (px * P + kx));
     }
-    float h, l; split_tf32(v, h, l);
-    hi[row * Kp + c] = h; lo[row * Kp + c] = l;
+    PairOut<F16>::put(hi, lo, row * Kp + c, v);
   }
 }
 
@@ -45,11 +63,11 @@ __global__ void assemble_tokens_kernel(const float* __restrict__ patch, const fl
 }
 
 // LayerNorm over the last dim (biased variance, eps inside sqrt) -> (hi,lo). One warp per row.
-template <int MAXV>   // float4 per lane
+template <int MAXV, bool F16>   // float4 per lane
 __global__ void __launch_bounds__(256)
 layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ w,
                        const float* __restrict__ b, int M, int D, float eps,
-                       float* __restrict__ y_hi, float* __restrict__ y_lo) {
+                       typename PairOut<F16>::T* __restrict__ y_hi, typename PairOut<F16>::T* __restrict__ y_lo) {
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= M) return;
@@ -75,18 +93,25 @@ layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ w,
   const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
   const float4* w4 = reinterpret_cast<const float4*>(w);
   const float4* b4 = reinterpret_cast<const float4*>(b);
-  float4* h4 = reinterpret_cast<float4*>(y_hi + (size_t)row * D);
-  float4* l4 = reinterpret_cast<float4*>(y_lo + (size_t)row * D);
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     int d = lane + i * 32;
     if (d < D4) {
-      float4 ww = __ldg(w4 + d), bb = __ldg(b4 + d), h, l;
-      split_tf32((v[i].x - mean) * rstd * ww.x + bb.x, h.x, l.x);
-      split_tf32((v[i].y - mean) * rstd * ww.y + bb.y, h.y, l.y);
-      split_tf32((v[i].z - mean) * rstd * ww.z + bb.z, h.z, l.z);
-      split_tf32((v[i].w - mean) * rstd * ww.w + bb.w, h.w, l.w);
-      h4[d] = h; l4[d] = l;
+      float4 ww = __ldg(w4 + d), bb = __ldg(b4 + d);
+      const float y0 = (v[i].x - mean) * rstd * ww.x + bb.x, y1 = (v[i].y - mean) * rstd * ww.y + bb.y;
+      const float y2 = (v[i].z - mean) * rstd * ww.z + bb.z, y3 = (v[i].w - mean) * rstd * ww.w + bb.w;
+      if constexpr (F16) {
+        __half h[4], l[4];
+        split_f16(y0 * kActScale, h[0], l[0]); split_f16(y1 * kActScale, h[1], l[1]);
+        split_f16(y2 * kActScale, h[2], l[2]); split_f16(y3 * kActScale, h[3], l[3]);
+        reinterpret_cast<uint2*>(y_hi + (size_t)row * D)[d] = *reinterpret_cast<uint2*>(h);
+        reinterpret_cast<uint2*>(y_lo + (size_t)row * D)[d] = *reinterpret_cast<uint2*>(l);
+      } else {
+        float4 h, l;
+        split_tf32(y0, h.x, l.x); split_tf32(y1, h.y, l.y); split_tf32(y2, h.z, l.z); split_tf32(y3, h.w, l.w);
+        reinterpret_cast<float4*>(y_hi + (size_t)row * D)[d] = h;
+        reinterpret_cast<float4*>(y_lo + (size_t)row * D)[d] = l;
+      }
     }
   }
 }
@@ -140,8 +165,16 @@ int launch_split(const float* x, float* hi, float* lo, size_t n, cudaStream_t st
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }
-int launch_im2col(const float* img, int B, int H, int W, int P, int Kp, float* hi, float* lo, cudaStream_t st) {
-  im2col_split_kernel<<<B * (H / P) * (W / P), 128, 0, st>>>(img, B, H, W, P, Kp, hi, lo);
+int launch_split_f16(const float* x, void* hi, void* lo, size_t n, float scale, cudaStream_t st) {
+  int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)device_sm_count() * 16);
+  if (blocks < 1) blocks = 1;
+  split_f16_kernel<<<blocks, 256, 0, st>>>(x, (__half*)hi, (__half*)lo, n, scale);
+  ANYLOC_CHECK_LAUNCH();
+  return ANYLOC_OK;
+}
+int launch_im2col(const float* img, int B, int H, int W, int P, int Kp, void* hi, void* lo, bool f16, cudaStream_t st) {
+  if (f16) im2col_split_kernel<true><<<B * (H / P) * (W / P), 128, 0, st>>>(img, B, H, W, P, Kp, (__half*)hi, (__half*)lo);
+  else im2col_split_kernel<false><<<B * (H / P) * (W / P), 128, 0, st>>>(img, B, H, W, P, Kp, (float*)hi, (float*)lo);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }
@@ -151,13 +184,20 @@ int launch_assemble(const float* patch, const float* cls, const float* pos, int 
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }
-int launch_layernorm(const float* x, const float* w, const float* b, int M, int D, float eps, float* y_hi,
-                     float* y_lo, cudaStream_t st) {
-  ANYLOC_REQUIRE(D % 4 == 0 && D <= 2048, "layernorm: D=%d unsupported (multiple of 4, <= 2048)", D);
+template <bool F16>
+static void ln_launch(const float* x, const float* w, const float* b, int M, int D, float eps, void* y_hi, void* y_lo,
+                      cudaStream_t st) {
+  typedef typename PairOut<F16>::T T;
   int blocks = cdiv(M, 8);
-  if (D <= 512) layernorm_split_kernel<4><<<blocks, 256, 0, st>>>(x, w, b, M, D, eps, y_hi, y_lo);
-  else if (D <= 1024) layernorm_split_kernel<8><<<blocks, 256, 0, st>>>(x, w, b, M, D, eps, y_hi, y_lo);
-  else layernorm_split_kernel<16><<<blocks, 256, 0, st>>>(x, w, b, M, D, eps, y_hi, y_lo);
+  if (D <= 512) layernorm_split_kernel<4, F16><<<blocks, 256, 0, st>>>(x, w, b, M, D, eps, (T*)y_hi, (T*)y_lo);
+  else if (D <= 1024) layernorm_split_kernel<8, F16><<<blocks, 256, 0, st>>>(x, w, b, M, D, eps, (T*)y_hi, (T*)y_lo);
+  else layernorm_split_kernel<16, F16><<<blocks, 256, 0, st>>>(x, w, b, M, D, eps, (T*)y_hi, (T*)y_lo);
+}
+int launch_layernorm(const float* x, const float* w, const float* b, int M, int D, float eps, void* y_hi,
+                     void* y_lo, bool f16, cudaStream_t st) {
+  ANYLOC_REQUIRE(D % 4 == 0 && D <= 2048, "layernorm: D=%d unsupported (multiple of 4, <= 2048)", D);
+  if (f16) ln_launch<true>(x, w, b, M, D, eps, y_hi, y_lo, st);
+  else ln_launch<false>(x, w, b, M, D, eps, y_hi, y_lo, st);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }

@@ -113,11 +113,15 @@ class DinoV2ExtractFeatures:
     0..layer-1, then either the whole block `layer` ("token") or norm1 + the requested third of
     its qkv projection), which is output-identical to the reference's full forward + hook.
     Extra keyword-only arguments: `weights` (an upstream state_dict, else see
-    vit.resolve_state_dict) and `gemm_engine` ("auto" | "tc3" | "simt")."""
+    vit.resolve_state_dict), `gemm_engine` ("auto" | "tc3" | "simt") and `precision`: how fp32
+    operands are fed to the tensor cores -- "tf32x3" (tf32 (hi,lo) pairs, full fp32 exponent range)
+    or "f16x3" (fp16 (hi,lo) pairs with power-of-two scaling: same ~22-bit products on the 2x faster
+    kind::f16 path; operands beyond the fp16 range overflow to inf/NaN instead of losing accuracy
+    silently).  Both accumulate in fp32 with round-to-nearest chunk accumulation."""
 
     def __init__(self, dino_model: _DINO_V2_MODELS, layer: int, facet: _DINO_FACETS = "token",
                  use_cls=False, norm_descs=True, device: str = "cpu", *, weights=None,
-                 gemm_engine: str = "auto") -> None:
+                 gemm_engine: str = "auto", precision: str = None) -> None:
         self.vit_type: str = dino_model
         self.device = torch.device(device)
         dev = _lib.require_cuda(self.device)
@@ -125,7 +129,12 @@ class DinoV2ExtractFeatures:
             raise ValueError(f"facet must be one of {sorted(_lib.FACET)}, got {facet!r}")
         sd = weights if weights is not None else _vit.resolve_state_dict(dino_model, dev)
         # only blocks 0..layer are ever executed (early exit), so only those are uploaded
-        self.dino_model = _vit.VitWeights(dino_model, sd, dev, depth=layer + 1)
+        precision = precision or os.environ.get("ANYLOC_B200_PRECISION", "tf32x3")
+        if precision not in ("tf32x3", "f16x3"):
+            raise ValueError(f"precision must be 'tf32x3' or 'f16x3', got {precision!r}")
+        self.precision = precision
+        self.dino_model = _vit.VitWeights(dino_model, sd, dev, depth=layer + 1,
+                                          pair="f16" if precision == "f16x3" else "tf32")
         self.layer: int = layer
         self.facet = facet
         self.use_cls = use_cls

@@ -96,10 +96,13 @@ def interpolate_pos_embed(pos_embed, gh, gw):
 class VitWeights:
     """Device-resident, kernel-ready weights of one DINOv2 backbone (blocks 0..depth-1)."""
 
-    def __init__(self, name, state_dict, device, depth=None):
+    def __init__(self, name, state_dict, device, depth=None, pair="tf32"):
         if name not in ARCHS:
             raise ValueError(f"unknown DINOv2 model {name!r}; expected one of {sorted(ARCHS)}")
+        if pair not in _lib.PAIR:
+            raise ValueError(f"pair must be one of {sorted(_lib.PAIR)}, got {pair!r}")
         self.name = name
+        self.pair = pair
         self.device = _lib.require_cuda(device)
         self.dim, full_depth, self.heads, self.ffn_kind = ARCHS[name]
         n_blocks = 1 + max([int(k.split(".")[1]) for k in state_dict if k.startswith("blocks.")], default=-1)
@@ -115,13 +118,27 @@ class VitWeights:
             return t.detach().to(device=dev, dtype=torch.float32).contiguous()
 
         def split(t):
+            """-> (hi, lo, alpha): the kernel-ready pair of a weight matrix and the accumulator scale
+            1/(s_act*s_w) its GEMM epilogue applies (1.0 for tf32 pairs)."""
             t = f32(t)
-            hi, lo = torch.empty_like(t), torch.empty_like(t)
             with torch.cuda.device(dev):
-                _lib.check(lib.anyloc_split_tf32(_lib.ptr(t), _lib.ptr(hi), _lib.ptr(lo), t.numel(),
-                                                 _lib.stream_ptr()), "split_tf32")
+                if pair == "tf32":
+                    hi, lo = torch.empty_like(t), torch.empty_like(t)
+                    _lib.check(lib.anyloc_split_tf32(_lib.ptr(t), _lib.ptr(hi), _lib.ptr(lo), t.numel(),
+                                                     _lib.stream_ptr()), "split_tf32")
+                    alpha = 1.0
+                else:
+                    # per-tensor power-of-two scale: largest |w| lands in [8192, 16384) -- far from fp16's 65504
+                    # ceiling, and typical weights sit well inside the normal range (hi+lo keeps ~22 bits)
+                    amax = float(t.abs().max().item())
+                    s_w = 2.0 ** math.floor(math.log2(16384.0 / amax)) if amax > 0 else 1.0
+                    hi = torch.empty(t.shape, dtype=torch.float16, device=dev)
+                    lo = torch.empty(t.shape, dtype=torch.float16, device=dev)
+                    _lib.check(lib.anyloc_split_f16(_lib.ptr(t), _lib.ptr(hi), _lib.ptr(lo), t.numel(),
+                                                    C.c_float(s_w), _lib.stream_ptr()), "split_f16")
+                    alpha = 1.0 / (_lib.ACT_SCALE * s_w)
             self._keep += [hi, lo]
-            return hi, lo
+            return hi, lo, alpha
 
         def keep(t):
             t = f32(t)
@@ -132,6 +149,7 @@ class VitWeights:
         pw = f32(sd["patch_embed.proj.weight"]).reshape(self.dim, -1)
         pw = F.pad(pw, (0, self.patch_k - pw.shape[1]))
         self.patch_w = split(pw)
+        patch_alpha = self.patch_w[2]
         self.patch_b = keep(sd["patch_embed.proj.bias"])
         self.cls_token = keep(sd["cls_token"].reshape(-1))
         self.pos_embed = sd["pos_embed"].detach().float().cpu()
@@ -144,9 +162,9 @@ class VitWeights:
                 setattr(blk, field, t.data_ptr())
 
             put("ln1_w", keep(sd[p + "norm1.weight"])); put("ln1_b", keep(sd[p + "norm1.bias"]))
-            hi, lo = split(sd[p + "attn.qkv.weight"]); put("qkv_w_hi", hi); put("qkv_w_lo", lo)
+            hi, lo, blk.qkv_alpha = split(sd[p + "attn.qkv.weight"]); put("qkv_w_hi", hi); put("qkv_w_lo", lo)
             put("qkv_b", keep(sd[p + "attn.qkv.bias"]))
-            hi, lo = split(sd[p + "attn.proj.weight"]); put("proj_w_hi", hi); put("proj_w_lo", lo)
+            hi, lo, blk.proj_alpha = split(sd[p + "attn.proj.weight"]); put("proj_w_hi", hi); put("proj_w_lo", lo)
             put("proj_b", keep(sd[p + "attn.proj.bias"]))
             put("ls1", keep(sd[p + "ls1.gamma"]))
             put("ln2_w", keep(sd[p + "norm2.weight"])); put("ln2_b", keep(sd[p + "norm2.bias"]))
@@ -161,12 +179,14 @@ class VitWeights:
                 w_in = sd[p + "mlp.w12.weight"].detach().cpu()[perm]
                 b_in = sd[p + "mlp.w12.bias"].detach().cpu()[perm]
                 w_out, b_out = sd[p + "mlp.w3.weight"], sd[p + "mlp.w3.bias"]
-            hi, lo = split(w_in); put("in_w_hi", hi); put("in_w_lo", lo); put("in_b", keep(b_in))
-            hi, lo = split(w_out); put("out_w_hi", hi); put("out_w_lo", lo); put("out_b", keep(b_out))
+            hi, lo, blk.in_alpha = split(w_in); put("in_w_hi", hi); put("in_w_lo", lo); put("in_b", keep(b_in))
+            hi, lo, blk.out_alpha = split(w_out); put("out_w_hi", hi); put("out_w_lo", lo); put("out_b", keep(b_out))
             put("ls2", keep(sd[p + "ls2.gamma"]))
-        self.cfg = _lib.VitCfg(self.dim, self.depth, self.heads, _lib.FFN[self.ffn_kind], self.hidden, PATCH)
+        self.cfg = _lib.VitCfg(self.dim, self.depth, self.heads, _lib.FFN[self.ffn_kind], self.hidden, PATCH,
+                               _lib.PAIR[pair])
         self.struct = _lib.VitWeightsStruct(self.patch_w[0].data_ptr(), self.patch_w[1].data_ptr(),
-                                            self.patch_b.data_ptr(), self.cls_token.data_ptr(), self.blocks)
+                                            self.patch_b.data_ptr(), self.cls_token.data_ptr(), self.blocks,
+                                            patch_alpha)
         torch.cuda.synchronize(dev)
 
     def pos_for(self, gh, gw):

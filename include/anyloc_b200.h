@@ -52,10 +52,15 @@ extern "C" {
 #define ANYLOC_EPI_SWIGLU_SPLIT 3  /* cols (2j,2j+1)=(x1,x2); v=silu(x1)*x2 -> (hi,lo)[j] */
 #define ANYLOC_EPI_LS_RESID 4      /* out = resid + gamma * (acc + bias)                 */
 #define ANYLOC_EPI_QKV_SPLIT 5     /* internal (ViT): q,k thirds -> (hi,lo); v third -> per-head transposed (hi,lo) */
+/* GEMM input / SPLIT-output pair formats: x is carried as (hi, lo) with hi + lo ~ x to ~22 bits */
+#define ANYLOC_PAIR_TF32 0         /* two fp32 arrays: hi = rna_tf32(x), lo = x - hi (kind::tf32 tensor path)          */
+#define ANYLOC_PAIR_F16 1          /* two fp16 arrays of s*x (s power of two): hi = fp16(s x), lo = fp16(s x - hi);
+                                      kind::f16 tensor path (2x rate); activations use s = 8, the epilogue's alpha
+                                      undoes s_A*s_B.  Values beyond the fp16 range (|s x| > 65504) overflow. */
 /* GEMM engines */
 #define ANYLOC_GEMM_AUTO 0
 #define ANYLOC_GEMM_SIMT 1         /* fp32 FFMA (validation / odd shapes)               */
-#define ANYLOC_GEMM_TC3 2          /* tcgen05 kind::tf32, 3-term split (fp32-equivalent) */
+#define ANYLOC_GEMM_TC3 2          /* tcgen05, 3-term split (kind::tf32 or kind::f16 by pair format) */
 
 const char* anyloc_last_error(void);
 int anyloc_version(void);
@@ -119,6 +124,7 @@ typedef struct {
   int ffn_kind;    /* ANYLOC_FFN_* */
   int ffn_hidden;  /* 4*D (mlp) or 4096-style fused hidden (swiglu) */
   int patch;       /* 14 */
+  int pair_dtype;  /* ANYLOC_PAIR_*: format of the weight pairs and of all GEMM-input activations */
 } AnylocVitCfg;
 
 /* Per-block device pointers.  Matrices are [out,in] row-major like nn.Linear.weight, supplied as
@@ -126,20 +132,23 @@ typedef struct {
  * interleaved (row 2j = w12[j], row 2j+1 = w12[hidden+j]) and b_in likewise. */
 typedef struct {
   const float *ln1_w, *ln1_b;
-  const float *qkv_w_hi, *qkv_w_lo, *qkv_b;     /* [3D,D], [3D] */
-  const float *proj_w_hi, *proj_w_lo, *proj_b;  /* [D,D],  [D]  */
-  const float *ls1;                             /* [D] LayerScale gamma */
+  const void *qkv_w_hi, *qkv_w_lo; const float *qkv_b;     /* [3D,D], [3D] */
+  const void *proj_w_hi, *proj_w_lo; const float *proj_b;  /* [D,D],  [D]  */
+  const float *ls1;                                        /* [D] LayerScale gamma */
   const float *ln2_w, *ln2_b;
-  const float *in_w_hi, *in_w_lo, *in_b;        /* fc1 [4D,D] or interleaved w12 [2H,D] */
-  const float *out_w_hi, *out_w_lo, *out_b;     /* fc2 [D,4D] or w3 [D,H] */
+  const void *in_w_hi, *in_w_lo; const float *in_b;        /* fc1 [4D,D] or interleaved w12 [2H,D] */
+  const void *out_w_hi, *out_w_lo; const float *out_b;     /* fc2 [D,4D] or w3 [D,H] */
   const float *ls2;
+  /* accumulator scales 1/(s_act * s_weight) of the four GEMMs (1.0 for tf32 pairs) */
+  float qkv_alpha, proj_alpha, in_alpha, out_alpha;
 } AnylocVitBlock;
 
 typedef struct {
-  const float *patch_w_hi, *patch_w_lo; /* [D, Kp] conv weight flattened (c,ky,kx), zero padded to Kp */
+  const void *patch_w_hi, *patch_w_lo;  /* [D, Kp] conv weight flattened (c,ky,kx), zero padded to Kp */
   const float *patch_b;                 /* [D] */
   const float *cls_token;               /* [D] */
   const AnylocVitBlock* blocks;         /* HOST array [depth] of device pointers */
+  float patch_alpha;
 } AnylocVitWeights;
 
 /* padded patch-embed reduction length (3*14*14=588 -> multiple of 32) */
@@ -155,16 +164,18 @@ int anyloc_vit_extract(const AnylocVitCfg* cfg, const AnylocVitWeights* w_host, 
 /* ------------------------------------------- building blocks (exported for parity tests)
  * C[M,N] = (A_hi+A_lo)[M,K] . (B_hi+B_lo)[N,K]^T with epilogue; *_lo nullable (treated as 0).
  * lda/ldb/ldo in elements.  out_lo/bias/gamma/resid per epilogue. */
-int anyloc_gemm_nt(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo,
-                   int ldb, int M, int N, int K, int epilogue, const float* bias, const float* gamma,
-                   const float* resid, float* out, float* out_lo, int ldo, int engine, void* stream);
+int anyloc_gemm_nt(const void* a_hi, const void* a_lo, int lda, const void* b_hi, const void* b_lo,
+                   int ldb, int M, int N, int K, int in_dtype, float alpha, int epilogue, const float* bias,
+                   const float* gamma, const float* resid, void* out, void* out_lo, int ldo, int out_dtype,
+                   int engine, void* stream);
 int anyloc_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream);
+int anyloc_split_f16(const float* x, void* hi, void* lo, size_t n, float scale, void* stream);
 int anyloc_layernorm_split(const float* x, const float* w, const float* b, int M, int D, float eps,
-                           float* y_hi, float* y_lo, void* stream);
+                           void* y_hi, void* y_lo, int out_dtype, void* stream);
 /* softmax(q k^T / 8) v per head (head_dim 64).  qkv (hi,lo) pairs [B,T,3D] ([q|k|v] thirds); qkv_lo may
  * be NULL for the SIMT engine (plain fp32 input).  -> o (hi,lo) [B,T,D].  engine: ANYLOC_GEMM_*. */
 int anyloc_attention(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads,
-                     float* o_hi, float* o_lo, int engine, void* stream);
+                     void* o_hi, void* o_lo, int out_dtype, int engine, void* stream);
 int anyloc_l2_normalize_rows(const float* x, int64_t rows, int D, int64_t ld_in, float* y, void* stream);
 
 #ifdef __cplusplus

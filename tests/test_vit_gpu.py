@@ -11,7 +11,7 @@ from tests.util import load_cases, rel_inf
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
-ENGINES = ["simt", "auto"]
+ENGINES = [("simt", "tf32x3"), ("auto", "tf32x3"), ("auto", "f16x3"), ("simt", "f16x3")]
 
 
 @pytest.fixture(scope="module")
@@ -24,17 +24,19 @@ def u(cuda):
 @pytest.mark.parametrize("tag,name,depth,layer", [("vits14_l9_56x70", "dinov2_vits14", None, 9),
                                                    ("vitg14_d2_l1_42x42", "dinov2_vitg14", 2, 1)])
 def test_extract_golden(u, engine, tag, name, depth, layer):
+    engine, precision = engine
     g = load_cases("extract.npz")[tag]
     sd = dr.perturb(dr.build(name, seed=0, depth_override=depth), seed=1).state_dict()
     img = torch.from_numpy(g["img"]).cuda()
     for facet in ("value", "key", "query", "token"):
-        ext = u.DinoV2ExtractFeatures(name, layer, facet, device="cuda", weights=sd, gemm_engine=engine)
+        ext = u.DinoV2ExtractFeatures(name, layer, facet, device="cuda", weights=sd, gemm_engine=engine,
+                                      precision=precision)
         out = ext(img)
         assert out.is_cuda and out.shape == g[facet].shape
         err = rel_inf(out.cpu(), g[facet])
         assert err < TOL, (facet, err)
     ext = u.DinoV2ExtractFeatures(name, layer, "value", use_cls=True, norm_descs=False, device="cuda", weights=sd,
-                                  gemm_engine=engine)
+                                  gemm_engine=engine, precision=precision)
     err = rel_inf(ext(img).cpu(), g["value_cls_nonorm"])
     assert err < TOL, err
 
@@ -45,17 +47,32 @@ def test_extract_golden(u, engine, tag, name, depth, layer):
                                                     ("dinov2_vitl14", 3, 2, 518, 518, 1),
                                                     ("dinov2_vitg14", 3, 2, 322, 322, 2)])
 def test_extract_vs_oracle(u, engine, name, depth, layer, H, W, B):
+    engine, precision = engine
     model = dr.perturb(dr.build(name, seed=0, depth_override=depth), seed=2)
     img = torch.randn(B, 3, H, W, generator=torch.Generator().manual_seed(1234))
     for facet in ("value", "token"):
         ref = ao.extract_features(model, img, layer, facet)
         ext = u.DinoV2ExtractFeatures(name, layer, facet, device="cuda", weights=model.state_dict(),
-                                      gemm_engine=engine)
+                                      gemm_engine=engine, precision=precision)
         out = ext(img.cuda())
         err = rel_inf(out.cpu(), ref)
         assert err < TOL, (name, facet, err)
     with pytest.raises(ValueError):
         ext(torch.randn(1, 3, 225, 224, device="cuda"))
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "f16x3"])
+@pytest.mark.parametrize("name,depth,layer,HW", [("dinov2_vitg14", 32, 31, 98), ("dinov2_vitl14", 21, 20, 126)])
+def test_extract_full_depth(u, precision, name, depth, layer, HW):
+    """The depth of BASELINE configs 2 / 5 (ViT-G layer 31, ViT-L layer 20) at a reduced resolution the CPU
+    oracle finishes in seconds: error accumulation over all blocks stays within 1e-4."""
+    model = dr.build(name, seed=0, depth_override=depth)
+    img = torch.randn(2, 3, HW, HW, generator=torch.Generator().manual_seed(1234))
+    ref = ao.extract_features(model, img, layer, "value")
+    ext = u.DinoV2ExtractFeatures(name, layer, "value", device="cuda", weights=model.state_dict(), precision=precision)
+    err = rel_inf(ext(img.cuda()).cpu(), ref)
+    assert err < TOL, (name, precision, err)
+    print(f"full-depth {name} L{layer} {precision}: rel err {err:.2e}")
 
 
 def test_extractor_errors(u):
