@@ -8,7 +8,9 @@
 // MN-major tf32 operand in the plain 128B swizzle yields zeros -- so V is made K-major at the source.)
 // Output is the (hi,lo) pair [B*T, D] that feeds the `proj` GEMM.
 // One CTA per (128-query tile, head, image), 256 threads:
-//   warp 0   : TMA producer -- Q tile once, then a 2-stage ring of 64-key blocks {K_hi,K_lo,V_hi,V_lo}
+//   (persistent: CTAs stride over the (q-tile, head, image) work items so TMEM allocation, barrier init and
+//    load latency are paid once and the producer/MMA warps run ahead into the next item)
+//   warp 0   : TMA producer -- Q tile per item, then a 2-stage ring of 64-key blocks {K_hi,K_lo,Vt_hi,Vt_lo}
 //   warp 1   : MMA issuer   -- S_j = Q K_j^T  (A,B from smem, K-major, M128 x N64 x K8, 24 UMMAs)
 //                              O_j = P_j V_j  (A = P from TMEM, B = V^T tile from smem K-major, 24 UMMAs)
 //   warp 2   : TMEM allocator (S double-buffered 2x64, P_hi 64, P_lo 64, O chunk 64 columns)
@@ -127,29 +129,28 @@ __global__ void __launch_bounds__(256, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_constant__ CUtensorMap tm_lo_q,
                     const __grid_constant__ CUtensorMap tm_hi_kv, const __grid_constant__ CUtensorMap tm_lo_kv,
                     const __grid_constant__ CUtensorMap tm_hi_vt, const __grid_constant__ CUtensorMap tm_lo_vt,
-                    int T, int D, float* __restrict__ o_hi, float* __restrict__ o_lo, int out_f16,
+                    int B, int T, int D, float* __restrict__ o_hi, float* __restrict__ o_lo, int out_f16,
                     float* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                                  // [hi kb0][hi kb1][lo kb0][lo kb1], 16 KB each
-  uint8_t* sKV = smem + Q_BYTES;                       // STAGES x {K_hi0,K_hi1,K_lo0,K_lo1,V_hi0,V_hi1,V_lo0,V_lo1}
+  uint8_t* sKV = smem + Q_BYTES;                       // STAGES x {K_hi0,K_hi1,K_lo0,K_lo1,Vt_hi0,Vt_hi1,Vt_lo0,Vt_lo1}
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + STAGES * STAGE_BYTES);
-  uint64_t* q_full = bars;             // 1
-  uint64_t* kv_full = bars + 1;        // [STAGES]
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* q_empty = bars + 1;            // 1
+  uint64_t* kv_full = bars + 2;            // [STAGES]
   uint64_t* kv_empty = kv_full + STAGES;   // [STAGES]
   uint64_t* s_full = kv_empty + STAGES;    // [2]
-  uint64_t* p_full = s_full + 2;       // 1
-  uint64_t* o_full = p_full + 1;       // 1
-  uint64_t* dbg_full = o_full + 1;     // debug only
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dbg_full + 1);
+  uint64_t* p_full = s_full + 2;           // 1
+  uint64_t* o_full = p_full + 1;           // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int heads = D / HD;
+  const int q_tiles = (T + BQ - 1) / BQ;
   const int nblk = (T + BKV - 1) / BKV;
-  const int row0 = b * T;                    // first token row of this image in the [B*T, 3D] matrices
-  const int colq = h * HD, colk = D + h * HD;
-  const int vrow = (b * (D / HD) + h) * HD;  // first row of this head's V^T in vt[(b*heads+h)*64 + d][t]
+  const int total = q_tiles * heads * B;       // work items; persistent CTAs stride over them
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi_q) : "memory");
@@ -160,12 +161,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo_vt) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(smem_u32(q_full), 1);
+    mbar_init(smem_u32(q_full), 1); mbar_init(smem_u32(q_empty), 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(kv_full + s), 1); mbar_init(smem_u32(kv_empty + s), 1); }
     mbar_init(smem_u32(s_full), 1); mbar_init(smem_u32(s_full + 1), 1);
     mbar_init(smem_u32(p_full), 4);          // one arrive per softmax warp
     mbar_init(smem_u32(o_full), 1);
-    mbar_init(smem_u32(dbg_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -178,31 +178,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
+  // All three roles walk the same sequence of work items and of key blocks; g counts key blocks globally so the
+  // ring / double-buffer parities carry over from one work item to the next.
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------ TMA producer
-      const uint32_t qb = smem_u32(q_full);
-      mbar_expect_tx(qb, Q_BYTES);
-      tma_load_2d(smem_u32(sQ + 0 * Q_HALF), &tm_hi_q, qb, colq, row0 + q0);
-      tma_load_2d(smem_u32(sQ + 1 * Q_HALF), &tm_hi_q, qb, colq + 32, row0 + q0);
-      tma_load_2d(smem_u32(sQ + 2 * Q_HALF), &tm_lo_q, qb, colq, row0 + q0);
-      tma_load_2d(smem_u32(sQ + 3 * Q_HALF), &tm_lo_q, qb, colq + 32, row0 + q0);
-      int stage = 0; uint32_t phase = 0;
-      for (int j = 0; j < nblk; ++j) {
-        mbar_wait(smem_u32(kv_empty + stage), phase ^ 1);
-        const uint32_t fb = smem_u32(kv_full + stage);
-        mbar_expect_tx(fb, STAGE_BYTES);
-        const uint32_t sb = smem_u32(sKV + stage * STAGE_BYTES);
-        const int r = row0 + j * BKV;
-        tma_load_2d(sb + 0 * KV_BOX, &tm_hi_kv, fb, colk, r);
-        tma_load_2d(sb + 1 * KV_BOX, &tm_hi_kv, fb, colk + 32, r);
-        tma_load_2d(sb + 2 * KV_BOX, &tm_lo_kv, fb, colk, r);
-        tma_load_2d(sb + 3 * KV_BOX, &tm_lo_kv, fb, colk + 32, r);
-        tma_load_2d(sb + 4 * KV_BOX, &tm_hi_vt, fb, j * BKV, vrow);         // V^T [64 d x 32 keys] k-block 0
-        tma_load_2d(sb + 5 * KV_BOX, &tm_hi_vt, fb, j * BKV + 32, vrow);    //                      k-block 1
-        tma_load_2d(sb + 6 * KV_BOX, &tm_lo_vt, fb, j * BKV, vrow);
-        tma_load_2d(sb + 7 * KV_BOX, &tm_lo_vt, fb, j * BKV + 32, vrow);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      int g = 0, it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const int qt = w % q_tiles, h = (w / q_tiles) % heads, b = w / (q_tiles * heads);
+        const int row0 = b * T, colq = h * HD, colk = D + h * HD, vrow = (b * heads + h) * HD;
+        mbar_wait(smem_u32(q_empty), (uint32_t)((it & 1) ^ 1));     // previous tile's S MMAs are done with Q
+        const uint32_t qb = smem_u32(q_full);
+        mbar_expect_tx(qb, Q_BYTES);
+        tma_load_2d(smem_u32(sQ + 0 * Q_HALF), &tm_hi_q, qb, colq, row0 + qt * BQ);
+        tma_load_2d(smem_u32(sQ + 1 * Q_HALF), &tm_hi_q, qb, colq + 32, row0 + qt * BQ);
+        tma_load_2d(smem_u32(sQ + 2 * Q_HALF), &tm_lo_q, qb, colq, row0 + qt * BQ);
+        tma_load_2d(smem_u32(sQ + 3 * Q_HALF), &tm_lo_q, qb, colq + 32, row0 + qt * BQ);
+        for (int j = 0; j < nblk; ++j, ++g) {
+          const int stage = g % STAGES;
+          mbar_wait(smem_u32(kv_empty + stage), (uint32_t)(((g / STAGES) & 1) ^ 1));
+          const uint32_t fb = smem_u32(kv_full + stage);
+          mbar_expect_tx(fb, STAGE_BYTES);
+          const uint32_t sb = smem_u32(sKV + stage * STAGE_BYTES);
+          const int r = row0 + j * BKV;
+          tma_load_2d(sb + 0 * KV_BOX, &tm_hi_kv, fb, colk, r);
+          tma_load_2d(sb + 1 * KV_BOX, &tm_hi_kv, fb, colk + 32, r);
+          tma_load_2d(sb + 2 * KV_BOX, &tm_lo_kv, fb, colk, r);
+          tma_load_2d(sb + 3 * KV_BOX, &tm_lo_kv, fb, colk + 32, r);
+          tma_load_2d(sb + 4 * KV_BOX, &tm_hi_vt, fb, j * BKV, vrow);         // V^T [64 d x 32 keys] k-block 0
+          tma_load_2d(sb + 5 * KV_BOX, &tm_hi_vt, fb, j * BKV + 32, vrow);    //                      k-block 1
+          tma_load_2d(sb + 6 * KV_BOX, &tm_lo_vt, fb, j * BKV, vrow);
+          tma_load_2d(sb + 7 * KV_BOX, &tm_lo_vt, fb, j * BKV + 32, vrow);
+        }
       }
     }
   } else if (warp == 1) {
@@ -214,10 +221,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_co
       constexpr uint32_t idesc_pv = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HD >> 3) << 17) |
                                     ((uint32_t)(BQ >> 4) << 24);
       const uint32_t q_base = smem_u32(sQ);
-      auto issue_s = [&](int j) {
-        const int st = j % STAGES;
+      auto issue_s = [&](int gb) {
+        const int st = gb % STAGES;
+        mbar_wait(smem_u32(kv_full + st), (uint32_t)((gb / STAGES) & 1));
+        tc_fence_after();
         const uint32_t kb = smem_u32(sKV + st * STAGE_BYTES);
-        const uint32_t d = tmem_base + COL_S + (uint32_t)((j & 1) * BKV);
+        const uint32_t d = tmem_base + COL_S + (uint32_t)((gb & 1) * BKV);
 #pragma unroll
         for (int k = 0; k < HD / 8; ++k) {                   // 8 k-steps over the head dim
           const uint32_t off = (uint32_t)((k >> 2) * Q_HALF + (k & 3) * 32);
@@ -228,133 +237,151 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_co
           umma_ss(d, a_lo, b_hi, idesc_s, 1u);
           umma_ss(d, a_hi, b_lo, idesc_s, 1u);
         }
-        umma_commit(smem_u32(s_full + (j & 1)));
+        umma_commit(smem_u32(s_full + (gb & 1)));
       };
-      mbar_wait(smem_u32(q_full), 0);
-      mbar_wait(smem_u32(kv_full + 0), 0);
-      tc_fence_after();
-      issue_s(0);
-      for (int j = 0; j < nblk; ++j) {
-        const int st = j % STAGES;
-        if (j + 1 < nblk) {
-          mbar_wait(smem_u32(kv_full + ((j + 1) % STAGES)), (uint32_t)(((j + 1) / STAGES) & 1));
-          tc_fence_after();
-          issue_s(j + 1);          // S buffer (j+1)&1 was consumed before P_{j-1} was published (program order)
-        }
-        mbar_wait(smem_u32(p_full), (uint32_t)(j & 1));
+      int g = 0, it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        mbar_wait(smem_u32(q_full), (uint32_t)(it & 1));
         tc_fence_after();
-        const uint32_t vb = smem_u32(sKV + st * STAGE_BYTES) + 4 * KV_BOX;
-        const uint32_t d = tmem_base + COL_O;
+        issue_s(g);
+        if (nblk == 1) umma_commit(smem_u32(q_empty));
+        for (int j = 0; j < nblk; ++j) {
+          const int gb = g + j, st = gb % STAGES;
+          if (j + 1 < nblk) {
+            issue_s(gb + 1);       // S buffer (gb+1)&1 was consumed before P_{gb-1} was published (program order)
+            if (j + 2 == nblk) umma_commit(smem_u32(q_empty));   // last S of this tile issued: Q may be reloaded
+          }
+          mbar_wait(smem_u32(p_full), (uint32_t)(gb & 1));
+          tc_fence_after();
+          const uint32_t vb = smem_u32(sKV + st * STAGE_BYTES) + 4 * KV_BOX;
+          const uint32_t d = tmem_base + COL_O;
 #pragma unroll
-        for (int k = 0; k < BKV / 8; ++k) {                   // 8 k-steps over the 64 keys
-          const uint32_t voff = (uint32_t)((k >> 2) * KV_BOX + (k & 3) * 32);
-          const uint64_t v_hi = desc_kmajor(vb + voff), v_lo = desc_kmajor(vb + 2 * KV_BOX + voff);
-          const uint32_t p_hi = tmem_base + COL_PHI + (uint32_t)(k * 8), p_lo = tmem_base + COL_PLO + (uint32_t)(k * 8);
-          umma_ts(d, p_hi, v_hi, idesc_pv, k != 0);
-          umma_ts(d, p_lo, v_hi, idesc_pv, 1u);
-          umma_ts(d, p_hi, v_lo, idesc_pv, 1u);
+          for (int k = 0; k < BKV / 8; ++k) {                   // 8 k-steps over the 64 keys
+            const uint32_t voff = (uint32_t)((k >> 2) * KV_BOX + (k & 3) * 32);
+            const uint64_t v_hi = desc_kmajor(vb + voff), v_lo = desc_kmajor(vb + 2 * KV_BOX + voff);
+            const uint32_t p_hi = tmem_base + COL_PHI + (uint32_t)(k * 8), p_lo = tmem_base + COL_PLO + (uint32_t)(k * 8);
+            umma_ts(d, p_hi, v_hi, idesc_pv, k != 0);
+            umma_ts(d, p_lo, v_hi, idesc_pv, 1u);
+            umma_ts(d, p_hi, v_lo, idesc_pv, 1u);
+          }
+          umma_commit(smem_u32(o_full));
+          umma_commit(smem_u32(kv_empty + st));     // K_j / V_j no longer needed once these MMAs retire
         }
-        umma_commit(smem_u32(o_full));
-        umma_commit(smem_u32(kv_empty + st));     // K_j / V_j no longer needed once these MMAs retire
+        g += nblk;
       }
     }
   } else if (warp >= 4) {
     // -------------------------------------------------- softmax + RN accumulation (thread = query row)
     const int qd = warp & 3;
-    const int qrow = q0 + qd * 32 + lane;             // token index inside the image
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
     const float kScale = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
-    float m = -INFINITY, l = 0.f;
-    float o[HD];
+    int g = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int qt = w % q_tiles, h = (w / q_tiles) % heads, b = w / (q_tiles * heads);
+      const int qrow = qt * BQ + qd * 32 + lane;          // token index inside the image
+      const bool dump = dbg != nullptr && w == 0;
+      float m = -INFINITY, l = 0.f;
+      float o[HD];
 #pragma unroll
-    for (int c = 0; c < HD; ++c) o[c] = 0.f;
-    for (int j = 0; j < nblk; ++j) {
-      mbar_wait(smem_u32(s_full + (j & 1)), (uint32_t)((j >> 1) & 1));
-      tc_fence_after();
-      float s[BKV];
-      tmem_ld32(lane_addr + COL_S + (uint32_t)((j & 1) * BKV), s);
-      tmem_ld32(lane_addr + COL_S + (uint32_t)((j & 1) * BKV + 32), s + 32);
-      float mx = m;
-#pragma unroll
-      for (int c = 0; c < BKV; ++c) {
-        s[c] = (j * BKV + c < T) ? s[c] * kScale : -INFINITY;
-        mx = fmaxf(mx, s[c]);
-      }
-      const bool dump = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-      if (dump && j == 0) for (int c = 0; c < BKV; ++c) dbg[(qd * 32 + lane) * 64 + c] = s[c];
-      const float alpha = exp2f(m - mx);                // 0 on the first block (m = -inf, mx finite)
-      float rs = 0.f;
-#pragma unroll
-      for (int c = 0; c < BKV; ++c) { s[c] = exp2f(s[c] - mx); rs += s[c]; }
-      l = l * alpha + rs;
-      m = mx;
-      if (dump && j == 0) for (int c = 0; c < BKV; ++c) dbg[8192 + (qd * 32 + lane) * 64 + c] = s[c];
-      if (j > 0) {                                      // fold in O_{j-1} (RN), frees the P and O buffers
-        mbar_wait(smem_u32(o_full), (uint32_t)((j - 1) & 1));
+      for (int c = 0; c < HD; ++c) o[c] = 0.f;
+      for (int j = 0; j < nblk; ++j) {
+        const int gb = g + j;
+        mbar_wait(smem_u32(s_full + (gb & 1)), (uint32_t)((gb >> 1) & 1));
         tc_fence_after();
+        float s[BKV];
+        tmem_ld32(lane_addr + COL_S + (uint32_t)((gb & 1) * BKV), s);
+        tmem_ld32(lane_addr + COL_S + (uint32_t)((gb & 1) * BKV + 32), s + 32);
+        if (j == nblk - 1) {                              // only the last block can hold keys >= T
+#pragma unroll
+          for (int c = 0; c < BKV; ++c) if (j * BKV + c >= T) s[c] = -INFINITY;
+        }
+        float mx0 = m, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < BKV; c += 4) {
+          s[c] *= kScale; s[c + 1] *= kScale; s[c + 2] *= kScale; s[c + 3] *= kScale;
+          mx0 = fmaxf(mx0, s[c]); mx1 = fmaxf(mx1, s[c + 1]); mx2 = fmaxf(mx2, s[c + 2]); mx3 = fmaxf(mx3, s[c + 3]);
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        if (dump && j == 0) for (int c = 0; c < BKV; ++c) dbg[(qd * 32 + lane) * 64 + c] = s[c];
+        const float alpha = exp2f(m - mx);                // 0 on the first block (m = -inf, mx finite)
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < BKV; c += 4) {
+          s[c] = exp2f(s[c] - mx); s[c + 1] = exp2f(s[c + 1] - mx);
+          s[c + 2] = exp2f(s[c + 2] - mx); s[c + 3] = exp2f(s[c + 3] - mx);
+          r0 += s[c]; r1 += s[c + 1]; r2 += s[c + 2]; r3 += s[c + 3];
+        }
+        l = l * alpha + ((r0 + r1) + (r2 + r3));
+        m = mx;
+        if (dump && j == 0) for (int c = 0; c < BKV; ++c) dbg[8192 + (qd * 32 + lane) * 64 + c] = s[c];
+        if (j > 0) {                                      // fold in O_{j-1} (RN), frees the P and O buffers
+          mbar_wait(smem_u32(o_full), (uint32_t)((gb - 1) & 1));
+          tc_fence_after();
+          float t[32];
+          tmem_ld32(lane_addr + COL_O, t);
+          if (dump && j == 1) for (int c = 0; c < 32; ++c) dbg[16384 + (qd * 32 + lane) * 64 + c] = t[c];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[c] += t[c];
+          tmem_ld32(lane_addr + COL_O + 32, t);
+          if (dump && j == 1) for (int c = 0; c < 32; ++c) dbg[16384 + (qd * 32 + lane) * 64 + 32 + c] = t[c];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[32 + c] += t[c];
+        }
+#pragma unroll
+        for (int c = 0; c < HD; ++c) o[c] *= alpha;
+        // publish P_j = (hi, lo)
+        {
+          float t[32];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) { float hh, ll; split_tf32(s[half * 32 + c], hh, ll); t[c] = hh; s[half * 32 + c] = ll; }
+            tmem_st32(lane_addr + COL_PHI + (uint32_t)(half * 32), t);
+          }
+          tmem_st32(lane_addr + COL_PLO, s);
+          tmem_st32(lane_addr + COL_PLO + 32, s + 32);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(p_full));
+      }
+      // last chunk of this work item
+      mbar_wait(smem_u32(o_full), (uint32_t)((g + nblk - 1) & 1));
+      tc_fence_after();
+      {
         float t[32];
         tmem_ld32(lane_addr + COL_O, t);
-        if (dump && j == 1) for (int c = 0; c < 32; ++c) dbg[16384 + (qd * 32 + lane) * 64 + c] = t[c];
 #pragma unroll
         for (int c = 0; c < 32; ++c) o[c] += t[c];
         tmem_ld32(lane_addr + COL_O + 32, t);
-        if (dump && j == 1) for (int c = 0; c < 32; ++c) dbg[16384 + (qd * 32 + lane) * 64 + 32 + c] = t[c];
 #pragma unroll
         for (int c = 0; c < 32; ++c) o[32 + c] += t[c];
       }
+      g += nblk;
+      if (qrow < T) {
+        const float inv = 1.0f / l;
+        const size_t off = ((size_t)b * T + qrow) * D + (size_t)h * HD;
+        if (out_f16) {
+          uint4* ph = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(o_hi) + off);
+          uint4* pl = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(o_lo) + off);
 #pragma unroll
-      for (int c = 0; c < HD; ++c) o[c] *= alpha;
-      // publish P_j = (hi, lo)
-      {
-        float t[32];
+          for (int c = 0; c < HD; c += 8) {
+            __half hh[8], ll[8];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+            for (int j = 0; j < 8; ++j) split_f16(o[c + j] * inv * kActScale, hh[j], ll[j]);
+            ph[c >> 3] = *reinterpret_cast<uint4*>(hh); pl[c >> 3] = *reinterpret_cast<uint4*>(ll);
+          }
+        } else {
+          float4* ph = reinterpret_cast<float4*>(o_hi + off);
+          float4* pl = reinterpret_cast<float4*>(o_lo + off);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) { float hh, ll; split_tf32(s[half * 32 + c], hh, ll); t[c] = hh; s[half * 32 + c] = ll; }
-          tmem_st32(lane_addr + COL_PHI + (uint32_t)(half * 32), t);
-        }
-        tmem_st32(lane_addr + COL_PLO, s);
-        tmem_st32(lane_addr + COL_PLO + 32, s + 32);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(p_full));
-    }
-    // last chunk
-    mbar_wait(smem_u32(o_full), (uint32_t)((nblk - 1) & 1));
-    tc_fence_after();
-    {
-      float t[32];
-      tmem_ld32(lane_addr + COL_O, t);
-#pragma unroll
-      for (int c = 0; c < 32; ++c) o[c] += t[c];
-      tmem_ld32(lane_addr + COL_O + 32, t);
-#pragma unroll
-      for (int c = 0; c < 32; ++c) o[32 + c] += t[c];
-    }
-    if (qrow < T) {
-      const float inv = 1.0f / l;
-      const size_t off = ((size_t)row0 + qrow) * D + (size_t)h * HD;
-      if (out_f16) {
-        uint4* ph = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(o_hi) + off);
-        uint4* pl = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(o_lo) + off);
-#pragma unroll
-        for (int c = 0; c < HD; c += 8) {
-          __half hh[8], ll[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) split_f16(o[c + j] * inv * kActScale, hh[j], ll[j]);
-          ph[c >> 3] = *reinterpret_cast<uint4*>(hh); pl[c >> 3] = *reinterpret_cast<uint4*>(ll);
-        }
-      } else {
-        float4* ph = reinterpret_cast<float4*>(o_hi + off);
-        float4* pl = reinterpret_cast<float4*>(o_lo + off);
-#pragma unroll
-        for (int c = 0; c < HD; c += 4) {
-          float4 hh, ll;
-          split_tf32(o[c] * inv, hh.x, ll.x); split_tf32(o[c + 1] * inv, hh.y, ll.y);
-          split_tf32(o[c + 2] * inv, hh.z, ll.z); split_tf32(o[c + 3] * inv, hh.w, ll.w);
-          ph[c >> 2] = hh; pl[c >> 2] = ll;
+          for (int c = 0; c < HD; c += 4) {
+            float4 hh, ll;
+            split_tf32(o[c] * inv, hh.x, ll.x); split_tf32(o[c + 1] * inv, hh.y, ll.y);
+            split_tf32(o[c + 2] * inv, hh.z, ll.z); split_tf32(o[c + 3] * inv, hh.w, ll.w);
+            ph[c >> 2] = hh; pl[c >> 2] = ll;
+          }
         }
       }
     }
@@ -440,8 +467,9 @@ int attention_tc_launch(const float* qkv_hi, const float* qkv_lo, const float* v
     ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-  attention_tc_kernel<<<dim3(cdiv(T, BQ), heads, B), 256, SMEM_BYTES, st>>>(hq, lq, hkv, lkv, hvt, lvt, T, D, (float*)o_hi,
-                                                                             (float*)o_lo, out_f16 ? 1 : 0, dbg);
+  const int total = cdiv(T, BQ) * heads * B;
+  attention_tc_kernel<<<std::min(total, device_sm_count()), 256, SMEM_BYTES, st>>>(
+      hq, lq, hkv, lkv, hvt, lvt, B, T, D, (float*)o_hi, (float*)o_lo, out_f16 ? 1 : 0, dbg);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }

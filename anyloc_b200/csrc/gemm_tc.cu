@@ -37,7 +37,8 @@ template <int BN> struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;          // 512 or 256: power of two
 };
-constexpr int CHUNK_KB = 2;               // k-blocks accumulated inside the tensor core before an RN drain
+constexpr int CHUNK_KB_TF32 = 2;          // k-blocks (128 B of K each) accumulated in the tensor core before an RN
+constexpr int CHUNK_KB_F16 = 4;           // drain: 24 / 48 MMAs per chunk -> RZ bias ~4e-7 / ~8e-7 relative
 constexpr int EPI_WARPS = 16;             // 4 TMEM lane quarters x 4 column quarters
 constexpr int THREADS = 128 + EPI_WARPS * 32;
 
@@ -233,6 +234,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   constexpr int BKE = F16 ? 64 : 32;         // elements per k-block (128 bytes)
+  constexpr int CHUNK_KB = F16 ? CHUNK_KB_F16 : CHUNK_KB_TF32;
   const int num_k = (K + BKE - 1) / BKE;
   const int num_chunks = (num_k + CHUNK_KB - 1) / CHUNK_KB;
 

@@ -186,7 +186,7 @@ def run_ours(args, wl):
     D = ARCHS[wl["model"]][0]
     sd = random_state_dict(wl["model"], seed=0, device=dev, depth=wl["layer"] + 1)
     ext = u.DinoV2ExtractFeatures(wl["model"], wl["layer"], wl["facet"], device=dev, weights=sd,
-                                  gemm_engine=args.engine)
+                                  gemm_engine=args.engine, precision=args.precision)
     del sd
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     img_dev = torch.randn(B, 3, H, W, device=dev, generator=g)
@@ -266,13 +266,19 @@ def run_ours(args, wl):
     roof = None
     if g_n:
         ach = g_fl / (g_ms / 1e3) / 1e12
-        roof = {"kernel": "gemm_tc3_kernel<256> (tcgen05 kind::tf32, 3-term split, fp32-equivalent)",
+        f16 = args.precision == "f16x3"
+        passes = 3.0 if f16 else 6.0       # bf16-rate-equivalent tensor passes per algorithmic product
+        roof = {"kernel": "gemm_tc3_kernel<256,%s> (tcgen05 kind::%s, 3-term split, fp32 accumulate, RN chunk "
+                          "accumulation)" % ("true", "f16") if f16 else
+                          "gemm_tc3_kernel<256,false> (tcgen05 kind::tf32, 3-term split, fp32 accumulate, RN chunk "
+                          "accumulation)",
                 "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tflops_sustained"], "traffic": None,
                 "peak_source": f"{peaks['source']} cuBLAS bf16 sustained (MEASURED_PEAKS.json)",
-                "note": "achieved = algorithmic 2MNK FLOPs / device time; the engine issues 3 tf32 MMAs per "
-                        "product at half the bf16 rate, so the tensor pipe is busy for 6x the bf16-equivalent time",
-                "tensor_pipe_frac_est": 6.0 * ach / peaks["tflops_sustained"],
+                "note": "achieved = algorithmic 2MNK FLOPs / device time; the engine issues 3 MMAs per product "
+                        "(fp32-equivalent accuracy) at %s the bf16 rate, i.e. %d bf16-equivalent passes"
+                        % ("1x" if f16 else "0.5x", int(passes)),
+                "tensor_pipe_frac_est": passes * ach / peaks["tflops_sustained"],
                 "launches": g_n, "avg_launch_ms": g_ms / g_n, "share_of_step": g_ms / ms_total}
     v_ms, v_n, v_bytes = prof["vlad"]
     vroof = None
@@ -284,10 +290,13 @@ def run_ours(args, wl):
     shares = {c: round(prof[c][0] / ms_total, 4) for c in prof if prof[c][1]}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (tcgen05 tf32x3 split, fp32 accumulate)", "data": "synthetic",
+            "vs_baseline": None,
+            "dtype": "f32-equivalent (tcgen05 %s 3-term split, fp32 accumulate)" % ("fp16" if args.precision == "f16x3" else "tf32"),
+            "data": "synthetic",
             "config": {"workload": wl["name"], "per_gpu_batch": B, "global_batch": B * world,
                        "weights": "random-init (upstream recipe), no checkpoint offline",
                        "parallelism": f"dp{world} (images sharded, no collective in the step)",
+                       "precision": args.precision,
                        "cache": "inputs larger than L2: weights (hi+lo) streamed every step"},
             "vit_tflops_algorithmic": flops_img * value / 1e12,
             "roofline": roof, "roofline_vlad": vroof, "time_shares": shares,
@@ -315,6 +324,8 @@ def main():
     ap.add_argument("--ref-images", type=int, default=2, help="images per CPU-reference step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--vocab", default="fit", choices=["fit", "random"])
+    ap.add_argument("--precision", default="f16x3", choices=["f16x3", "tf32x3"],
+                    help="operand pair format of the tensor-core GEMMs (both fp32-equivalent; see DESIGN.md)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
