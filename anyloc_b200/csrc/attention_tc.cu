@@ -10,11 +10,12 @@
 // One CTA per (128-query tile, head, image), 256 threads:
 //   (persistent: CTAs stride over the (q-tile, head, image) work items so TMEM allocation, barrier init and
 //    load latency are paid once and the producer/MMA warps run ahead into the next item)
-//   warp 0   : TMA producer -- Q tile per item, then a 2-stage ring of 64-key blocks {K_hi,K_lo,Vt_hi,Vt_lo}
+//   warp 0/3 : TMA producers -- Q tile per item + 2-stage K ring (warp 0), 2-stage V^T ring (warp 3), 64-key blocks
 //   warp 1   : MMA issuer   -- S_j = Q K_j^T  (A,B from smem, K-major, M128 x N64 x K8, 24 UMMAs)
 //                              O_j = P_j V_j  (A = P from TMEM, B = V^T tile from smem K-major, 24 UMMAs)
 //   warp 2   : TMEM allocator (S double-buffered 2x64, P_hi 64, P_lo 64, O chunk 64 columns)
-//   warps 4-7: softmax      -- thread = query row: tcgen05.ld S, online softmax in fp32 registers,
+//   warps 4-11: softmax     -- two warps per 32-row TMEM lane quarter (key / head-dim halves): tcgen05.ld S,
+//                              online softmax in fp32 registers,
 //                              tcgen05.st P (hi,lo), and round-to-nearest accumulation of the per-block
 //                              O_j chunks into register accumulators (the tensor core's accumulator
 //                              rounds toward zero, see gemm_tc.cu), final 1/l scaling, (hi,lo) stores.
@@ -32,7 +33,9 @@ constexpr int Q_HALF = BQ * 32 * 4;           // one [128 x 32] fp32 k-block: 16
 constexpr int Q_BYTES = 4 * Q_HALF;           // hi(2 k-blocks) + lo(2 k-blocks): 64 KB
 constexpr int KV_BOX = BKV * 32 * 4;          // one [64 x 32] fp32 box: 8 KB
 constexpr int STAGE_BYTES = 8 * KV_BOX;       // K_hi(2) K_lo(2) V_hi(2) V_lo(2): 64 KB
-constexpr int SMEM_BYTES = Q_BYTES + STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int THREADS = 128 + 256;        // producer / MMA / alloc / spare + 8 softmax warps
+constexpr int XCHG_BYTES = 6 * BQ * 4;    // row-max (2 slots x 2 halves) and row-sum (2 halves) exchange
+constexpr int SMEM_BYTES = Q_BYTES + STAGES * STAGE_BYTES + 1024 + 256 + XCHG_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t COL_S = 0;       // 2 x 64
 constexpr uint32_t COL_PHI = 128;   // 64
@@ -69,6 +72,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -125,7 +131,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
       : "memory");
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_constant__ CUtensorMap tm_lo_q,
                     const __grid_constant__ CUtensorMap tm_hi_kv, const __grid_constant__ CUtensorMap tm_lo_kv,
                     const __grid_constant__ CUtensorMap tm_hi_vt, const __grid_constant__ CUtensorMap tm_lo_vt,
@@ -138,12 +144,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + STAGES * STAGE_BYTES);
   uint64_t* q_full = bars;                 // 1
   uint64_t* q_empty = bars + 1;            // 1
-  uint64_t* kv_full = bars + 2;            // [STAGES]
-  uint64_t* kv_empty = kv_full + STAGES;   // [STAGES]
-  uint64_t* s_full = kv_empty + STAGES;    // [2]
+  uint64_t* k_full = bars + 2;             // [STAGES]   K and V^T rings are released separately: K_j as soon
+  uint64_t* k_empty = k_full + STAGES;     // [STAGES]   as S_j retires (early), V_j after PV_j -- so the next
+  uint64_t* v_full = k_empty + STAGES;     // [STAGES]   K block streams in while softmax/PV of the current
+  uint64_t* v_empty = v_full + STAGES;     // [STAGES]   block are still running
+  uint64_t* s_full = v_empty + STAGES;     // [2]
   uint64_t* p_full = s_full + 2;           // 1
   uint64_t* o_full = p_full + 1;           // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  float* xchg = reinterpret_cast<float*>(bars) + 64;      // 256 B after the barrier block
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -162,9 +171,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_co
   }
   if (warp == 1 && lane == 0) {
     mbar_init(smem_u32(q_full), 1); mbar_init(smem_u32(q_empty), 1);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(kv_full + s), 1); mbar_init(smem_u32(kv_empty + s), 1); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(k_full + s), 1); mbar_init(smem_u32(k_empty + s), 1);
+      mbar_init(smem_u32(v_full + s), 1); mbar_init(smem_u32(v_empty + s), 1);
+    }
     mbar_init(smem_u32(s_full), 1); mbar_init(smem_u32(s_full + 1), 1);
-    mbar_init(smem_u32(p_full), 4);          // one arrive per softmax warp
+    mbar_init(smem_u32(p_full), 8);          // one arrive per softmax warp
     mbar_init(smem_u32(o_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -182,11 +194,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_co
   // ring / double-buffer parities carry over from one work item to the next.
   if (warp == 0) {
     if (lane == 0) {
-      // ------------------------------------------------ TMA producer
+      // ------------------------------------------------ TMA producer: Q tiles and the K ring
       int g = 0, it = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
         const int qt = w % q_tiles, h = (w / q_tiles) % heads, b = w / (q_tiles * heads);
-        const int row0 = b * T, colq = h * HD, colk = D + h * HD, vrow = (b * heads + h) * HD;
+        const int row0 = b * T, colq = h * HD, colk = D + h * HD;
         mbar_wait(smem_u32(q_empty), (uint32_t)((it & 1) ^ 1));     // previous tile's S MMAs are done with Q
         const uint32_t qb = smem_u32(q_full);
         mbar_expect_tx(qb, Q_BYTES);
@@ -196,15 +208,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_co
         tma_load_2d(smem_u32(sQ + 3 * Q_HALF), &tm_lo_q, qb, colq + 32, row0 + qt * BQ);
         for (int j = 0; j < nblk; ++j, ++g) {
           const int stage = g % STAGES;
-          mbar_wait(smem_u32(kv_empty + stage), (uint32_t)(((g / STAGES) & 1) ^ 1));
-          const uint32_t fb = smem_u32(kv_full + stage);
-          mbar_expect_tx(fb, STAGE_BYTES);
+          mbar_wait(smem_u32(k_empty + stage), (uint32_t)(((g / STAGES) & 1) ^ 1));
+          const uint32_t fb = smem_u32(k_full + stage);
+          mbar_expect_tx(fb, STAGE_BYTES / 2);
           const uint32_t sb = smem_u32(sKV + stage * STAGE_BYTES);
           const int r = row0 + j * BKV;
           tma_load_2d(sb + 0 * KV_BOX, &tm_hi_kv, fb, colk, r);
           tma_load_2d(sb + 1 * KV_BOX, &tm_hi_kv, fb, colk + 32, r);
           tma_load_2d(sb + 2 * KV_BOX, &tm_lo_kv, fb, colk, r);
           tma_load_2d(sb + 3 * KV_BOX, &tm_lo_kv, fb, colk + 32, r);
+        }
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      // ------------------------------------------------ TMA producer: the V^T ring
+      int g = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int h = (w / q_tiles) % heads, b = w / (q_tiles * heads);
+        const int vrow = (b * heads + h) * HD;
+        for (int j = 0; j < nblk; ++j, ++g) {
+          const int stage = g % STAGES;
+          mbar_wait(smem_u32(v_empty + stage), (uint32_t)(((g / STAGES) & 1) ^ 1));
+          const uint32_t fb = smem_u32(v_full + stage);
+          mbar_expect_tx(fb, STAGE_BYTES / 2);
+          const uint32_t sb = smem_u32(sKV + stage * STAGE_BYTES);
           tma_load_2d(sb + 4 * KV_BOX, &tm_hi_vt, fb, j * BKV, vrow);         // V^T [64 d x 32 keys] k-block 0
           tma_load_2d(sb + 5 * KV_BOX, &tm_hi_vt, fb, j * BKV + 32, vrow);    //                      k-block 1
           tma_load_2d(sb + 6 * KV_BOX, &tm_lo_vt, fb, j * BKV, vrow);
@@ -223,7 +251,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_co
       const uint32_t q_base = smem_u32(sQ);
       auto issue_s = [&](int gb) {
         const int st = gb % STAGES;
-        mbar_wait(smem_u32(kv_full + st), (uint32_t)((gb / STAGES) & 1));
+        mbar_wait(smem_u32(k_full + st), (uint32_t)((gb / STAGES) & 1));
         tc_fence_after();
         const uint32_t kb = smem_u32(sKV + st * STAGE_BYTES);
         const uint32_t d = tmem_base + COL_S + (uint32_t)((gb & 1) * BKV);
@@ -238,21 +266,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_co
           umma_ss(d, a_hi, b_lo, idesc_s, 1u);
         }
         umma_commit(smem_u32(s_full + (gb & 1)));
+        umma_commit(smem_u32(k_empty + st));      // K_gb may be overwritten as soon as S_gb retires
       };
       int g = 0, it = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const bool tdump = dbg != nullptr && it == 1 && blockIdx.x == 0;
+        const long long tb = tdump ? clock64() : 0;
+#define MSTAMP(jj, slot) do { if (tdump) dbg[40960 + (jj) * 16 + 8 + (slot)] = (float)(clock64() - tb); } while (0)
         mbar_wait(smem_u32(q_full), (uint32_t)(it & 1));
         tc_fence_after();
+        MSTAMP(0, 0);
         issue_s(g);
+        MSTAMP(0, 1);
         if (nblk == 1) umma_commit(smem_u32(q_empty));
         for (int j = 0; j < nblk; ++j) {
           const int gb = g + j, st = gb % STAGES;
           if (j + 1 < nblk) {
+            MSTAMP(j + 1, 0);
             issue_s(gb + 1);       // S buffer (gb+1)&1 was consumed before P_{gb-1} was published (program order)
+            MSTAMP(j + 1, 1);
             if (j + 2 == nblk) umma_commit(smem_u32(q_empty));   // last S of this tile issued: Q may be reloaded
           }
+          mbar_wait(smem_u32(v_full + st), (uint32_t)((gb / STAGES) & 1));
           mbar_wait(smem_u32(p_full), (uint32_t)(gb & 1));
           tc_fence_after();
+          MSTAMP(j, 2);
           const uint32_t vb = smem_u32(sKV + st * STAGE_BYTES) + 4 * KV_BOX;
           const uint32_t d = tmem_base + COL_O;
 #pragma unroll
@@ -265,118 +303,127 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi_q, const __grid_co
             umma_ts(d, p_hi, v_lo, idesc_pv, 1u);
           }
           umma_commit(smem_u32(o_full));
-          umma_commit(smem_u32(kv_empty + st));     // K_j / V_j no longer needed once these MMAs retire
+          MSTAMP(j, 3);
+          umma_commit(smem_u32(v_empty + st));      // V_gb no longer needed once these MMAs retire
         }
         g += nblk;
       }
     }
   } else if (warp >= 4) {
-    // -------------------------------------------------- softmax + RN accumulation (thread = query row)
-    const int qd = warp & 3;
+    // -------------------------------------------------- softmax + RN accumulation
+    // 8 warps: two per TMEM lane quarter.  Both own the same 32 query rows; warp `half` handles key columns
+    // [32*half, 32*half+32) of every S block and head-dim columns [32*half, +32) of O, so each thread carries
+    // 32 + 32 live values instead of 64 + 64 and every SM sub-partition has two warps to hide latency with.
+    // Only the running row maximum must agree between the pair: exchanged through shared memory per block.
+    const int qd = warp & 3, half = (warp - 4) >> 2;
+    const int row = qd * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
     const float kScale = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
     int g = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int qt = w % q_tiles, h = (w / q_tiles) % heads, b = w / (q_tiles * heads);
-      const int qrow = qt * BQ + qd * 32 + lane;          // token index inside the image
+      const int qrow = qt * BQ + row;                     // token index inside the image
       const bool dump = dbg != nullptr && w == 0;
-      float m = -INFINITY, l = 0.f;
-      float o[HD];
+      const bool tdump = dbg != nullptr && w == (int)gridDim.x && blockIdx.x == 0 && warp == 4 && lane == 0;  // 2nd item of CTA 0
+      long long tb = tdump ? clock64() : 0;
+#define TSTAMP(slot) do { if (tdump) dbg[40960 + j * 16 + (slot)] = (float)(clock64() - tb); } while (0)
+      float m = -INFINITY, l = 0.f;                       // l: this warp's half of the row sum
+      float o[32];
 #pragma unroll
-      for (int c = 0; c < HD; ++c) o[c] = 0.f;
+      for (int c = 0; c < 32; ++c) o[c] = 0.f;
       for (int j = 0; j < nblk; ++j) {
         const int gb = g + j;
+        TSTAMP(0);
         mbar_wait(smem_u32(s_full + (gb & 1)), (uint32_t)((gb >> 1) & 1));
         tc_fence_after();
-        float s[BKV];
-        tmem_ld32(lane_addr + COL_S + (uint32_t)((gb & 1) * BKV), s);
-        tmem_ld32(lane_addr + COL_S + (uint32_t)((gb & 1) * BKV + 32), s + 32);
+        TSTAMP(1);
+        float s[32];
+        tmem_ld32(lane_addr + COL_S + (uint32_t)((gb & 1) * BKV + half * 32), s);
+        TSTAMP(2);
         if (j == nblk - 1) {                              // only the last block can hold keys >= T
 #pragma unroll
-          for (int c = 0; c < BKV; ++c) if (j * BKV + c >= T) s[c] = -INFINITY;
+          for (int c = 0; c < 32; ++c) if (j * BKV + half * 32 + c >= T) s[c] = -INFINITY;
         }
-        float mx0 = m, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < BKV; c += 4) {
+        for (int c = 0; c < 32; c += 4) {
           s[c] *= kScale; s[c + 1] *= kScale; s[c + 2] *= kScale; s[c + 3] *= kScale;
           mx0 = fmaxf(mx0, s[c]); mx1 = fmaxf(mx1, s[c + 1]); mx2 = fmaxf(mx2, s[c + 2]); mx3 = fmaxf(mx3, s[c + 3]);
         }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        if (dump && j == 0) for (int c = 0; c < BKV; ++c) dbg[(qd * 32 + lane) * 64 + c] = s[c];
-        const float alpha = exp2f(m - mx);                // 0 on the first block (m = -inf, mx finite)
+        const float pm = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        xchg[((gb & 1) * 2 + half) * BQ + row] = pm;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");      // the two warps of this lane quarter
+        const float mx = fmaxf(m, fmaxf(pm, xchg[((gb & 1) * 2 + (half ^ 1)) * BQ + row]));
+        TSTAMP(3);
+        if (dump && j == 0) for (int c = 0; c < 32; ++c) dbg[row * 64 + half * 32 + c] = s[c];
+        const float alpha = ex2(m - mx);                  // 0 on the first block (m = -inf, mx finite)
         float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
 #pragma unroll
-        for (int c = 0; c < BKV; c += 4) {
-          s[c] = exp2f(s[c] - mx); s[c + 1] = exp2f(s[c + 1] - mx);
-          s[c + 2] = exp2f(s[c + 2] - mx); s[c + 3] = exp2f(s[c + 3] - mx);
+        for (int c = 0; c < 32; c += 4) {
+          s[c] = ex2(s[c] - mx); s[c + 1] = ex2(s[c + 1] - mx);
+          s[c + 2] = ex2(s[c + 2] - mx); s[c + 3] = ex2(s[c + 3] - mx);
           r0 += s[c]; r1 += s[c + 1]; r2 += s[c + 2]; r3 += s[c + 3];
         }
         l = l * alpha + ((r0 + r1) + (r2 + r3));
         m = mx;
-        if (dump && j == 0) for (int c = 0; c < BKV; ++c) dbg[8192 + (qd * 32 + lane) * 64 + c] = s[c];
+        TSTAMP(4);
+        if (dump && j == 0) for (int c = 0; c < 32; ++c) dbg[8192 + row * 64 + half * 32 + c] = s[c];
         if (j > 0) {                                      // fold in O_{j-1} (RN), frees the P and O buffers
           mbar_wait(smem_u32(o_full), (uint32_t)((gb - 1) & 1));
           tc_fence_after();
+          TSTAMP(5);
           float t[32];
-          tmem_ld32(lane_addr + COL_O, t);
-          if (dump && j == 1) for (int c = 0; c < 32; ++c) dbg[16384 + (qd * 32 + lane) * 64 + c] = t[c];
+          tmem_ld32(lane_addr + COL_O + (uint32_t)(half * 32), t);
+          if (dump && j == 1) for (int c = 0; c < 32; ++c) dbg[16384 + row * 64 + half * 32 + c] = t[c];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) o[c] += t[c];
-          tmem_ld32(lane_addr + COL_O + 32, t);
-          if (dump && j == 1) for (int c = 0; c < 32; ++c) dbg[16384 + (qd * 32 + lane) * 64 + 32 + c] = t[c];
-#pragma unroll
-          for (int c = 0; c < 32; ++c) o[32 + c] += t[c];
+          for (int c = 0; c < 32; ++c) o[c] = (o[c] + t[c]) * alpha;
         }
-#pragma unroll
-        for (int c = 0; c < HD; ++c) o[c] *= alpha;
-        // publish P_j = (hi, lo)
+        // publish this warp's 32 key columns of P_j = (hi, lo)
         {
           float t[32];
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) { float hh, ll; split_tf32(s[half * 32 + c], hh, ll); t[c] = hh; s[half * 32 + c] = ll; }
-            tmem_st32(lane_addr + COL_PHI + (uint32_t)(half * 32), t);
-          }
-          tmem_st32(lane_addr + COL_PLO, s);
-          tmem_st32(lane_addr + COL_PLO + 32, s + 32);
+          for (int c = 0; c < 32; ++c) { float hh, ll; split_tf32(s[c], hh, ll); t[c] = hh; s[c] = ll; }
+          tmem_st32(lane_addr + COL_PHI + (uint32_t)(half * 32), t);
+          tmem_st32(lane_addr + COL_PLO + (uint32_t)(half * 32), s);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
+        TSTAMP(6);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(p_full));
+        TSTAMP(7);
       }
-      // last chunk of this work item
+      // last chunk of this work item, then the row sum of the partner warp
       mbar_wait(smem_u32(o_full), (uint32_t)((g + nblk - 1) & 1));
       tc_fence_after();
       {
         float t[32];
-        tmem_ld32(lane_addr + COL_O, t);
+        tmem_ld32(lane_addr + COL_O + (uint32_t)(half * 32), t);
 #pragma unroll
         for (int c = 0; c < 32; ++c) o[c] += t[c];
-        tmem_ld32(lane_addr + COL_O + 32, t);
-#pragma unroll
-        for (int c = 0; c < 32; ++c) o[32 + c] += t[c];
       }
       g += nblk;
+      xchg[(4 + half) * BQ + row] = l;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+      const float inv = 1.0f / (l + xchg[(4 + (half ^ 1)) * BQ + row]);
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");        // slot reusable by the next work item
       if (qrow < T) {
-        const float inv = 1.0f / l;
-        const size_t off = ((size_t)b * T + qrow) * D + (size_t)h * HD;
+        const size_t off = ((size_t)b * T + qrow) * D + (size_t)h * HD + half * 32;
         if (out_f16) {
           uint4* ph = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(o_hi) + off);
           uint4* pl = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(o_lo) + off);
 #pragma unroll
-          for (int c = 0; c < HD; c += 8) {
+          for (int c = 0; c < 32; c += 8) {
             __half hh[8], ll[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) split_f16(o[c + j] * inv * kActScale, hh[j], ll[j]);
+            for (int q = 0; q < 8; ++q) split_f16(o[c + q] * inv * kActScale, hh[q], ll[q]);
             ph[c >> 3] = *reinterpret_cast<uint4*>(hh); pl[c >> 3] = *reinterpret_cast<uint4*>(ll);
           }
         } else {
           float4* ph = reinterpret_cast<float4*>(o_hi + off);
           float4* pl = reinterpret_cast<float4*>(o_lo + off);
 #pragma unroll
-          for (int c = 0; c < HD; c += 4) {
+          for (int c = 0; c < 32; c += 4) {
             float4 hh, ll;
             split_tf32(o[c] * inv, hh.x, ll.x); split_tf32(o[c + 1] * inv, hh.y, ll.y);
             split_tf32(o[c + 2] * inv, hh.z, ll.z); split_tf32(o[c + 3] * inv, hh.w, ll.w);
@@ -468,7 +515,7 @@ int attention_tc_launch(const float* qkv_hi, const float* qkv_lo, const float* v
     attr_set = true;
   }
   const int total = cdiv(T, BQ) * heads * B;
-  attention_tc_kernel<<<std::min(total, device_sm_count()), 256, SMEM_BYTES, st>>>(
+  attention_tc_kernel<<<std::min(total, device_sm_count()), THREADS, SMEM_BYTES, st>>>(
       hq, lq, hkv, lkv, hvt, lvt, B, T, D, (float*)o_hi, (float*)o_lo, out_f16 ? 1 : 0, dbg);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;

@@ -1,20 +1,25 @@
 // Hard-assignment VLAD (reference: /root/reference/utilities.py:819-926, residuals :956-962,
 // assignment fpk.KMeans.predict :849).  See include/anyloc_b200.h for the contract.
 //
-// v1 layout (SIMT): three kernels per batch --
-//   centre_prep : c^_k = c_k/(|c_k|+1e-8) (cosine) or c_k with bias -|c_k|^2/2 (euclid)
-//   assign      : one warp per descriptor row: |x|, K dot products against c^ (L1/L2 resident),
-//                 first-max argmax  -> labels, 1/max(|x|,1e-12)
-//   accumulate  : CTA per (image, 128-wide D slice): sum_{label=k}(x^ - c_k) in shared memory,
-//                 per-(image,k,slice) partial sums of squares (deterministic, no atomics)
+// v2 pipeline (5 launches per batch):
+//   centre_prep : c^_k = c_k/(|c_k|+1e-8) (cosine) or c_k with bias -|c_k|^2/2 (euclid), plus a tf32-rounded copy
+//   coarse      : S~[R,K] = X . c^T on the tcgen05 GEMM engine, single tf32 pass straight from the raw fp32
+//                 features (no conversion pass; the tensor core truncates) -- HBM-bound, reads X once
+//   rescore     : warp per row: |x|, candidate set {k : S~_k >= max - 2 eps} with the rigorous tf32 bound
+//                 eps = 2^-9 |x| max|c^|, exact fp32 dot products only for the candidates (row held in registers),
+//                 first-max argmax -> labels identical to an exact fp32 evaluation; 1/max(|x|,1e-12)
+//   accumulate  : CTA per (image, 128-column slice), warps split the rows, float4 lanes:
+//                 sum_{label=k}(x^ - c_k) in shared memory, deterministic per-slice sums of squares
 //   normalise   : intra + global L2 normalisation, in place on the [B,K*D] output
-#include "common.cuh"
+// (The v1 FFMA assignment kernel is kept for K > 256 / D > 2048 and as the k-means assignment step.)
+#include "epilogue.cuh"
 
 namespace anyloc {
 
 // ------------------------------------------------------------------ centre prep
 __global__ void vlad_centre_prep_kernel(const float* __restrict__ c, int K, int D, int dist_mode,
-                                        float* __restrict__ chat, float* __restrict__ cbias) {
+                                        float* __restrict__ chat, float* __restrict__ cbias,
+                                        float* __restrict__ chat_tf32, float* __restrict__ cnorm) {
   int k = blockIdx.x;
   const float* row = c + (size_t)k * D;
   float ss = 0.f;
@@ -32,12 +37,20 @@ __global__ void vlad_centre_prep_kernel(const float* __restrict__ c, int K, int 
   ss = red[0];
   if (dist_mode == ANYLOC_DIST_COSINE) {
     const float den = sqrtf(ss) + 1e-8f;            // fpk cos_sim: b / (|b| + 1e-8)
-    for (int d = threadIdx.x; d < D; d += blockDim.x) chat[(size_t)k * D + d] = row[d] / den;
-    if (threadIdx.x == 0) cbias[k] = 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      float v = row[d] / den, h, l;
+      chat[(size_t)k * D + d] = v;
+      if (chat_tf32) { split_tf32(v, h, l); chat_tf32[(size_t)k * D + d] = h; }
+    }
+    if (threadIdx.x == 0) { cbias[k] = 0.f; if (cnorm) cnorm[k] = sqrtf(ss) / den; }
   } else {
     // argmax_k 2 x.c_k - |x|^2 - |c_k|^2  ==  argmax_k (x.c_k - |c_k|^2/2)
-    for (int d = threadIdx.x; d < D; d += blockDim.x) chat[(size_t)k * D + d] = row[d];
-    if (threadIdx.x == 0) cbias[k] = -0.5f * ss;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      float v = row[d], h, l;
+      chat[(size_t)k * D + d] = v;
+      if (chat_tf32) { split_tf32(v, h, l); chat_tf32[(size_t)k * D + d] = h; }
+    }
+    if (threadIdx.x == 0) { cbias[k] = -0.5f * ss; if (cnorm) cnorm[k] = sqrtf(ss); }
   }
 }
 
@@ -111,6 +124,137 @@ vlad_assign_kernel(const float* __restrict__ x, const int32_t* __restrict__ n_va
         }
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------ rescore (exact labels from coarse scores)
+// One warp per row.  The row (D <= 2048) lives in registers; only the candidates whose coarse tf32 score is within
+// 2*eps of the row maximum are re-evaluated exactly (fp32 FMA, same c^ as the exact path), so the label equals the
+// exact-fp32 argmax (lowest index among exact ties).
+template <int MAXV>      // float4 per lane: D <= 128 * MAXV
+__global__ void __launch_bounds__(256)
+vlad_rescore_kernel(const float* __restrict__ x, const int32_t* __restrict__ n_valid, int N_per_img, int64_t R,
+                    int D, int K, const float* __restrict__ chat, const float* __restrict__ cbias,
+                    const float* __restrict__ cnorm, const float* __restrict__ coarse /*[R,K]*/,
+                    int32_t* __restrict__ labels, float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= R) return;
+  bool valid = true;
+  if (n_valid) { int b = (int)(row / N_per_img), n = (int)(row % N_per_img); valid = n < n_valid[b]; }
+  const int D4 = D >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * (int64_t)D);
+  float4 v[MAXV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int d = lane + i * 32;
+    if (d < D4) { v[i] = __ldg(xr + d); ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w; }
+  }
+  ss = warp_sum(ss);
+  const float xn = sqrtf(ss);
+  // coarse maximum and the largest centre norm (lanes stride over k)
+  float smax = -INFINITY, cmax = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    smax = fmaxf(smax, coarse[row * K + k]);
+    cmax = fmaxf(cmax, cnorm[k]);
+  }
+  smax = warp_max(smax); cmax = warp_max(cmax);
+  // |S~_k - S_k| <= (2^-10 + 2^-11) sum|x_i c_i| <= 1.5 * 2^-10 |x||c_k| < 2^-9 |x||c_k|  (truncated x, rounded c)
+  const float thresh = smax - 2.0f * (0.001953125f * xn * cmax) - 1e-30f;
+  float best = -INFINITY; int bestk = 0; int ncand = 0, lastk = 0;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    const int k = k0 + lane;
+    const bool cand = k < K && coarse[row * K + k] >= thresh;
+    unsigned mask = __ballot_sync(0xffffffffu, cand);
+    while (mask) {
+      const int kk = k0 + __ffs(mask) - 1;
+      mask &= mask - 1;
+      ++ncand; lastk = kk;
+      const float4* cr = reinterpret_cast<const float4*>(chat + (size_t)kk * D);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        int d = lane + i * 32;
+        if (d < D4) {
+          float4 c = __ldg(cr + d);
+          acc = fmaf(v[i].x, c.x, acc); acc = fmaf(v[i].y, c.y, acc);
+          acc = fmaf(v[i].z, c.z, acc); acc = fmaf(v[i].w, c.w, acc);
+        }
+      }
+      const float sc = warp_sum(acc) + cbias[kk];
+      if (sc > best) { best = sc; bestk = kk; }          // ascending k, strict >: lowest index wins exact ties
+    }
+  }
+  if (lane == 0) {
+    labels[row] = valid ? bestk : -1;
+    if (inv_norm) inv_norm[row] = 1.0f / fmaxf(xn, 1e-12f);
+  }
+  (void)ncand; (void)lastk;
+}
+
+// ------------------------------------------------------------------ accumulate v2
+// CTA = (image, 128-column slice); WARPS warps split the rows; lane owns 4 consecutive columns (float4).
+// Per-warp accumulators [K][128] in shared memory (no conflicts: a warp touches 512 contiguous bytes per row),
+// reduced across warps at the end in a fixed order -> deterministic.
+__global__ void __launch_bounds__(256)
+vlad_accumulate2_kernel(const float* __restrict__ x, const int32_t* __restrict__ labels,
+                        const float* __restrict__ inv_norm, const float* __restrict__ centers,
+                        int N, int D, int K, int norm_descs, int warps, float* __restrict__ vlad,
+                        float* __restrict__ partial_ss /* [B,K,nslices] */) {
+  extern __shared__ float sm[];
+  float* cen = sm;                                        // [K][128]
+  float* acc = sm + (size_t)K * 128;                      // [warps][K][128]
+  const int b = blockIdx.y, slice = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int col = slice * 128 + lane * 4;
+  const bool colok = col < D;                             // D % 4 == 0
+  for (int i = t; i < K * 32; i += blockDim.x) {
+    const int k = i >> 5, c4 = (i & 31) * 4, gc = slice * 128 + c4;
+    float4 cv = gc < D ? __ldg(reinterpret_cast<const float4*>(centers + (size_t)k * D + gc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(cen + k * 128 + c4) = cv;
+  }
+  for (int i = t; i < warps * K * 32; i += blockDim.x) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  if (w < warps && colok) {
+    float* my = acc + (size_t)w * K * 128 + lane * 4;
+    const float* xb = x + (size_t)b * N * D + col;
+    const int32_t* lb = labels + (size_t)b * N;
+    const float* ib = inv_norm + (size_t)b * N;
+    for (int n = w; n < N; n += 2 * warps) {              // two rows in flight per iteration
+      const int n2 = n + warps;
+      const int l0 = lb[n], l1 = n2 < N ? lb[n2] : -1;
+      float4 v0 = __ldg(reinterpret_cast<const float4*>(xb + (size_t)n * D));
+      float4 v1 = l1 >= 0 ? __ldg(reinterpret_cast<const float4*>(xb + (size_t)n2 * D)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (l0 >= 0) {
+        const float s0 = norm_descs ? ib[n] : 1.0f;
+        float4 a = *reinterpret_cast<float4*>(my + l0 * 128), c = *reinterpret_cast<const float4*>(cen + l0 * 128 + lane * 4);
+        a.x += v0.x * s0 - c.x; a.y += v0.y * s0 - c.y; a.z += v0.z * s0 - c.z; a.w += v0.w * s0 - c.w;
+        *reinterpret_cast<float4*>(my + l0 * 128) = a;
+      }
+      if (l1 >= 0) {
+        const float s1 = norm_descs ? ib[n2] : 1.0f;
+        float4 a = *reinterpret_cast<float4*>(my + l1 * 128), c = *reinterpret_cast<const float4*>(cen + l1 * 128 + lane * 4);
+        a.x += v1.x * s1 - c.x; a.y += v1.y * s1 - c.y; a.z += v1.z * s1 - c.z; a.w += v1.w * s1 - c.w;
+        *reinterpret_cast<float4*>(my + l1 * 128) = a;
+      }
+    }
+  }
+  __syncthreads();
+  // reduce the warps' partials (fixed order), write V and the per-slice sums of squares
+  const int nslices = gridDim.x;
+  for (int k = w; k < K; k += blockDim.x >> 5) {          // one warp per cluster row
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < warps; ++q) {
+      float4 p = *reinterpret_cast<const float4*>(acc + ((size_t)q * K + k) * 128 + lane * 4);
+      a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+    }
+    float ss = 0.f;
+    if (colok) {
+      *reinterpret_cast<float4*>(vlad + ((size_t)b * K + k) * D + col) = a;
+      ss = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) partial_ss[((size_t)b * K + k) * nslices + slice] = ss;
   }
 }
 
@@ -264,27 +408,70 @@ __global__ void kmeans_finalize_kernel(const float* __restrict__ sums, const flo
 
 using namespace anyloc;
 
+namespace anyloc {
+// GEMM engines (gemm_tc.cu)
+int gemm_tc_launch(const void*, const void*, int, const void*, const void*, int, int, int, int, const EpiParams&, bool,
+                   cudaStream_t);
+bool gemm_tc_supported(const void*, const void*, int, const void*, const void*, int, int, int, int, const EpiParams&,
+                       bool);
+}  // namespace anyloc
+
 extern "C" size_t anyloc_vlad_workspace_bytes(int B, int N, int D, int K) {
   size_t R = (size_t)B * N;
   int nslices = cdiv(D, ACC_COLS);
-  return align_up((size_t)K * D * 4, 256) + align_up((size_t)K * 4, 256) + align_up(R * 4, 256) * 2 +
-         align_up((size_t)B * K * nslices * 4, 256) + align_up(((size_t)K * D + K) * 4, 256) + 4096;
+  return 2 * align_up((size_t)K * D * 4, 256) + 2 * align_up((size_t)K * 4, 256) + align_up(R * 4, 256) * 2 +
+         align_up(R * (size_t)K * 4, 256) + align_up((size_t)B * K * nslices * 4, 256) +
+         align_up(((size_t)K * D + K) * 4, 256) + 4096;
 }
 
-static int launch_assign(const float* feats, const int32_t* n_valid, int N_per_img, int64_t R, int D,
-                         int K, const float* centers, int dist_mode, float* chat, float* cbias,
-                         int32_t* labels, float* inv_norm, cudaStream_t st) {
-  vlad_centre_prep_kernel<<<K, 256, 0, st>>>(centers, K, D, dist_mode, chat, cbias);
+namespace {
+struct AssignBufs { float *chat, *chat_tf32, *cbias, *cnorm, *coarse; };
+
+// labels (+ 1/|x|) for R rows: tensor-core coarse scores + exact rescoring when the shape allows it, else the
+// FFMA kernel
+int launch_assign(const float* feats, const int32_t* n_valid, int N_per_img, int64_t R, int D, int K,
+                  const float* centers, int dist_mode, const AssignBufs& ab, int32_t* labels, float* inv_norm,
+                  cudaStream_t st) {
+  vlad_centre_prep_kernel<<<K, 256, 0, st>>>(centers, K, D, dist_mode, ab.chat, ab.cbias, ab.chat_tf32, ab.cnorm);
   ANYLOC_CHECK_LAUNCH();
+  EpiParams ep{ANYLOC_EPI_BIAS, ab.cbias, nullptr, nullptr, ab.coarse, nullptr, K};
+  const bool fast = ab.coarse != nullptr && D <= 2048 && R >= 256 && R < (1ll << 31) &&
+                    gemm_tc_supported(feats, nullptr, D, ab.chat_tf32, nullptr, D, (int)R, K, D, ep, false);
+  if (fast) {
+    int rc = gemm_tc_launch(feats, nullptr, D, ab.chat_tf32, nullptr, D, (int)R, K, D, ep, false, st);
+    if (rc) return rc;
+    const int blocks = (int)((R + 7) / 8);
+    if (D <= 512)
+      vlad_rescore_kernel<4><<<blocks, 256, 0, st>>>(feats, n_valid, N_per_img, R, D, K, ab.chat, ab.cbias, ab.cnorm,
+                                                     ab.coarse, labels, inv_norm);
+    else if (D <= 1024)
+      vlad_rescore_kernel<8><<<blocks, 256, 0, st>>>(feats, n_valid, N_per_img, R, D, K, ab.chat, ab.cbias, ab.cnorm,
+                                                     ab.coarse, labels, inv_norm);
+    else
+      vlad_rescore_kernel<16><<<blocks, 256, 0, st>>>(feats, n_valid, N_per_img, R, D, K, ab.chat, ab.cbias, ab.cnorm,
+                                                      ab.coarse, labels, inv_norm);
+    ANYLOC_CHECK_LAUNCH();
+    return ANYLOC_OK;
+  }
   int sms = device_sm_count();
   int64_t warps_needed = (R + 1) / 2;
   int blocks = (int)std::min<int64_t>((warps_needed + 7) / 8, (int64_t)sms * 8);
   if (blocks < 1) blocks = 1;
-  vlad_assign_kernel<2><<<blocks, 256, 0, st>>>(feats, n_valid, N_per_img, R, D, K, chat, cbias, labels,
+  vlad_assign_kernel<2><<<blocks, 256, 0, st>>>(feats, n_valid, N_per_img, R, D, K, ab.chat, ab.cbias, labels,
                                                inv_norm);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }
+
+bool take_assign_bufs(Workspace& w, int64_t R, int D, int K, AssignBufs* ab) {
+  ab->chat = w.take<float>((size_t)K * D);
+  ab->chat_tf32 = w.take<float>((size_t)K * D);
+  ab->cbias = w.take<float>(K);
+  ab->cnorm = w.take<float>(K);
+  ab->coarse = w.take<float>((size_t)R * K);        // may be null when the caller's workspace is the small one
+  return ab->chat && ab->chat_tf32 && ab->cbias && ab->cnorm;
+}
+}  // namespace
 
 extern "C" int anyloc_vlad_assign(const float* feats, const float* centers, int R, int D, int K,
                                   int dist_mode, int32_t* labels, void* ws, size_t ws_bytes,
@@ -293,11 +480,9 @@ extern "C" int anyloc_vlad_assign(const float* feats, const float* centers, int 
   ANYLOC_REQUIRE(R >= 0 && D > 0 && K > 0 && D % 4 == 0, "vlad_assign: bad dims R=%d D=%d K=%d", R, D, K);
   if (R == 0) return ANYLOC_OK;
   Workspace w(ws, ws_bytes);
-  float* chat = w.take<float>((size_t)K * D);
-  float* cbias = w.take<float>(K);
-  if (!chat || !cbias) { set_error("vlad_assign: workspace too small"); return ANYLOC_ERR_WORKSPACE; }
-  return launch_assign(feats, nullptr, R, R, D, K, centers, dist_mode, chat, cbias, labels, nullptr,
-                       (cudaStream_t)stream);
+  AssignBufs ab;
+  if (!take_assign_bufs(w, R, D, K, &ab)) { set_error("vlad_assign: workspace too small"); return ANYLOC_ERR_WORKSPACE; }
+  return launch_assign(feats, nullptr, R, R, D, K, centers, dist_mode, ab, labels, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, const float* centers,
@@ -315,25 +500,31 @@ extern "C" int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, 
   Workspace w(ws, ws_bytes);
   const size_t R = (size_t)B * N;
   const int nslices = cdiv(D, ACC_COLS);
-  float* chat = w.take<float>((size_t)K * D);
-  float* cbias = w.take<float>(K);
   int32_t* labels = w.take<int32_t>(R);
   float* inv_norm = w.take<float>(R);
   float* partial = w.take<float>((size_t)B * K * nslices);
-  if (!chat || !cbias || !labels || !inv_norm || !partial) {
+  AssignBufs ab;
+  if (!labels || !inv_norm || !partial || !take_assign_bufs(w, (int64_t)R, D, K, &ab)) {
     set_error("vlad_generate: workspace too small (%zu bytes given)", ws_bytes);
     return ANYLOC_ERR_WORKSPACE;
   }
   ProfScope ps(PC_VLAD, st, 4.0 * ((double)B * N * D + (double)B * K * D + (double)K * D));
-  int rc = launch_assign(feats, n_valid, N, (int64_t)R, D, K, centers, dist_mode, chat, cbias, labels,
-                         inv_norm, st);
+  int rc = launch_assign(feats, n_valid, N, (int64_t)R, D, K, centers, dist_mode, ab, labels, inv_norm, st);
   if (rc) return rc;
-  size_t smem = ((size_t)2 * K * ACC_COLS + 2 * (size_t)N) * 4;
-  ANYLOC_REQUIRE(smem <= 220 * 1024, "vlad_generate: K=%d N=%d needs %zu B shared memory", K, N, smem);
-  ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(vlad_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem));
-  vlad_accumulate_kernel<<<dim3(nslices, B), ACC_COLS, smem, st>>>(feats, labels, inv_norm, centers, N, D,
-                                                                  K, norm_descs, vlad, partial);
+  // accumulate: as many row-splitting warps as shared memory allows ((1 + warps) * K * 128 floats), at most 8
+  int warps = (int)std::min<size_t>(8, (200 * 1024) / ((size_t)K * 128 * 4) - 1);
+  if (warps >= 1) {
+    size_t smem = (size_t)(1 + warps) * K * 128 * 4;
+    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(vlad_accumulate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vlad_accumulate2_kernel<<<dim3(nslices, B), 256, smem, st>>>(feats, labels, inv_norm, centers, N, D, K, norm_descs,
+                                                                 warps, vlad, partial);
+  } else {
+    size_t smem = ((size_t)2 * K * ACC_COLS + 2 * (size_t)N) * 4;
+    ANYLOC_REQUIRE(smem <= 220 * 1024, "vlad_generate: K=%d N=%d needs %zu B shared memory", K, N, smem);
+    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(vlad_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vlad_accumulate_kernel<<<dim3(nslices, B), ACC_COLS, smem, st>>>(feats, labels, inv_norm, centers, N, D, K,
+                                                                    norm_descs, vlad, partial);
+  }
   ANYLOC_CHECK_LAUNCH();
   int ysplit = std::max(1, std::min(64, (int)(((size_t)K * D + 256 * 16 - 1) / (256 * 16))));
   vlad_normalize_kernel<<<dim3(B, ysplit), 256, 2 * K * sizeof(float), st>>>(vlad, partial, D, K, nslices,

@@ -177,7 +177,7 @@ class _KMeans:
         K = centers.shape[0]
         labels = torch.empty(R, dtype=torch.int32, device=x.device)
         with torch.cuda.device(x.device):
-            ws = _lib.workspaces.get(x.device, lib.anyloc_vlad_workspace_bytes(1, 1, D, K), "kmeans")
+            ws = _lib.workspaces.get(x.device, lib.anyloc_vlad_workspace_bytes(1, R, D, K), "kmeans")
             _lib.check(lib.anyloc_vlad_assign(_lib.ptr(x), _lib.ptr(centers), R, D, K, _lib.DIST[self.mode],
                                               _lib.ptr(labels), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
                        "anyloc_vlad_assign")

@@ -9,13 +9,13 @@ def split(x):
 fn = lib.anyloc_attention_tc_debug
 fn.restype = C.c_int
 fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-B, T, heads = 1, 257, 2
+B, T, heads = int(os.environ.get('AB', 1)), int(os.environ.get('AT', 257)), int(os.environ.get('AH', 2))
 D = heads * 64
 g = torch.Generator(device="cuda").manual_seed(1)
 qkv = torch.randn(B, T, 3 * D, device="cuda", generator=g) * 1.5
 qh, ql = split(qkv)
 oh, ol = torch.zeros(B, T, D, device="cuda"), torch.zeros(B, T, D, device="cuda")
-dbg = torch.full((5 * 8192,), float("nan"), device="cuda")
+dbg = torch.full((6 * 8192,), float("nan"), device="cuda")
 rc = fn(L.ptr(qh), L.ptr(ql), B, T, D, heads, L.ptr(oh), L.ptr(ol), L.ptr(dbg), L.stream_ptr())
 torch.cuda.synchronize()
 print("rc", rc)
@@ -32,3 +32,8 @@ print("O0 dbg sample", o_d[0, :6].tolist(), "ref", O0[0, :6].tolist())
 ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1) @ v).transpose(1, 2).reshape(B, T, D)
 out = (oh + ol).double()
 print("final err", float((out - ref).abs().max()), "out max", float(out.abs().max()))
+
+ts = dbg[40960:40960 + 16 * 16].reshape(16, 16).cpu()
+print("softmax stamps per block [before s_full, after s_full, after ld, after max xchg, after exp, after o_full, after P st, after arrive] | MMA [before S issue, after S issue, after p_full, after PV issue]")
+for j in range(min(10, (T + 63) // 64)):
+    print(j, [int(v) if v == v else -1 for v in ts[j, :8].tolist()], "|", [int(v) if v == v else -1 for v in ts[j, 8:12].tolist()])
