@@ -30,10 +30,13 @@ constexpr int BM = 128;
 constexpr int KSTEPS = 4;                  // UMMA k-steps per 128-byte k-block (32 B each: 8 tf32 or 16 fp16)
 constexpr int A_BYTES = BM * 128;         // 16 KB: 128 rows x 128 B
 
-template <int BN> struct Cfg {
+// LO = true : stages hold {A_hi, A_lo, B_hi, B_lo} (3-term split).  LO = false: hi-only single pass (coarse
+// scores, e.g. the VLAD assignment): {A_hi, B_hi} per stage -> twice the pipeline depth for latency-bound streams.
+template <int BN, bool LO = true> struct Cfg {
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 2 : 3;
+  static constexpr int STAGE_BYTES = (LO ? 2 : 1) * (A_BYTES + B_BYTES);
+  static constexpr int B_OFF = (LO ? 2 : 1) * A_BYTES;
+  static constexpr int STAGES = (LO ? 2 : 4);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;          // 512 or 256: power of two
 };
@@ -214,12 +217,12 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, i
 
 // F16 = false: operands are fp32 words read as tf32 (32 elements per 128 B k-block, UMMA K=8, kind::tf32)
 // F16 = true : operands are fp16            (64 elements per 128 B k-block, UMMA K=16, kind::f16, 2x rate)
-template <int BN, bool F16>
+template <int BN, bool F16, bool LO>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                 int M, int N, int K, int has_a_lo, int has_b_lo, EpiParams ep) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, LO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* bar_area = smem + C::STAGES * C::STAGE_BYTES;
@@ -265,7 +268,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0 && lane == 0) {
       // ------------------------------------------------ TMA producer
-      const uint32_t tx_bytes = A_BYTES * (1 + (has_a_lo ? 1 : 0)) + C::B_BYTES * (1 + (has_b_lo ? 1 : 0));
+      const uint32_t tx_bytes = A_BYTES * (1 + ((LO && has_a_lo) ? 1 : 0)) + C::B_BYTES * (1 + ((LO && has_b_lo) ? 1 : 0));
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
@@ -275,9 +278,9 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           mbar_expect_tx(fb, tx_bytes);
           const uint32_t sbase = smem_u32(smem + stage * C::STAGE_BYTES);
           tma_load_2d(sbase, &tm_a_hi, fb, kb * BKE, m0);
-          if (has_a_lo) tma_load_2d(sbase + A_BYTES, &tm_a_lo, fb, kb * BKE, m0);
-          tma_load_2d(sbase + 2 * A_BYTES, &tm_b_hi, fb, kb * BKE, n0);
-          if (has_b_lo) tma_load_2d(sbase + 2 * A_BYTES + C::B_BYTES, &tm_b_lo, fb, kb * BKE, n0);
+          if (LO && has_a_lo) tma_load_2d(sbase + A_BYTES, &tm_a_lo, fb, kb * BKE, m0);
+          tma_load_2d(sbase + C::B_OFF, &tm_b_hi, fb, kb * BKE, n0);
+          if (LO && has_b_lo) tma_load_2d(sbase + C::B_OFF + C::B_BYTES, &tm_b_lo, fb, kb * BKE, n0);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -300,13 +303,13 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           tc_fence_after();
           const uint32_t sbase = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t a_hi = make_desc(sbase), a_lo = make_desc(sbase + A_BYTES);
-          const uint64_t b_hi = make_desc(sbase + 2 * A_BYTES), b_lo = make_desc(sbase + 2 * A_BYTES + C::B_BYTES);
+          const uint64_t b_hi = make_desc(sbase + C::B_OFF), b_lo = make_desc(sbase + C::B_OFF + C::B_BYTES);
 #pragma unroll
           for (int k = 0; k < KSTEPS; ++k) {
             const uint64_t adv = (uint64_t)((k * 32) >> 4);      // +32 B per k-step inside the atom (both types)
             umma<F16>(d_tmem, a_hi + adv, b_hi + adv, idesc, (in_chunk | k) != 0);
-            if (has_a_lo) umma<F16>(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-            if (has_b_lo) umma<F16>(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+            if (LO && has_a_lo) umma<F16>(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+            if (LO && has_b_lo) umma<F16>(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
           }
           umma_commit(smem_u32(empty_bar + stage));      // frees the smem stage when these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -411,7 +414,7 @@ bool gemm_tc_supported(const void* a_hi, const void* a_lo, int lda, const void* 
   return true;
 }
 
-template <bool F16>
+template <bool F16, bool LO>
 static int launch_impl(const void* a_hi, const void* a_lo, int lda, const void* b_hi, const void* b_lo, int ldb, int M,
                        int N, int K, const EpiParams& ep, cudaStream_t st) {
   using namespace tc;
@@ -424,22 +427,25 @@ static int launch_impl(const void* a_hi, const void* a_lo, int lda, const void* 
   if ((rc = make_map(&mb_lo, b_lo ? b_lo : b_hi, N, K, ldb, BN, F16))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           Cfg<BN>::SMEM_BYTES));
+    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<BN, F16, LO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg<BN, LO>::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles = cdiv(M, BM) * cdiv(N, BN);
   const int grid = std::min(tiles, device_sm_count());
-  gemm_tc3_kernel<BN, F16><<<grid, THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K,
-                                                                       a_lo != nullptr, b_lo != nullptr, ep);
+  gemm_tc3_kernel<BN, F16, LO><<<grid, THREADS, Cfg<BN, LO>::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K,
+                                                                               a_lo != nullptr, b_lo != nullptr, ep);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }
 
 int gemm_tc_launch(const void* a_hi, const void* a_lo, int lda, const void* b_hi, const void* b_lo, int ldb, int M,
                    int N, int K, const EpiParams& ep, bool f16, cudaStream_t st) {
-  return f16 ? launch_impl<true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st)
-             : launch_impl<false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st);
+  const bool lo = a_lo != nullptr || b_lo != nullptr;
+  if (f16) return lo ? launch_impl<true, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st)
+                     : launch_impl<true, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st);
+  return lo ? launch_impl<false, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st)
+            : launch_impl<false, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st);
 }
 
 }  // namespace anyloc

@@ -220,22 +220,24 @@ vlad_accumulate2_kernel(const float* __restrict__ x, const int32_t* __restrict__
     const float* xb = x + (size_t)b * N * D + col;
     const int32_t* lb = labels + (size_t)b * N;
     const float* ib = inv_norm + (size_t)b * N;
-    for (int n = w; n < N; n += 2 * warps) {              // two rows in flight per iteration
-      const int n2 = n + warps;
-      const int l0 = lb[n], l1 = n2 < N ? lb[n2] : -1;
-      float4 v0 = __ldg(reinterpret_cast<const float4*>(xb + (size_t)n * D));
-      float4 v1 = l1 >= 0 ? __ldg(reinterpret_cast<const float4*>(xb + (size_t)n2 * D)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (l0 >= 0) {
-        const float s0 = norm_descs ? ib[n] : 1.0f;
-        float4 a = *reinterpret_cast<float4*>(my + l0 * 128), c = *reinterpret_cast<const float4*>(cen + l0 * 128 + lane * 4);
-        a.x += v0.x * s0 - c.x; a.y += v0.y * s0 - c.y; a.z += v0.z * s0 - c.z; a.w += v0.w * s0 - c.w;
-        *reinterpret_cast<float4*>(my + l0 * 128) = a;
+    constexpr int U = 8;                                  // rows in flight per warp (latency hiding)
+    for (int n0 = w; n0 < N; n0 += U * warps) {
+      float4 v[U]; int lab[U]; float sc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int n = n0 + u * warps;
+        lab[u] = n < N ? lb[n] : -1;
+        sc[u] = (n < N && norm_descs) ? ib[n] : 1.0f;
+        v[u] = lab[u] >= 0 ? __ldg(reinterpret_cast<const float4*>(xb + (size_t)n * D)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (l1 >= 0) {
-        const float s1 = norm_descs ? ib[n2] : 1.0f;
-        float4 a = *reinterpret_cast<float4*>(my + l1 * 128), c = *reinterpret_cast<const float4*>(cen + l1 * 128 + lane * 4);
-        a.x += v1.x * s1 - c.x; a.y += v1.y * s1 - c.y; a.z += v1.z * s1 - c.z; a.w += v1.w * s1 - c.w;
-        *reinterpret_cast<float4*>(my + l1 * 128) = a;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (lab[u] >= 0) {
+          float4 a = *reinterpret_cast<float4*>(my + lab[u] * 128);
+          const float4 c = *reinterpret_cast<const float4*>(cen + lab[u] * 128 + lane * 4);
+          a.x += v[u].x * sc[u] - c.x; a.y += v[u].y * sc[u] - c.y; a.z += v[u].z * sc[u] - c.z; a.w += v[u].w * sc[u] - c.w;
+          *reinterpret_cast<float4*>(my + lab[u] * 128) = a;
+        }
       }
     }
   }
