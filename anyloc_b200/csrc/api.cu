@@ -68,6 +68,10 @@ int attention_tc_launch(const float*, const float*, const float*, const float*, 
                         float*, cudaStream_t);
 int attention_tc_standalone(const float*, const float*, int, int, int, int, void*, void*, bool, float*, cudaStream_t);
 int attention_vt_pitch(int T);
+int attention16_vt_pitch(int T);
+int attention_tc16_launch(const void*, const void*, const void*, const void*, int, int, int, int, void*, void*, bool,
+                          cudaStream_t);
+int attention_tc16_standalone(const float*, const float*, int, int, int, int, void*, void*, bool, cudaStream_t);
 
 static int gemm_dispatch(const void* a_hi, const void* a_lo, int lda, const void* b_hi, const void* b_lo,
                          int ldb, int M, int N, int K, const EpiParams& ep, int engine, bool f16, cudaStream_t st) {
@@ -174,6 +178,10 @@ static int attention_dispatch(const float* qkv_hi, const float* qkv_lo, const fl
   }
   if (engine == ANYLOC_GEMM_SIMT || !tc_ok)
     return attention_launch(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, out_f16, st);
+  if (out_f16) {     // fp16-pair precision: operands are fp16 pairs too (inside the ViT the qkv epilogue wrote them)
+    if (vt_hi) return attention_tc16_launch(qkv_hi, qkv_lo, vt_hi, vt_lo, B, T, D, heads, o_hi, o_lo, true, st);
+    return attention_tc16_standalone(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, true, st);
+  }
   if (vt_hi) return attention_tc_launch(qkv_hi, qkv_lo, vt_hi, vt_lo, B, T, D, heads, o_hi, o_lo, out_f16, nullptr, st);
   return attention_tc_standalone(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, out_f16, nullptr, st);
 }
@@ -238,7 +246,9 @@ static int vit_block(const AnylocVitCfg* c, const AnylocVitBlock& wb, const VitB
   EpiParams e_qkv{tc_attn ? ANYLOC_EPI_QKV_SPLIT : ANYLOC_EPI_BIAS_SPLIT, wb.qkv_b, nullptr, nullptr, bf.qkv,
                   bf.qkv_lo, 3 * D};
   e_qkv.vt_hi = bf.vt_hi; e_qkv.vt_lo = bf.vt_lo;
-  e_qkv.qkv_T = T; e_qkv.qkv_Tp = attention_vt_pitch(T); e_qkv.qkv_D = D;
+  const bool f16_attn = tc_attn && f16;       // fp16 operands for the fp16-pair precision
+  e_qkv.qkv_T = T; e_qkv.qkv_Tp = f16_attn ? attention16_vt_pitch(T) : attention_vt_pitch(T); e_qkv.qkv_D = D;
+  e_qkv.qkv_f16 = f16_attn;
   e_qkv.alpha = wb.qkv_alpha;          // q,k,v always leave as tf32 pairs (attention input)
   if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.qkv_w_hi, wb.qkv_w_lo, D, M, 3 * D, D, e_qkv, engine, f16, st))) return rc;
   if ((rc = attention_dispatch(bf.qkv, bf.qkv_lo, tc_attn ? bf.vt_hi : nullptr, tc_attn ? bf.vt_lo : nullptr, B, T, D,
@@ -279,7 +289,8 @@ extern "C" int anyloc_vit_extract(const AnylocVitCfg* cfg, const AnylocVitWeight
     return ANYLOC_ERR_WORKSPACE;
   }
   int rc;
-  if (gemm_engine != ANYLOC_GEMM_SIMT && (attention_vt_pitch(T) != T)) {
+  if (gemm_engine != ANYLOC_GEMM_SIMT &&
+      (cfg->pair_dtype == ANYLOC_PAIR_F16 ? attention16_vt_pitch(T) != T : attention_vt_pitch(T) != T)) {
     // pad columns [T, Tp) of the transposed-V buffers are read by TMA but never written: keep them finite (zero)
     ANYLOC_CHECK_CUDA(cudaMemsetAsync(bf.vt_hi, 0, bf.vt_elems * sizeof(float), st));
     ANYLOC_CHECK_CUDA(cudaMemsetAsync(bf.vt_lo, 0, bf.vt_elems * sizeof(float), st));

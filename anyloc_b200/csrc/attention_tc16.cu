@@ -1,0 +1,496 @@
+// tcgen05 flash attention on fp16 (hi,lo) pairs -- the precision="f16x3" companion of attention_tc.cu.
+// Same algorithm (softmax(Q K^T / 8) V per head, head_dim 64, 3-term split on both GEMMs, round-to-nearest
+// accumulation of the per-block P.V chunks in registers), but every operand is an fp16 pair:
+//   q, k : (hi,lo) fp16 of 8*x, [B*T, 3D] (q | k thirds; written by the qkv GEMM's QKV_SPLIT epilogue)
+//   v    : (hi,lo) fp16 of 8*x, per-head TRANSPOSED vt[(b*heads+h)*64 + d][t] (row pitch Tp, multiple of 8)
+//   p    : (hi,lo) fp16 of 1024*p, packed two per 32-bit TMEM column as the A operand of the P.V MMAs
+// kind::f16 UMMAs take K=16 per instruction and, at 2 bytes per element, a 128-key block fits where the tf32
+// kernel holds 64 keys: 12 (S) + 24 (PV) UMMAs per 128 keys instead of 96 -- the measured bottleneck of the tf32
+// kernel was exactly the UMMA count (about 66-92 cycles each regardless of N).
+// Persistent CTAs, 384 threads: warp 0 = TMA (Q tile + 2-stage K ring), warp 3 = TMA (2-stage V^T ring),
+// warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-11 = softmax (two warps per 32-row lane quarter:
+// key halves of S / head-dim halves of O).
+#include <cuda.h>
+#include "common.cuh"
+
+namespace anyloc {
+namespace atc16 {
+
+constexpr int BQ = 128, BKV = 128, HD = 64, STAGES = 2;
+constexpr int THREADS = 128 + 256;
+constexpr int Q_HALF = BQ * 128;               // [128 rows x 64 fp16] = 16 KB (one 128-byte k-block)
+constexpr int Q_BYTES = 2 * Q_HALF;            // hi, lo
+constexpr int K_HALF = BKV * 128;              // [128 keys x 64 dims] = 16 KB
+constexpr int V_BOX = HD * 128;                // [64 dims x 64 keys] = 8 KB; two boxes per 128-key block
+constexpr int KSTAGE = 2 * K_HALF;             // K hi, lo: 32 KB
+constexpr int VSTAGE = 4 * V_BOX;              // V^T hi(2 boxes), lo(2 boxes): 32 KB
+constexpr int XCHG_BYTES = 6 * BQ * 4;
+constexpr int SMEM_BYTES = Q_BYTES + STAGES * (KSTAGE + VSTAGE) + 1024 + 256 + XCHG_BYTES;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t COL_S = 0;        // 2 x 128
+constexpr uint32_t COL_PHI = 256;    // 64 columns = 128 packed fp16
+constexpr uint32_t COL_PLO = 320;    // 64
+constexpr uint32_t COL_O = 384;      // 64
+constexpr float P_SCALE = 1024.0f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0; !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done && (it & 0x3ff) == 0x3ff) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {      // a -> low 16 bits (element k), b -> high (k+1)
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid_constant__ CUtensorMap tm_lo_qk,
+                      const __grid_constant__ CUtensorMap tm_hi_vt, const __grid_constant__ CUtensorMap tm_lo_vt,
+                      int B, int T, int D, void* __restrict__ o_hi, void* __restrict__ o_lo, int out_f16) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                                   // [hi][lo], 16 KB each
+  uint8_t* sK = smem + Q_BYTES;                         // STAGES x {K_hi, K_lo}
+  uint8_t* sV = sK + STAGES * KSTAGE;                   // STAGES x {Vt_hi box0, box1, Vt_lo box0, box1}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + STAGES * VSTAGE);
+  uint64_t* q_full = bars;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;             // [STAGES]
+  uint64_t* k_empty = k_full + STAGES;
+  uint64_t* v_full = k_empty + STAGES;
+  uint64_t* v_empty = v_full + STAGES;
+  uint64_t* s_full = v_empty + STAGES;     // [2]
+  uint64_t* p_full = s_full + 2;
+  uint64_t* o_full = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  float* xchg = reinterpret_cast<float*>(bars) + 64;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int heads = D / HD;
+  const int q_tiles = (T + BQ - 1) / BQ;
+  const int nblk = (T + BKV - 1) / BKV;
+  const int total = q_tiles * heads * B;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi_qk) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo_qk) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi_vt) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo_vt) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(smem_u32(q_full), 1); mbar_init(smem_u32(q_empty), 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(k_full + s), 1); mbar_init(smem_u32(k_empty + s), 1);
+      mbar_init(smem_u32(v_full + s), 1); mbar_init(smem_u32(v_empty + s), 1);
+    }
+    mbar_init(smem_u32(s_full), 1); mbar_init(smem_u32(s_full + 1), 1);
+    mbar_init(smem_u32(p_full), 8);
+    mbar_init(smem_u32(o_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------ TMA: Q tiles and the K ring
+      int g = 0, it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const int qt = w % q_tiles, h = (w / q_tiles) % heads, b = w / (q_tiles * heads);
+        const int row0 = b * T, colq = h * HD, colk = D + h * HD;
+        mbar_wait(smem_u32(q_empty), (uint32_t)((it & 1) ^ 1));
+        const uint32_t qb = smem_u32(q_full);
+        mbar_expect_tx(qb, Q_BYTES);
+        tma_load_2d(smem_u32(sQ), &tm_hi_qk, qb, colq, row0 + qt * BQ);
+        tma_load_2d(smem_u32(sQ + Q_HALF), &tm_lo_qk, qb, colq, row0 + qt * BQ);
+        for (int j = 0; j < nblk; ++j, ++g) {
+          const int stage = g % STAGES;
+          mbar_wait(smem_u32(k_empty + stage), (uint32_t)(((g / STAGES) & 1) ^ 1));
+          const uint32_t fb = smem_u32(k_full + stage);
+          mbar_expect_tx(fb, KSTAGE);
+          const uint32_t sb = smem_u32(sK + stage * KSTAGE);
+          tma_load_2d(sb, &tm_hi_qk, fb, colk, row0 + j * BKV);
+          tma_load_2d(sb + K_HALF, &tm_lo_qk, fb, colk, row0 + j * BKV);
+        }
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      // ------------------------------------------------ TMA: the V^T ring
+      int g = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int h = (w / q_tiles) % heads, b = w / (q_tiles * heads);
+        const int vrow = (b * heads + h) * HD;
+        for (int j = 0; j < nblk; ++j, ++g) {
+          const int stage = g % STAGES;
+          mbar_wait(smem_u32(v_empty + stage), (uint32_t)(((g / STAGES) & 1) ^ 1));
+          const uint32_t fb = smem_u32(v_full + stage);
+          mbar_expect_tx(fb, VSTAGE);
+          const uint32_t sb = smem_u32(sV + stage * VSTAGE);
+          tma_load_2d(sb + 0 * V_BOX, &tm_hi_vt, fb, j * BKV, vrow);
+          tma_load_2d(sb + 1 * V_BOX, &tm_hi_vt, fb, j * BKV + 64, vrow);
+          tma_load_2d(sb + 2 * V_BOX, &tm_lo_vt, fb, j * BKV, vrow);
+          tma_load_2d(sb + 3 * V_BOX, &tm_lo_vt, fb, j * BKV + 64, vrow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------ MMA issuer (kind::f16: a/b format 0 = F16, c format 1 = F32)
+      constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t)(BKV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      constexpr uint32_t idesc_pv = (1u << 4) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      const uint32_t q_base = smem_u32(sQ);
+      auto issue_s = [&](int gb) {
+        const int st = gb % STAGES;
+        mbar_wait(smem_u32(k_full + st), (uint32_t)((gb / STAGES) & 1));
+        tc_fence_after();
+        const uint32_t kb = smem_u32(sK + st * KSTAGE);
+        const uint32_t d = tmem_base + COL_S + (uint32_t)((gb & 1) * BKV);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {                  // 4 k-steps of 16 dims (32 bytes)
+          const uint32_t off = (uint32_t)(k * 32);
+          const uint64_t a_hi = desc_kmajor(q_base + off), a_lo = desc_kmajor(q_base + Q_HALF + off);
+          const uint64_t b_hi = desc_kmajor(kb + off), b_lo = desc_kmajor(kb + K_HALF + off);
+          umma_ss(d, a_hi, b_hi, idesc_s, k != 0);
+          umma_ss(d, a_lo, b_hi, idesc_s, 1u);
+          umma_ss(d, a_hi, b_lo, idesc_s, 1u);
+        }
+        umma_commit(smem_u32(s_full + (gb & 1)));
+        umma_commit(smem_u32(k_empty + st));
+      };
+      int g = 0, it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        mbar_wait(smem_u32(q_full), (uint32_t)(it & 1));
+        tc_fence_after();
+        issue_s(g);
+        if (nblk == 1) umma_commit(smem_u32(q_empty));
+        for (int j = 0; j < nblk; ++j) {
+          const int gb = g + j, st = gb % STAGES;
+          if (j + 1 < nblk) {
+            issue_s(gb + 1);
+            if (j + 2 == nblk) umma_commit(smem_u32(q_empty));
+          }
+          mbar_wait(smem_u32(v_full + st), (uint32_t)((gb / STAGES) & 1));
+          mbar_wait(smem_u32(p_full), (uint32_t)(gb & 1));
+          tc_fence_after();
+          const uint32_t vb = smem_u32(sV + st * VSTAGE);
+          const uint32_t d = tmem_base + COL_O;
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k) {                // 8 k-steps of 16 keys
+            const uint32_t voff = (uint32_t)((k >> 2) * V_BOX + (k & 3) * 32);
+            const uint64_t v_hi = desc_kmajor(vb + voff), v_lo = desc_kmajor(vb + 2 * V_BOX + voff);
+            const uint32_t p_hi = tmem_base + COL_PHI + (uint32_t)(k * 8), p_lo = tmem_base + COL_PLO + (uint32_t)(k * 8);
+            umma_ts(d, p_hi, v_hi, idesc_pv, k != 0);
+            umma_ts(d, p_lo, v_hi, idesc_pv, 1u);
+            umma_ts(d, p_hi, v_lo, idesc_pv, 1u);
+          }
+          umma_commit(smem_u32(o_full));
+          umma_commit(smem_u32(v_empty + st));
+        }
+        g += nblk;
+      }
+    }
+  } else if (warp >= 4) {
+    // -------------------------------------------------- softmax + RN accumulation
+    const int qd = warp & 3, half = (warp - 4) >> 2;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
+    // S holds (8q).(8k): fold 1/64 into the 1/sqrt(64)*log2(e) scale
+    const float kScale = 0.125f * 1.4426950408889634f * (1.0f / (kActScale * kActScale));
+    int g = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int qt = w % q_tiles, h = (w / q_tiles) % heads, b = w / (q_tiles * heads);
+      const int qrow = qt * BQ + row;
+      float m = -INFINITY, l = 0.f;
+      float o[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) o[c] = 0.f;
+      for (int j = 0; j < nblk; ++j) {
+        const int gb = g + j;
+        mbar_wait(smem_u32(s_full + (gb & 1)), (uint32_t)((gb >> 1) & 1));
+        tc_fence_after();
+        float s[64];
+        tmem_ld32(lane_addr + COL_S + (uint32_t)((gb & 1) * BKV + half * 64), s);
+        tmem_ld32(lane_addr + COL_S + (uint32_t)((gb & 1) * BKV + half * 64 + 32), s + 32);
+        if (j == nblk - 1) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) if (j * BKV + half * 64 + c >= T) s[c] = -INFINITY;
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 64; c += 4) {
+          s[c] *= kScale; s[c + 1] *= kScale; s[c + 2] *= kScale; s[c + 3] *= kScale;
+          mx0 = fmaxf(mx0, s[c]); mx1 = fmaxf(mx1, s[c + 1]); mx2 = fmaxf(mx2, s[c + 2]); mx3 = fmaxf(mx3, s[c + 3]);
+        }
+        const float pm = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        xchg[((gb & 1) * 2 + half) * BQ + row] = pm;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+        const float mx = fmaxf(m, fmaxf(pm, xchg[((gb & 1) * 2 + (half ^ 1)) * BQ + row]));
+        const float alpha = ex2(m - mx);
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; c += 4) {
+          s[c] = ex2(s[c] - mx); s[c + 1] = ex2(s[c + 1] - mx);
+          s[c + 2] = ex2(s[c + 2] - mx); s[c + 3] = ex2(s[c + 3] - mx);
+          r0 += s[c]; r1 += s[c + 1]; r2 += s[c + 2]; r3 += s[c + 3];
+        }
+        l = l * alpha + ((r0 + r1) + (r2 + r3));
+        m = mx;
+        if (j > 0) {
+          mbar_wait(smem_u32(o_full), (uint32_t)((gb - 1) & 1));
+          tc_fence_after();
+          float t[32];
+          tmem_ld32(lane_addr + COL_O + (uint32_t)(half * 32), t);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[c] = (o[c] + t[c]) * alpha;
+        }
+        // publish this warp's 64 key columns of P_j as packed fp16 pairs of 1024*p
+        {
+          uint32_t ph[32], pl[32];
+#pragma unroll
+          for (int c = 0; c < 64; c += 2) {
+            __half h0, l0, h1, l1;
+            split_f16(s[c] * P_SCALE, h0, l0); split_f16(s[c + 1] * P_SCALE, h1, l1);
+            ph[c >> 1] = pack_h2(h0, h1); pl[c >> 1] = pack_h2(l0, l1);
+          }
+          tmem_st32(lane_addr + COL_PHI + (uint32_t)(half * 32), ph);
+          tmem_st32(lane_addr + COL_PLO + (uint32_t)(half * 32), pl);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(p_full));
+      }
+      mbar_wait(smem_u32(o_full), (uint32_t)((g + nblk - 1) & 1));
+      tc_fence_after();
+      {
+        float t[32];
+        tmem_ld32(lane_addr + COL_O + (uint32_t)(half * 32), t);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) o[c] += t[c];
+      }
+      g += nblk;
+      xchg[(4 + half) * BQ + row] = l;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+      // o holds (1024 p) . (8 v): undo both scales together with the softmax denominator
+      const float inv = 1.0f / ((l + xchg[(4 + (half ^ 1)) * BQ + row]) * (P_SCALE * kActScale));
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+      if (qrow < T) {
+        const size_t off = ((size_t)b * T + qrow) * D + (size_t)h * HD + half * 32;
+        if (out_f16) {
+          uint4* ph = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(o_hi) + off);
+          uint4* pl = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(o_lo) + off);
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            __half hh[8], ll[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) split_f16(o[c + q] * inv * kActScale, hh[q], ll[q]);
+            ph[c >> 3] = *reinterpret_cast<uint4*>(hh); pl[c >> 3] = *reinterpret_cast<uint4*>(ll);
+          }
+        } else {
+          float4* ph = reinterpret_cast<float4*>(reinterpret_cast<float*>(o_hi) + off);
+          float4* pl = reinterpret_cast<float4*>(reinterpret_cast<float*>(o_lo) + off);
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            float4 hh, ll;
+            split_tf32(o[c] * inv, hh.x, ll.x); split_tf32(o[c + 1] * inv, hh.y, ll.y);
+            split_tf32(o[c + 2] * inv, hh.z, ll.z); split_tf32(o[c + 3] * inv, hh.w, ll.w);
+            ph[c >> 2] = hh; pl[c >> 2] = ll;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// fp32 (hi,lo) qkv pairs -> fp16 pairs of 8*x for q,k (same [M,3D] layout; the v third is left untouched) and the
+// per-head transposed fp16 V^T.  Standalone building-block path only.
+__global__ void __launch_bounds__(128)
+qkv_to_f16_kernel(const float* __restrict__ qkv_hi, const float* __restrict__ qkv_lo, int T, int Tp, int D,
+                  __half* __restrict__ q16_hi, __half* __restrict__ q16_lo, __half* __restrict__ vt_hi,
+                  __half* __restrict__ vt_lo) {
+  const int t = blockIdx.x * 128 + threadIdx.x, h = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  const size_t rowoff = ((size_t)b * T + t) * 3 * D;
+  for (int part = 0; part < 2; ++part) {
+    const size_t src = rowoff + (size_t)part * D + (size_t)h * HD;
+    for (int d = 0; d < HD; ++d) {
+      __half hh, ll; split_f16((qkv_hi[src + d] + qkv_lo[src + d]) * kActScale, hh, ll);
+      q16_hi[src + d] = hh; q16_lo[src + d] = ll;
+    }
+  }
+  const size_t src = rowoff + 2 * (size_t)D + (size_t)h * HD;
+  const size_t dst = ((size_t)b * D + (size_t)h * HD) * Tp + t;
+  for (int d = 0; d < HD; ++d) {
+    __half hh, ll; split_f16((qkv_hi[src + d] + qkv_lo[src + d]) * kActScale, hh, ll);
+    vt_hi[dst + (size_t)d * Tp] = hh; vt_lo[dst + (size_t)d * Tp] = ll;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("attention_tc16: cuTensorMapEncodeTiled unavailable"); return ANYLOC_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("attention_tc16: cuTensorMapEncodeTiled failed (%d)", (int)r); return ANYLOC_ERR_CUDA; }
+  return ANYLOC_OK;
+}
+
+}  // namespace atc16
+
+int attention16_vt_pitch(int T) { return (T + 7) & ~7; }     // fp16 rows: multiple of 16 bytes
+
+// qk16_{hi,lo}: fp16 [B*T, 3D] (q | k thirds of 8*x); vt16_{hi,lo}: fp16 [B*D, Tp], pad columns zero.
+int attention_tc16_launch(const void* qk_hi, const void* qk_lo, const void* vt_hi, const void* vt_lo, int B, int T,
+                          int D, int heads, void* o_hi, void* o_lo, bool out_f16, cudaStream_t st) {
+  using namespace atc16;
+  ANYLOC_REQUIRE(D == heads * HD, "attention_tc16: head_dim must be 64 (D=%d heads=%d)", D, heads);
+  CUtensorMap hqk, lqk, hvt, lvt;
+  int rc;
+  const int Tp = attention16_vt_pitch(T);
+  if ((rc = make_map(&hqk, qk_hi, (int64_t)B * T, 3 * (int64_t)D, BQ))) return rc;
+  if ((rc = make_map(&lqk, qk_lo, (int64_t)B * T, 3 * (int64_t)D, BQ))) return rc;
+  if ((rc = make_map(&hvt, vt_hi, (int64_t)B * D, Tp, HD))) return rc;
+  if ((rc = make_map(&lvt, vt_lo, (int64_t)B * D, Tp, HD))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const int total = cdiv(T, BQ) * heads * B;
+  attention_tc16_kernel<<<std::min(total, device_sm_count()), THREADS, SMEM_BYTES, st>>>(hqk, lqk, hvt, lvt, B, T, D,
+                                                                                         o_hi, o_lo, out_f16 ? 1 : 0);
+  ANYLOC_CHECK_LAUNCH();
+  return ANYLOC_OK;
+}
+
+// standalone: converts fp32 (hi,lo) qkv into the fp16 operand layout in a stream-ordered temporary first
+int attention_tc16_standalone(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads, void* o_hi,
+                              void* o_lo, bool out_f16, cudaStream_t st) {
+  const int Tp = attention16_vt_pitch(T);
+  const size_t nq = (size_t)B * T * 3 * D, nv = (size_t)B * D * Tp;
+  __half* buf = nullptr;
+  ANYLOC_CHECK_CUDA(cudaMallocAsync((void**)&buf, (2 * nq + 2 * nv) * sizeof(__half), st));
+  ANYLOC_CHECK_CUDA(cudaMemsetAsync(buf, 0, (2 * nq + 2 * nv) * sizeof(__half), st));
+  __half *q_hi = buf, *q_lo = buf + nq, *v_hi = buf + 2 * nq, *v_lo = buf + 2 * nq + nv;
+  atc16::qkv_to_f16_kernel<<<dim3(cdiv(T, 128), heads, B), 128, 0, st>>>(qkv_hi, qkv_lo, T, Tp, D, q_hi, q_lo, v_hi, v_lo);
+  ANYLOC_CHECK_LAUNCH();
+  int rc = attention_tc16_launch(q_hi, q_lo, v_hi, v_lo, B, T, D, heads, o_hi, o_lo, out_f16, st);
+  cudaFreeAsync(buf, st);
+  return rc;
+}
+
+}  // namespace anyloc

@@ -17,6 +17,7 @@ struct EpiParams {
   float* vt_hi = nullptr;
   float* vt_lo = nullptr;
   int qkv_T = 0, qkv_Tp = 0, qkv_D = 0;
+  int qkv_f16 = 0;      // QKV_SPLIT: q,k and V^T as fp16 pairs of kActScale*x (out/out_lo/vt_* point to __half)
   float alpha = 1.0f;   // accumulator scale (1/(s_A*s_B) for fp16-pair inputs, else 1)
   int out_f16 = 0;      // SPLIT outputs as fp16 pairs of kActScale*v (out/out_lo then point to __half)
 };
@@ -34,8 +35,13 @@ __device__ __forceinline__ void epi_store_vt(const EpiParams& p, int m, int n, f
   // n in [2D, 3D): head h = (n-2D)/64, dim d = (n-2D)%64; row m = b*T + t
   const int c = n - 2 * p.qkv_D, b = m / p.qkv_T, t = m - b * p.qkv_T;
   const size_t o = ((size_t)b * p.qkv_D + c) * p.qkv_Tp + t;      // (b*heads + h)*64 + d == b*D + c
-  float h, l; split_tf32(v, h, l);
-  p.vt_hi[o] = h; p.vt_lo[o] = l;
+  if (p.qkv_f16) {
+    __half h, l; split_f16(v * kActScale, h, l);
+    reinterpret_cast<__half*>(p.vt_hi)[o] = h; reinterpret_cast<__half*>(p.vt_lo)[o] = l;
+  } else {
+    float h, l; split_tf32(v, h, l);
+    p.vt_hi[o] = h; p.vt_lo[o] = l;
+  }
 }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -53,7 +59,10 @@ __device__ __forceinline__ void epi_store1(const EpiParams& p, int m, int n, flo
     case ANYLOC_EPI_LS_RESID: p.out[o] = p.resid[o] + __ldg(p.gamma + n) * v; break;
     case ANYLOC_EPI_QKV_SPLIT:
       if (n >= 2 * p.qkv_D) epi_store_vt(p, m, n, v);
-      else { float h, l; split_tf32(v, h, l); p.out[o] = h; p.out_lo[o] = l; }
+      else if (p.qkv_f16) {
+        __half h, l; split_f16(v * kActScale, h, l);
+        reinterpret_cast<__half*>(p.out)[o] = h; reinterpret_cast<__half*>(p.out_lo)[o] = l;
+      } else { float h, l; split_tf32(v, h, l); p.out[o] = h; p.out_lo[o] = l; }
       break;
     default: break;
   }

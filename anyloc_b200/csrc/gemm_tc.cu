@@ -168,10 +168,16 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, i
     const size_t o0 = ((size_t)b * ep.qkv_D + c0) * ep.qkv_Tp + t;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      float h, l;
-      split_tf32(v[j] * al + (ep.bias ? __ldg(ep.bias + n + j) : 0.f), h, l);
-      ep.vt_hi[o0 + (size_t)j * ep.qkv_Tp] = h;
-      ep.vt_lo[o0 + (size_t)j * ep.qkv_Tp] = l;
+      const float x = v[j] * al + (ep.bias ? __ldg(ep.bias + n + j) : 0.f);
+      if (ep.qkv_f16) {
+        __half h, l; split_f16(x * kActScale, h, l);
+        reinterpret_cast<__half*>(ep.vt_hi)[o0 + (size_t)j * ep.qkv_Tp] = h;
+        reinterpret_cast<__half*>(ep.vt_lo)[o0 + (size_t)j * ep.qkv_Tp] = l;
+      } else {
+        float h, l; split_tf32(x, h, l);
+        ep.vt_hi[o0 + (size_t)j * ep.qkv_Tp] = h;
+        ep.vt_lo[o0 + (size_t)j * ep.qkv_Tp] = l;
+      }
     }
     return;
   }
@@ -203,7 +209,13 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, i
       float4 g = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + j));
       reinterpret_cast<float4*>(ep.out + o)[j >> 2] =
           make_float4(r.x + g.x * x.x, r.y + g.y * x.y, r.z + g.z * x.z, r.w + g.w * x.w);
-    } else if (qkv) {   // q,k thirds: always tf32 pairs (attention input)
+    } else if (qkv && ep.qkv_f16) {   // q,k thirds as fp16 pairs (f16 attention input)
+      __half h[4], l[4];
+      split_f16(x.x * kActScale, h[0], l[0]); split_f16(x.y * kActScale, h[1], l[1]);
+      split_f16(x.z * kActScale, h[2], l[2]); split_f16(x.w * kActScale, h[3], l[3]);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out) + o + j) = *reinterpret_cast<uint2*>(h);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out_lo) + o + j) = *reinterpret_cast<uint2*>(l);
+    } else if (qkv) {   // q,k thirds as tf32 pairs (tf32 attention input)
       float4 h, l;
       split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
       reinterpret_cast<float4*>(ep.out + o)[j >> 2] = h;
