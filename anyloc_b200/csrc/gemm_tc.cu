@@ -90,6 +90,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Tile raster: bands of BAND_N column blocks; inside a band the tiles run n-fastest over all row blocks.  The ~148
+// resident CTAs then share a few A row panels and ONE band of B (<= BAND_N*256 rows of hi+lo) that stays in L2 while
+// the outputs stream through it; with a plain n-fastest raster over a wide N the whole B matrix (50-100 MB) is
+// evicted and re-read from HBM by every wave (ncu: up to 10x the algorithmic DRAM traffic on the w12 GEMM).
+constexpr int BAND_N = 8;
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
+  const int per_band = num_m * BAND_N;
+  const int band = tile / per_band, r = tile - band * per_band;
+  const int w = min(BAND_N, num_n - band * BAND_N);       // width of this (possibly last, narrower) band
+  m_blk = r / w;
+  n_blk = band * BAND_N + (r - m_blk * w);
+}
+
 template <bool F16>
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                      uint32_t accumulate) {
@@ -283,7 +296,8 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       const uint32_t tx_bytes = A_BYTES * (1 + ((LO && has_a_lo) ? 1 : 0)) + C::B_BYTES * (1 + ((LO && has_b_lo) ? 1 : 0));
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+        int mb, nb; tile_coords(tile, num_m, num_n, mb, nb);
+        const int m0 = mb * BM, n0 = nb * BN;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
           const uint32_t fb = smem_u32(full_bar + stage);
@@ -340,7 +354,8 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     constexpr int CPT = BN / 4;              // columns per thread
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+      int mb, nb; tile_coords(tile, num_m, num_n, mb, nb);
+      const int m0 = mb * BM, n0 = nb * BN;
       float sum[CPT];
 #pragma unroll
       for (int j = 0; j < CPT; ++j) sum[j] = 0.f;
