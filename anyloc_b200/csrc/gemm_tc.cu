@@ -20,6 +20,7 @@
 // Tiles are rastered n-fastest so that the CTAs resident at any moment share a handful of A row
 // panels and the whole B matrix in L2.
 #include <cuda.h>
+#include <stdlib.h>
 #include "epilogue.cuh"
 
 namespace anyloc {
@@ -94,13 +95,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 // resident CTAs then share a few A row panels and ONE band of B (<= BAND_N*256 rows of hi+lo) that stays in L2 while
 // the outputs stream through it; with a plain n-fastest raster over a wide N the whole B matrix (50-100 MB) is
 // evicted and re-read from HBM by every wave (ncu: up to 10x the algorithmic DRAM traffic on the w12 GEMM).
-constexpr int BAND_N = 8;
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
-  const int per_band = num_m * BAND_N;
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int band_n, int& m_blk, int& n_blk) {
+  const int per_band = num_m * band_n;
   const int band = tile / per_band, r = tile - band * per_band;
-  const int w = min(BAND_N, num_n - band * BAND_N);       // width of this (possibly last, narrower) band
+  const int w = min(band_n, num_n - band * band_n);       // width of this (possibly last, narrower) band
   m_blk = r / w;
-  n_blk = band * BAND_N + (r - m_blk * w);
+  n_blk = band * band_n + (r - m_blk * w);
 }
 
 template <bool F16>
@@ -246,7 +246,7 @@ template <int BN, bool F16, bool LO>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                int M, int N, int K, int has_a_lo, int has_b_lo, EpiParams ep) {
+                int M, int N, int K, int has_a_lo, int has_b_lo, int band_n, EpiParams ep) {
   using C = Cfg<BN, LO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -296,7 +296,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       const uint32_t tx_bytes = A_BYTES * (1 + ((LO && has_a_lo) ? 1 : 0)) + C::B_BYTES * (1 + ((LO && has_b_lo) ? 1 : 0));
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        int mb, nb; tile_coords(tile, num_m, num_n, mb, nb);
+        int mb, nb; tile_coords(tile, num_m, num_n, band_n, mb, nb);
         const int m0 = mb * BM, n0 = nb * BN;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
@@ -354,7 +354,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     constexpr int CPT = BN / 4;              // columns per thread
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      int mb, nb; tile_coords(tile, num_m, num_n, mb, nb);
+      int mb, nb; tile_coords(tile, num_m, num_n, band_n, mb, nb);
       const int m0 = mb * BM, n0 = nb * BN;
       float sum[CPT];
 #pragma unroll
@@ -390,6 +390,212 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
+// ====================================================================================================================
+// 2-CTA variant (cta_group::2): a CTA pair (cluster of 2, same TPC) owns one 256 x 256 tile.  Each CTA loads ITS 128
+// rows of A and ITS 128 of the 256 B rows (half the B bytes per SM -- the 1-CTA kernel needs ~62 B/clk/SM of L2->smem
+// ingest, right at the per-SM limit), the leader CTA issues M256 x N256 UMMAs that read both CTAs' shared memory, and
+// each CTA drains / post-processes its own 128 accumulator rows exactly like the 1-CTA kernel.  64 KB per stage ->
+// 3-stage ring.  Barriers: `full` lives in the leader (armed once with the bytes of BOTH CTAs; both CTAs' TMA
+// complete_tx on it), `empty` / `tfull` are signalled in both CTAs by multicast tcgen05.commit, `tempty` collects
+// the drain arrivals of all 32 accumulate warps of the pair in the leader.
+// ====================================================================================================================
+namespace two {
+constexpr int BH_BYTES = 128 * 128;                       // half of the B tile: 128 rows x 128 B
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;    // A_hi, A_lo, Bh_hi, Bh_lo = 64 KB
+constexpr int STAGES = 3;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int BN = 256;
+}  // namespace two
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t local) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(local)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void umma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (F16)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {       // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile(
+      "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+      ::"r"(bar) : "memory");
+}
+
+template <bool F16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm_tc3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                     const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                     int M, int N, int K, int band_n, EpiParams ep) {
+  using namespace two;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* bar_area = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_area);          // [STAGES]  (used in the leader)
+  uint64_t* empty_bar = full_bar + STAGES;                              // [STAGES]
+  uint64_t* tfull_bar = empty_bar + STAGES;                             // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                                 // [2]       (used in the leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();                 // 0 = leader
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_m = (M + 255) / 256, num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  constexpr int BKE = F16 ? 64 : 32;
+  constexpr int CHUNK_KB = F16 ? CHUNK_KB_F16 : CHUNK_KB_TF32;
+  const int num_k = (K + BKE - 1) / BKE;
+  const int num_chunks = (num_k + CHUNK_KB - 1) / CHUNK_KB;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_lo) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), 2 * EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                   // both CTAs' barriers are initialised before any remote use
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0 && lane == 0) {
+      // ------------------------------------------------ TMA producer (both CTAs; bytes land on the leader's barrier)
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        int mb, nb; tile_coords(tile, num_m, num_n, band_n, mb, nb);
+        const int m0 = mb * 256 + (int)rank * 128, n0 = nb * BN + (int)rank * 128;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+          const uint32_t fb_local = smem_u32(full_bar + stage);
+          if (rank == 0) mbar_expect_tx(fb_local, 2u * STAGE_BYTES);
+          const uint32_t fb = mapa_rank0(fb_local);
+          const uint32_t sbase = smem_u32(smem + stage * STAGE_BYTES);
+          tma_load_2d_2sm(sbase, &tm_a_hi, fb, kb * BKE, m0);
+          tma_load_2d_2sm(sbase + A_BYTES, &tm_a_lo, fb, kb * BKE, m0);
+          tma_load_2d_2sm(sbase + 2 * A_BYTES, &tm_b_hi, fb, kb * BKE, n0);
+          tma_load_2d_2sm(sbase + 2 * A_BYTES + BH_BYTES, &tm_b_lo, fb, kb * BKE, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+      // ------------------------------------------------ MMA issuer (leader CTA only): M256 x N256 per instruction
+      constexpr uint32_t fmt = F16 ? 0u : 2u;
+      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)(256 >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        for (int kb = 0; kb < num_k; ++kb) {
+          const int in_chunk = kb % CHUNK_KB;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+          if (in_chunk == 0) {
+            mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
+            tc_fence_after();
+          }
+          mbar_wait(smem_u32(full_bar + stage), phase);
+          tc_fence_after();
+          const uint32_t sbase = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t a_hi = make_desc(sbase), a_lo = make_desc(sbase + A_BYTES);
+          const uint64_t b_hi = make_desc(sbase + 2 * A_BYTES), b_lo = make_desc(sbase + 2 * A_BYTES + BH_BYTES);
+#pragma unroll
+          for (int k = 0; k < KSTEPS; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+            umma2<F16>(d_tmem, a_hi + adv, b_hi + adv, idesc, (in_chunk | k) != 0);
+            umma2<F16>(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+            umma2<F16>(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+          }
+          umma_commit_2sm(smem_u32(empty_bar + stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (in_chunk == CHUNK_KB - 1 || kb == num_k - 1) {
+            umma_commit_2sm(smem_u32(tfull_bar + acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------- accumulate (RN, registers) + epilogue: 16 warps per CTA, own 128 rows
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int q = warp & 3;
+    const int cq = (warp - 4) >> 2;
+    constexpr int CPT = BN / 4;
+    int acc = 0; uint32_t acc_phase = 0;
+    const uint32_t tempty_leader0 = mapa_rank0(smem_u32(tempty_bar)), tempty_leader1 = mapa_rank0(smem_u32(tempty_bar + 1));
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      int mb, nb; tile_coords(tile, num_m, num_n, band_n, mb, nb);
+      const int m0 = mb * 256 + (int)rank * 128, n0 = nb * BN;
+      float sum[CPT];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) sum[j] = 0.f;
+      for (int ch = 0; ch < num_chunks; ++ch) {
+        mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cq * CPT);
+#pragma unroll
+        for (int c = 0; c < CPT / 16; ++c) {
+          float v[16];
+          tmem_ld16(trow + (uint32_t)(c * 16), v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sum[c * 16 + j] += v[j];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      const int m = m0 + q * 32 + lane;
+      if (m < M) {
+#pragma unroll
+        for (int c = 0; c < CPT / 32; ++c) {
+          const int n = n0 + cq * CPT + c * 32;
+          if (n < N) epi_chunk32(ep, m, n, N, sum + c * 32);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                   // nobody exits (or frees TMEM) while the peer may still signal it
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -441,6 +647,30 @@ bool gemm_tc_supported(const void* a_hi, const void* a_lo, int lda, const void* 
   return true;
 }
 
+template <bool F16>
+static int launch_2cta(const void* a_hi, const void* a_lo, int lda, const void* b_hi, const void* b_lo, int ldb, int M,
+                       int N, int K, const EpiParams& ep, int band_n, cudaStream_t st) {
+  using namespace tc;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_map(&ma_hi, a_hi, M, K, lda, 128, F16))) return rc;
+  if ((rc = make_map(&ma_lo, a_lo, M, K, lda, 128, F16))) return rc;
+  if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, 128, F16))) return rc;
+  if ((rc = make_map(&mb_lo, b_lo, N, K, ldb, 128, F16))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_2cta_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           two::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = cdiv(M, 256) * cdiv(N, two::BN);
+  const int pairs = std::min(tiles, device_sm_count() / 2);
+  gemm_tc3_2cta_kernel<F16><<<2 * pairs, THREADS, two::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K,
+                                                                         std::min(band_n, cdiv(N, two::BN)), ep);
+  ANYLOC_CHECK_LAUNCH();
+  return ANYLOC_OK;
+}
+
 template <bool F16, bool LO>
 static int launch_impl(const void* a_hi, const void* a_lo, int lda, const void* b_hi, const void* b_lo, int ldb, int M,
                        int N, int K, const EpiParams& ep, cudaStream_t st) {
@@ -460,8 +690,10 @@ static int launch_impl(const void* a_hi, const void* a_lo, int lda, const void* 
   }
   const int tiles = cdiv(M, BM) * cdiv(N, BN);
   const int grid = std::min(tiles, device_sm_count());
-  gemm_tc3_kernel<BN, F16, LO><<<grid, THREADS, Cfg<BN, LO>::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K,
-                                                                               a_lo != nullptr, b_lo != nullptr, ep);
+  static int band_n = -1;
+  if (band_n < 0) { const char* e = getenv("ANYLOC_GEMM_BAND"); band_n = e ? atoi(e) : 8; if (band_n < 1) band_n = 1 << 20; }
+  gemm_tc3_kernel<BN, F16, LO><<<grid, THREADS, Cfg<BN, LO>::SMEM_BYTES, st>>>(
+      ma_hi, ma_lo, mb_hi, mb_lo, M, N, K, a_lo != nullptr, b_lo != nullptr, std::min(band_n, cdiv(N, BN)), ep);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }
@@ -469,6 +701,13 @@ static int launch_impl(const void* a_hi, const void* a_lo, int lda, const void* 
 int gemm_tc_launch(const void* a_hi, const void* a_lo, int lda, const void* b_hi, const void* b_lo, int ldb, int M,
                    int N, int K, const EpiParams& ep, bool f16, cudaStream_t st) {
   const bool lo = a_lo != nullptr || b_lo != nullptr;
+  static int band_n = -1, two_cta = -1;
+  if (band_n < 0) { const char* e = getenv("ANYLOC_GEMM_BAND"); band_n = e ? atoi(e) : 8; if (band_n < 1) band_n = 1 << 20; }
+  if (two_cta < 0) { const char* e = getenv("ANYLOC_GEMM_2CTA"); two_cta = e ? atoi(e) : 0; }
+  if (two_cta && a_lo && b_lo && M >= 512 && N >= 256) {
+    return f16 ? launch_2cta<true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, band_n, st)
+               : launch_2cta<false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, band_n, st);
+  }
   if (f16) return lo ? launch_impl<true, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st)
                      : launch_impl<true, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st);
   return lo ? launch_impl<false, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st)

@@ -162,42 +162,49 @@ vlad_rescore_kernel(const float* __restrict__ x, const int32_t* __restrict__ n_v
   smax = warp_max(smax); cmax = warp_max(cmax);
   // |S~_k - S_k| <= (2^-10 + 2^-11) sum|x_i c_i| <= 1.5 * 2^-10 |x||c_k| < 2^-9 |x||c_k|  (truncated x, rounded c)
   const float thresh = smax - 2.0f * (0.001953125f * xn * cmax) - 1e-30f;
-  float best = -INFINITY; int bestk = 0; int ncand = 0, lastk = 0;
+  float best = -INFINITY; int bestk = 0;
   for (int k0 = 0; k0 < K; k0 += 32) {
     const int k = k0 + lane;
     const bool cand = k < K && coarse[row * K + k] >= thresh;
     unsigned mask = __ballot_sync(0xffffffffu, cand);
     while (mask) {
-      const int kk = k0 + __ffs(mask) - 1;
-      mask &= mask - 1;
-      ++ncand; lastk = kk;
-      const float4* cr = reinterpret_cast<const float4*>(chat + (size_t)kk * D);
-      float acc = 0.f;
+      // up to four candidates at a time (independent accumulators hide the L1/L2 latency of the centre rows)
+      int kk[4]; int n = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (mask) { kk[q] = k0 + __ffs(mask) - 1; mask &= mask - 1; ++n; } else kk[q] = kk[0];
+      }
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < MAXV; ++i) {
         int d = lane + i * 32;
         if (d < D4) {
-          float4 c = __ldg(cr + d);
-          acc = fmaf(v[i].x, c.x, acc); acc = fmaf(v[i].y, c.y, acc);
-          acc = fmaf(v[i].z, c.z, acc); acc = fmaf(v[i].w, c.w, acc);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 c = __ldg(reinterpret_cast<const float4*>(chat + (size_t)kk[q] * D) + d);
+            acc[q] = fmaf(v[i].x, c.x, acc[q]); acc[q] = fmaf(v[i].y, c.y, acc[q]);
+            acc[q] = fmaf(v[i].z, c.z, acc[q]); acc[q] = fmaf(v[i].w, c.w, acc[q]);
+          }
         }
       }
-      const float sc = warp_sum(acc) + cbias[kk];
-      if (sc > best) { best = sc; bestk = kk; }          // ascending k, strict >: lowest index wins exact ties
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float sc = warp_sum(acc[q]) + cbias[kk[q]];
+        if (q < n && sc > best) { best = sc; bestk = kk[q]; }   // ascending k, strict >: lowest index wins exact ties
+      }
     }
   }
   if (lane == 0) {
     labels[row] = valid ? bestk : -1;
     if (inv_norm) inv_norm[row] = 1.0f / fmaxf(xn, 1e-12f);
   }
-  (void)ncand; (void)lastk;
 }
 
 // ------------------------------------------------------------------ accumulate v2
 // CTA = (image, 128-column slice); WARPS warps split the rows; lane owns 4 consecutive columns (float4).
 // Per-warp accumulators [K][128] in shared memory (no conflicts: a warp touches 512 contiguous bytes per row),
 // reduced across warps at the end in a fixed order -> deterministic.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 vlad_accumulate2_kernel(const float* __restrict__ x, const int32_t* __restrict__ labels,
                         const float* __restrict__ inv_norm, const float* __restrict__ centers,
                         int N, int D, int K, int norm_descs, int warps, float* __restrict__ vlad,
@@ -514,11 +521,12 @@ extern "C" int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, 
   int rc = launch_assign(feats, n_valid, N, (int64_t)R, D, K, centers, dist_mode, ab, labels, inv_norm, st);
   if (rc) return rc;
   // accumulate: as many row-splitting warps as shared memory allows ((1 + warps) * K * 128 floats), at most 8
-  int warps = (int)std::min<size_t>(8, (200 * 1024) / ((size_t)K * 128 * 4) - 1);
+  // 4 row-splitting warps when two CTAs then fit per SM ((1 + warps) * K * 128 floats each), else what fits in one
+  int warps = (int)std::min<size_t>(4, (200 * 1024) / ((size_t)K * 128 * 4) - 1);
   if (warps >= 1) {
     size_t smem = (size_t)(1 + warps) * K * 128 * 4;
     ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(vlad_accumulate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vlad_accumulate2_kernel<<<dim3(nslices, B), 256, smem, st>>>(feats, labels, inv_norm, centers, N, D, K, norm_descs,
+    vlad_accumulate2_kernel<<<dim3(nslices, B), 128, smem, st>>>(feats, labels, inv_norm, centers, N, D, K, norm_descs,
                                                                  warps, vlad, partial);
   } else {
     size_t smem = ((size_t)2 * K * ACC_COLS + 2 * (size_t)N) * 4;
