@@ -703,7 +703,7 @@ int gemm_tc_launch(const void* a_hi, const void* a_lo, int lda, const void* b_hi
   const bool lo = a_lo != nullptr || b_lo != nullptr;
   static int band_n = -1, two_cta = -1;
   if (band_n < 0) { const char* e = getenv("ANYLOC_GEMM_BAND"); band_n = e ? atoi(e) : 8; if (band_n < 1) band_n = 1 << 20; }
-  if (two_cta < 0) { const char* e = getenv("ANYLOC_GEMM_2CTA"); two_cta = e ? atoi(e) : 0; }
+  if (two_cta < 0) { const char* e = getenv("ANYLOC_GEMM_2CTA"); two_cta = e ? atoi(e) : 1; }
   if (two_cta && a_lo && b_lo && M >= 512 && N >= 256) {
     return f16 ? launch_2cta<true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, band_n, st)
                : launch_2cta<false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, band_n, st);
