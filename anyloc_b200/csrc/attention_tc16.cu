@@ -8,8 +8,8 @@
 // kernel holds 64 keys: 12 (S) + 24 (PV) UMMAs per 128 keys instead of 96 -- the measured bottleneck of the tf32
 // kernel was exactly the UMMA count (about 66-92 cycles each regardless of N).
 // Persistent CTAs, 384 threads: warp 0 = TMA (Q tile + 2-stage K ring), warp 3 = TMA (2-stage V^T ring),
-// warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-11 = softmax (two warps per 32-row lane quarter:
-// key halves of S / head-dim halves of O).
+// warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-19 = softmax (four warps per 32-row lane quarter:
+// 32-key quarters of S / 16-wide head-dim quarters of O -- the softmax, not the UMMAs, bounds this kernel).
 #include <cuda.h>
 #include "common.cuh"
 
@@ -17,14 +17,15 @@ namespace anyloc {
 namespace atc16 {
 
 constexpr int BQ = 128, BKV = 128, HD = 64, STAGES = 2;
-constexpr int THREADS = 128 + 256;
+constexpr int SM_WARPS = 16;                  // softmax warps: 4 TMEM lane quarters x 4 key / head-dim quarters
+constexpr int THREADS = 128 + SM_WARPS * 32;
 constexpr int Q_HALF = BQ * 128;               // [128 rows x 64 fp16] = 16 KB (one 128-byte k-block)
 constexpr int Q_BYTES = 2 * Q_HALF;            // hi, lo
 constexpr int K_HALF = BKV * 128;              // [128 keys x 64 dims] = 16 KB
 constexpr int V_BOX = HD * 128;                // [64 dims x 64 keys] = 8 KB; two boxes per 128-key block
 constexpr int KSTAGE = 2 * K_HALF;             // K hi, lo: 32 KB
 constexpr int VSTAGE = 4 * V_BOX;              // V^T hi(2 boxes), lo(2 boxes): 32 KB
-constexpr int XCHG_BYTES = 6 * BQ * 4;
+constexpr int XCHG_BYTES = 12 * BQ * 4;        // row max: 2 slots x 4 parts; row sum: 4 parts
 constexpr int SMEM_BYTES = Q_BYTES + STAGES * (KSTAGE + VSTAGE) + 1024 + 256 + XCHG_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t COL_S = 0;        // 2 x 128
@@ -118,6 +119,25 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {      // a -> low 16 bits (element k), b -> high (k+1)
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
@@ -164,7 +184,7 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
       mbar_init(smem_u32(v_full + s), 1); mbar_init(smem_u32(v_empty + s), 1);
     }
     mbar_init(smem_u32(s_full), 1); mbar_init(smem_u32(s_full + 1), 1);
-    mbar_init(smem_u32(p_full), 8);
+    mbar_init(smem_u32(p_full), SM_WARPS);
     mbar_init(smem_u32(o_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -178,6 +198,8 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
+  // register re-balancing inside the launch-time pool (640 x 96): 128 x 40 + 512 x 104 <= 61440
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------ TMA: Q tiles and the K ring
@@ -278,8 +300,9 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
       }
     }
   } else if (warp >= 4) {
-    // -------------------------------------------------- softmax + RN accumulation
-    const int qd = warp & 3, half = (warp - 4) >> 2;
+    // -------------------------------------------------- softmax + RN accumulation (16 warps)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int qd = warp & 3, part = (warp - 4) >> 2;       // part: keys [32*part,+32) of S, dims [16*part,+16) of O
     const int row = qd * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
     // S holds (8q).(8k): fold 1/64 into the 1/sqrt(64)*log2(e) scale
@@ -288,35 +311,35 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int qt = w % q_tiles, h = (w / q_tiles) % heads, b = w / (q_tiles * heads);
       const int qrow = qt * BQ + row;
-      float m = -INFINITY, l = 0.f;
-      float o[32];
+      float m = -INFINITY, l = 0.f;                         // l: this warp's quarter of the row sum
+      float o[16];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) o[c] = 0.f;
+      for (int c = 0; c < 16; ++c) o[c] = 0.f;
       for (int j = 0; j < nblk; ++j) {
         const int gb = g + j;
         mbar_wait(smem_u32(s_full + (gb & 1)), (uint32_t)((gb >> 1) & 1));
         tc_fence_after();
-        float s[64];
-        tmem_ld32(lane_addr + COL_S + (uint32_t)((gb & 1) * BKV + half * 64), s);
-        tmem_ld32(lane_addr + COL_S + (uint32_t)((gb & 1) * BKV + half * 64 + 32), s + 32);
+        float s[32];
+        tmem_ld32(lane_addr + COL_S + (uint32_t)((gb & 1) * BKV + part * 32), s);
         if (j == nblk - 1) {
 #pragma unroll
-          for (int c = 0; c < 64; ++c) if (j * BKV + half * 64 + c >= T) s[c] = -INFINITY;
+          for (int c = 0; c < 32; ++c) if (j * BKV + part * 32 + c >= T) s[c] = -INFINITY;
         }
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 64; c += 4) {
+        for (int c = 0; c < 32; c += 4) {
           s[c] *= kScale; s[c + 1] *= kScale; s[c + 2] *= kScale; s[c + 3] *= kScale;
           mx0 = fmaxf(mx0, s[c]); mx1 = fmaxf(mx1, s[c + 1]); mx2 = fmaxf(mx2, s[c + 2]); mx3 = fmaxf(mx3, s[c + 3]);
         }
         const float pm = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        xchg[((gb & 1) * 2 + half) * BQ + row] = pm;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
-        const float mx = fmaxf(m, fmaxf(pm, xchg[((gb & 1) * 2 + (half ^ 1)) * BQ + row]));
+        float* slot = xchg + (gb & 1) * 4 * BQ;
+        slot[part * BQ + row] = pm;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + qd) : "memory");      // the four warps of this lane quarter
+        const float mx = fmaxf(fmaxf(m, slot[row]), fmaxf(fmaxf(slot[BQ + row], slot[2 * BQ + row]), slot[3 * BQ + row]));
         const float alpha = ex2(m - mx);
         float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 64; c += 4) {
+        for (int c = 0; c < 32; c += 4) {
           s[c] = ex2(s[c] - mx); s[c + 1] = ex2(s[c + 1] - mx);
           s[c + 2] = ex2(s[c + 2] - mx); s[c + 3] = ex2(s[c + 3] - mx);
           r0 += s[c]; r1 += s[c + 1]; r2 += s[c + 2]; r3 += s[c + 3];
@@ -326,22 +349,22 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
         if (j > 0) {
           mbar_wait(smem_u32(o_full), (uint32_t)((gb - 1) & 1));
           tc_fence_after();
-          float t[32];
-          tmem_ld32(lane_addr + COL_O + (uint32_t)(half * 32), t);
+          float t[16];
+          tmem_ld16(lane_addr + COL_O + (uint32_t)(part * 16), t);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) o[c] = (o[c] + t[c]) * alpha;
+          for (int c = 0; c < 16; ++c) o[c] = (o[c] + t[c]) * alpha;
         }
-        // publish this warp's 64 key columns of P_j as packed fp16 pairs of 1024*p
+        // publish this warp's 32 key columns of P_j as packed fp16 pairs of 1024*p (16 TMEM columns each)
         {
-          uint32_t ph[32], pl[32];
+          uint32_t ph[16], pl[16];
 #pragma unroll
-          for (int c = 0; c < 64; c += 2) {
+          for (int c = 0; c < 32; c += 2) {
             __half h0, l0, h1, l1;
             split_f16(s[c] * P_SCALE, h0, l0); split_f16(s[c + 1] * P_SCALE, h1, l1);
             ph[c >> 1] = pack_h2(h0, h1); pl[c >> 1] = pack_h2(l0, l1);
           }
-          tmem_st32(lane_addr + COL_PHI + (uint32_t)(half * 32), ph);
-          tmem_st32(lane_addr + COL_PLO + (uint32_t)(half * 32), pl);
+          tmem_st16(lane_addr + COL_PHI + (uint32_t)(part * 16), ph);
+          tmem_st16(lane_addr + COL_PLO + (uint32_t)(part * 16), pl);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         tc_fence_before();
@@ -351,24 +374,26 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
       mbar_wait(smem_u32(o_full), (uint32_t)((g + nblk - 1) & 1));
       tc_fence_after();
       {
-        float t[32];
-        tmem_ld32(lane_addr + COL_O + (uint32_t)(half * 32), t);
+        float t[16];
+        tmem_ld16(lane_addr + COL_O + (uint32_t)(part * 16), t);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) o[c] += t[c];
+        for (int c = 0; c < 16; ++c) o[c] += t[c];
       }
       g += nblk;
-      xchg[(4 + half) * BQ + row] = l;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+      float* lsum = xchg + 8 * BQ;
+      lsum[part * BQ + row] = l;
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + qd) : "memory");
       // o holds (1024 p) . (8 v): undo both scales together with the softmax denominator
-      const float inv = 1.0f / ((l + xchg[(4 + (half ^ 1)) * BQ + row]) * (P_SCALE * kActScale));
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+      const float ltot = (lsum[row] + lsum[BQ + row]) + (lsum[2 * BQ + row] + lsum[3 * BQ + row]);
+      const float inv = 1.0f / (ltot * (P_SCALE * kActScale));
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + qd) : "memory");        // slot reusable by the next work item
       if (qrow < T) {
-        const size_t off = ((size_t)b * T + qrow) * D + (size_t)h * HD + half * 32;
+        const size_t off = ((size_t)b * T + qrow) * D + (size_t)h * HD + part * 16;
         if (out_f16) {
           uint4* ph = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(o_hi) + off);
           uint4* pl = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(o_lo) + off);
 #pragma unroll
-          for (int c = 0; c < 32; c += 8) {
+          for (int c = 0; c < 16; c += 8) {
             __half hh[8], ll[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) split_f16(o[c + q] * inv * kActScale, hh[q], ll[q]);
@@ -378,7 +403,7 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
           float4* ph = reinterpret_cast<float4*>(reinterpret_cast<float*>(o_hi) + off);
           float4* pl = reinterpret_cast<float4*>(reinterpret_cast<float*>(o_lo) + off);
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
+          for (int c = 0; c < 16; c += 4) {
             float4 hh, ll;
             split_tf32(o[c] * inv, hh.x, ll.x); split_tf32(o[c + 1] * inv, hh.y, ll.y);
             split_tf32(o[c + 2] * inv, hh.z, ll.z); split_tf32(o[c + 3] * inv, hh.w, ll.w);
