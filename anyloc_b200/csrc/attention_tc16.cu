@@ -145,7 +145,8 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {      // a -> l
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid_constant__ CUtensorMap tm_lo_qk,
                       const __grid_constant__ CUtensorMap tm_hi_vt, const __grid_constant__ CUtensorMap tm_lo_vt,
-                      int B, int T, int D, void* __restrict__ o_hi, void* __restrict__ o_lo, int out_f16) {
+                      int B, int T, int D, void* __restrict__ o_hi, void* __restrict__ o_lo, int out_f16,
+                      float* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                                   // [hi][lo], 16 KB each
@@ -269,19 +270,27 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
       };
       int g = 0, it = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const bool tdump = dbg != nullptr && it == 1 && blockIdx.x == 0;
+        const long long tb = tdump ? clock64() : 0;
+#define MSTAMP(jj, slot) do { if (tdump) dbg[(jj) * 16 + 8 + (slot)] = (float)(clock64() - tb); } while (0)
         mbar_wait(smem_u32(q_full), (uint32_t)(it & 1));
         tc_fence_after();
+        MSTAMP(0, 0);
         issue_s(g);
+        MSTAMP(0, 1);
         if (nblk == 1) umma_commit(smem_u32(q_empty));
         for (int j = 0; j < nblk; ++j) {
           const int gb = g + j, st = gb % STAGES;
           if (j + 1 < nblk) {
+            MSTAMP(j + 1, 0);
             issue_s(gb + 1);
+            MSTAMP(j + 1, 1);
             if (j + 2 == nblk) umma_commit(smem_u32(q_empty));
           }
           mbar_wait(smem_u32(v_full + st), (uint32_t)((gb / STAGES) & 1));
           mbar_wait(smem_u32(p_full), (uint32_t)(gb & 1));
           tc_fence_after();
+          MSTAMP(j, 2);
           const uint32_t vb = smem_u32(sV + st * VSTAGE);
           const uint32_t d = tmem_base + COL_O;
 #pragma unroll
@@ -294,6 +303,7 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
             umma_ts(d, p_hi, v_lo, idesc_pv, 1u);
           }
           umma_commit(smem_u32(o_full));
+          MSTAMP(j, 3);
           umma_commit(smem_u32(v_empty + st));
         }
         g += nblk;
@@ -311,16 +321,22 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int qt = w % q_tiles, h = (w / q_tiles) % heads, b = w / (q_tiles * heads);
       const int qrow = qt * BQ + row;
+      const bool tdump = dbg != nullptr && w == (int)gridDim.x && blockIdx.x == 0 && warp == 4 && lane == 0;
+      const long long tb = tdump ? clock64() : 0;
+#define TSTAMP(slot) do { if (tdump) dbg[j * 16 + (slot)] = (float)(clock64() - tb); } while (0)
       float m = -INFINITY, l = 0.f;                         // l: this warp's quarter of the row sum
       float o[16];
 #pragma unroll
       for (int c = 0; c < 16; ++c) o[c] = 0.f;
       for (int j = 0; j < nblk; ++j) {
         const int gb = g + j;
+        TSTAMP(0);
         mbar_wait(smem_u32(s_full + (gb & 1)), (uint32_t)((gb >> 1) & 1));
         tc_fence_after();
+        TSTAMP(1);
         float s[32];
         tmem_ld32(lane_addr + COL_S + (uint32_t)((gb & 1) * BKV + part * 32), s);
+        TSTAMP(2);
         if (j == nblk - 1) {
 #pragma unroll
           for (int c = 0; c < 32; ++c) if (j * BKV + part * 32 + c >= T) s[c] = -INFINITY;
@@ -336,6 +352,7 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
         slot[part * BQ + row] = pm;
         asm volatile("bar.sync %0, 128;" ::"r"(1 + qd) : "memory");      // the four warps of this lane quarter
         const float mx = fmaxf(fmaxf(m, slot[row]), fmaxf(fmaxf(slot[BQ + row], slot[2 * BQ + row]), slot[3 * BQ + row]));
+        TSTAMP(3);
         const float alpha = ex2(m - mx);
         float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
 #pragma unroll
@@ -346,9 +363,11 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
         }
         l = l * alpha + ((r0 + r1) + (r2 + r3));
         m = mx;
+        TSTAMP(4);
         if (j > 0) {
           mbar_wait(smem_u32(o_full), (uint32_t)((gb - 1) & 1));
           tc_fence_after();
+          TSTAMP(5);
           float t[16];
           tmem_ld16(lane_addr + COL_O + (uint32_t)(part * 16), t);
 #pragma unroll
@@ -358,18 +377,16 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
         {
           uint32_t ph[16], pl[16];
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            __half h0, l0, h1, l1;
-            split_f16(s[c] * P_SCALE, h0, l0); split_f16(s[c + 1] * P_SCALE, h1, l1);
-            ph[c >> 1] = pack_h2(h0, h1); pl[c >> 1] = pack_h2(l0, l1);
-          }
+          for (int c = 0; c < 32; c += 2) split_f16x2(s[c] * P_SCALE, s[c + 1] * P_SCALE, ph[c >> 1], pl[c >> 1]);
           tmem_st16(lane_addr + COL_PHI + (uint32_t)(part * 16), ph);
           tmem_st16(lane_addr + COL_PLO + (uint32_t)(part * 16), pl);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
+        TSTAMP(6);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(p_full));
+        TSTAMP(7);
       }
       mbar_wait(smem_u32(o_full), (uint32_t)((g + nblk - 1) & 1));
       tc_fence_after();
@@ -394,10 +411,11 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
           uint4* pl = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(o_lo) + off);
 #pragma unroll
           for (int c = 0; c < 16; c += 8) {
-            __half hh[8], ll[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) split_f16(o[c + q] * inv * kActScale, hh[q], ll[q]);
-            ph[c >> 3] = *reinterpret_cast<uint4*>(hh); pl[c >> 3] = *reinterpret_cast<uint4*>(ll);
+            uint4 hh, ll;
+            const float sc = inv * kActScale;
+            split_f16x2(o[c] * sc, o[c + 1] * sc, hh.x, ll.x); split_f16x2(o[c + 2] * sc, o[c + 3] * sc, hh.y, ll.y);
+            split_f16x2(o[c + 4] * sc, o[c + 5] * sc, hh.z, ll.z); split_f16x2(o[c + 6] * sc, o[c + 7] * sc, hh.w, ll.w);
+            ph[c >> 3] = hh; pl[c >> 3] = ll;
           }
         } else {
           float4* ph = reinterpret_cast<float4*>(reinterpret_cast<float*>(o_hi) + off);
@@ -479,6 +497,7 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
 int attention16_vt_pitch(int T) { return (T + 7) & ~7; }     // fp16 rows: multiple of 16 bytes
 
 // qk16_{hi,lo}: fp16 [B*T, 3D] (q | k thirds of 8*x); vt16_{hi,lo}: fp16 [B*D, Tp], pad columns zero.
+static float* g_attn16_dbg = nullptr;      // set by the (non-ABI) debug entry below
 int attention_tc16_launch(const void* qk_hi, const void* qk_lo, const void* vt_hi, const void* vt_lo, int B, int T,
                           int D, int heads, void* o_hi, void* o_lo, bool out_f16, cudaStream_t st) {
   using namespace atc16;
@@ -497,7 +516,7 @@ int attention_tc16_launch(const void* qk_hi, const void* qk_lo, const void* vt_h
   }
   const int total = cdiv(T, BQ) * heads * B;
   attention_tc16_kernel<<<std::min(total, device_sm_count()), THREADS, SMEM_BYTES, st>>>(hqk, lqk, hvt, lvt, B, T, D,
-                                                                                         o_hi, o_lo, out_f16 ? 1 : 0);
+                                                                                         o_hi, o_lo, out_f16 ? 1 : 0, g_attn16_dbg);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }
@@ -519,3 +538,12 @@ int attention_tc16_standalone(const float* qkv_hi, const float* qkv_lo, int B, i
 }
 
 }  // namespace anyloc
+
+// debug entry (not part of the public ABI): clock64 stamps of the 2nd work item of CTA 0 into dbg[16*16]
+extern "C" int anyloc_attention_tc16_debug(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads,
+                                           void* o_hi, void* o_lo, float* dbg, void* stream) {
+  anyloc::g_attn16_dbg = dbg;
+  int rc = anyloc::attention_tc16_standalone(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, true, (cudaStream_t)stream);
+  anyloc::g_attn16_dbg = nullptr;
+  return rc;
+}

@@ -74,9 +74,25 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // kind::f16 tensor path.  Activations use the fixed scale kActScale, weights a per-tensor scale (see vit.py);
 // the GEMM epilogue multiplies the accumulator by alpha = 1/(s_A*s_B) (exact).
 constexpr float kActScale = 8.0f;
+// f32 <-> f16 conversions run on the 16-lane/clk conversion path (measured: they, not the FMAs, bounded the softmax
+// warps of the attention kernel), so the hi part is rounded to 11 significant bits with Veltkamp's splitting on the
+// FMA pipe (t = x*(2^13+1); hi = t - (t - x), round-to-nearest) and only the final packs use cvt -- one
+// cvt.rn.f16x2.f32 per TWO elements in the packed variant.
+__device__ __forceinline__ float veltkamp_hi11(float x) {
+  const float t = __fmul_rn(x, 8193.0f);
+  return __fsub_rn(t, __fsub_rn(t, x));
+}
 __device__ __forceinline__ void split_f16(float xs, __half& hi, __half& lo) {
-  hi = __float2half_rn(xs);
-  lo = __float2half_rn(xs - __half2float(hi));
+  const float h = veltkamp_hi11(xs);
+  hi = __float2half_rn(h);                       // exact (11 significant bits) inside the fp16 normal range
+  lo = __float2half_rn(__fsub_rn(xs, h));
+}
+// two values -> packed (hi, lo) words; `a` lands in the low 16 bits (element k), `b` in the high 16 bits (k+1)
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  const float ha = veltkamp_hi11(a), hb = veltkamp_hi11(b);
+  const float la = __fsub_rn(a, ha), lb = __fsub_rn(b, hb);
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(hb), "f"(ha));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(lb), "f"(la));
 }
 
 int device_sm_count();

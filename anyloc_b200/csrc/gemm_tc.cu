@@ -148,11 +148,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 // ---- epilogue on 32 consecutive columns of one row (row m, columns n..n+31), raw accumulators in v[]
 __device__ __forceinline__ void store_split4(const EpiParams& ep, size_t o, float4 x) {
   if (ep.out_f16) {      // fp16 pair of kActScale*x: 4 halves = 8 bytes per array
-    __half h[4], l[4];
-    split_f16(x.x * kActScale, h[0], l[0]); split_f16(x.y * kActScale, h[1], l[1]);
-    split_f16(x.z * kActScale, h[2], l[2]); split_f16(x.w * kActScale, h[3], l[3]);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out) + o) = *reinterpret_cast<uint2*>(h);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out_lo) + o) = *reinterpret_cast<uint2*>(l);
+    uint2 h, l;
+    split_f16x2(x.x * kActScale, x.y * kActScale, h.x, l.x);
+    split_f16x2(x.z * kActScale, x.w * kActScale, h.y, l.y);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out) + o) = h;
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out_lo) + o) = l;
   } else {
     float4 h, l;
     split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
@@ -223,11 +223,11 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, i
       reinterpret_cast<float4*>(ep.out + o)[j >> 2] =
           make_float4(r.x + g.x * x.x, r.y + g.y * x.y, r.z + g.z * x.z, r.w + g.w * x.w);
     } else if (qkv && ep.qkv_f16) {   // q,k thirds as fp16 pairs (f16 attention input)
-      __half h[4], l[4];
-      split_f16(x.x * kActScale, h[0], l[0]); split_f16(x.y * kActScale, h[1], l[1]);
-      split_f16(x.z * kActScale, h[2], l[2]); split_f16(x.w * kActScale, h[3], l[3]);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out) + o + j) = *reinterpret_cast<uint2*>(h);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out_lo) + o + j) = *reinterpret_cast<uint2*>(l);
+      uint2 h, l;
+      split_f16x2(x.x * kActScale, x.y * kActScale, h.x, l.x);
+      split_f16x2(x.z * kActScale, x.w * kActScale, h.y, l.y);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out) + o + j) = h;
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out_lo) + o + j) = l;
     } else if (qkv) {   // q,k thirds as tf32 pairs (tf32 attention input)
       float4 h, l;
       split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);

@@ -101,11 +101,11 @@ layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ w,
       const float y0 = (v[i].x - mean) * rstd * ww.x + bb.x, y1 = (v[i].y - mean) * rstd * ww.y + bb.y;
       const float y2 = (v[i].z - mean) * rstd * ww.z + bb.z, y3 = (v[i].w - mean) * rstd * ww.w + bb.w;
       if constexpr (F16) {
-        __half h[4], l[4];
-        split_f16(y0 * kActScale, h[0], l[0]); split_f16(y1 * kActScale, h[1], l[1]);
-        split_f16(y2 * kActScale, h[2], l[2]); split_f16(y3 * kActScale, h[3], l[3]);
-        reinterpret_cast<uint2*>(y_hi + (size_t)row * D)[d] = *reinterpret_cast<uint2*>(h);
-        reinterpret_cast<uint2*>(y_lo + (size_t)row * D)[d] = *reinterpret_cast<uint2*>(l);
+        uint2 h, l;
+        split_f16x2(y0 * kActScale, y1 * kActScale, h.x, l.x);
+        split_f16x2(y2 * kActScale, y3 * kActScale, h.y, l.y);
+        reinterpret_cast<uint2*>(y_hi + (size_t)row * D)[d] = h;
+        reinterpret_cast<uint2*>(y_lo + (size_t)row * D)[d] = l;
       } else {
         float4 h, l;
         split_tf32(y0, h.x, l.x); split_tf32(y1, h.y, l.y); split_tf32(y2, h.z, l.z); split_tf32(y3, h.w, l.w);

@@ -227,7 +227,7 @@ vlad_accumulate2_kernel(const float* __restrict__ x, const int32_t* __restrict__
     const float* xb = x + (size_t)b * N * D + col;
     const int32_t* lb = labels + (size_t)b * N;
     const float* ib = inv_norm + (size_t)b * N;
-    constexpr int U = 8;                                  // rows in flight per warp (latency hiding)
+    constexpr int U = 16;                                 // rows in flight per warp (latency hiding)
     for (int n0 = w; n0 < N; n0 += U * warps) {
       float4 v[U]; int lab[U]; float sc[U];
 #pragma unroll
