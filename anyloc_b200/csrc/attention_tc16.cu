@@ -28,10 +28,10 @@ constexpr int VSTAGE = 4 * V_BOX;              // V^T hi(2 boxes), lo(2 boxes): 
 constexpr int XCHG_BYTES = 12 * BQ * 4;        // row max: 2 slots x 4 parts; row sum: 4 parts
 constexpr int SMEM_BYTES = Q_BYTES + STAGES * (KSTAGE + VSTAGE) + 1024 + 256 + XCHG_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t COL_S = 0;        // 2 x 128
-constexpr uint32_t COL_PHI = 256;    // 64 columns = 128 packed fp16
-constexpr uint32_t COL_PLO = 320;    // 64
-constexpr uint32_t COL_O = 384;      // 64
+constexpr uint32_t COL_S = 0;        // 2 x 128: S_j, later overwritten IN PLACE by P_j: each softmax warp replaces its 32
+                                     // S columns by 16 columns of packed P_hi + 16 of packed P_lo, so P is double-buffered
+                                     // for free and the softmax never waits for the previous P.V before publishing P_j
+constexpr uint32_t COL_O = 256;      // 2 x 64: O_j chunks, double-buffered
 constexpr float P_SCALE = 1024.0f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -161,8 +161,8 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
   uint64_t* v_empty = v_full + STAGES;
   uint64_t* s_full = v_empty + STAGES;     // [2]
   uint64_t* p_full = s_full + 2;
-  uint64_t* o_full = p_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* o_full = p_full + 1;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
   float* xchg = reinterpret_cast<float*>(bars) + 64;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -186,7 +186,7 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
     }
     mbar_init(smem_u32(s_full), 1); mbar_init(smem_u32(s_full + 1), 1);
     mbar_init(smem_u32(p_full), SM_WARPS);
-    mbar_init(smem_u32(o_full), 1);
+    mbar_init(smem_u32(o_full), 1); mbar_init(smem_u32(o_full + 1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -292,17 +292,19 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
           tc_fence_after();
           MSTAMP(j, 2);
           const uint32_t vb = smem_u32(sV + st * VSTAGE);
-          const uint32_t d = tmem_base + COL_O;
+          const uint32_t d = tmem_base + COL_O + (uint32_t)((gb & 1) * HD);
+          const uint32_t pbuf = tmem_base + COL_S + (uint32_t)((gb & 1) * BKV);
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k) {                // 8 k-steps of 16 keys
             const uint32_t voff = (uint32_t)((k >> 2) * V_BOX + (k & 3) * 32);
             const uint64_t v_hi = desc_kmajor(vb + voff), v_lo = desc_kmajor(vb + 2 * V_BOX + voff);
-            const uint32_t p_hi = tmem_base + COL_PHI + (uint32_t)(k * 8), p_lo = tmem_base + COL_PLO + (uint32_t)(k * 8);
+            // keys [16k,16k+16) live in the 32-column group of softmax part k/2: hi at +8*(k&1), lo at +16+8*(k&1)
+            const uint32_t p_hi = pbuf + (uint32_t)((k >> 1) * 32 + (k & 1) * 8), p_lo = p_hi + 16;
             umma_ts(d, p_hi, v_hi, idesc_pv, k != 0);
             umma_ts(d, p_lo, v_hi, idesc_pv, 1u);
             umma_ts(d, p_hi, v_lo, idesc_pv, 1u);
           }
-          umma_commit(smem_u32(o_full));
+          umma_commit(smem_u32(o_full + (gb & 1)));
           MSTAMP(j, 3);
           umma_commit(smem_u32(v_empty + st));
         }
@@ -326,6 +328,7 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
 #define TSTAMP(slot) do { if (tdump) dbg[j * 16 + (slot)] = (float)(clock64() - tb); } while (0)
       float m = -INFINITY, l = 0.f;                         // l: this warp's quarter of the row sum
       float o[16];
+      float alpha_prev = 0.f;       // rescale factor of the block whose O chunk is folded in next
 #pragma unroll
       for (int c = 0; c < 16; ++c) o[c] = 0.f;
       for (int j = 0; j < nblk; ++j) {
@@ -364,37 +367,41 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
         l = l * alpha + ((r0 + r1) + (r2 + r3));
         m = mx;
         TSTAMP(4);
-        if (j > 0) {
-          mbar_wait(smem_u32(o_full), (uint32_t)((gb - 1) & 1));
-          tc_fence_after();
-          TSTAMP(5);
-          float t[16];
-          tmem_ld16(lane_addr + COL_O + (uint32_t)(part * 16), t);
-#pragma unroll
-          for (int c = 0; c < 16; ++c) o[c] = (o[c] + t[c]) * alpha;
-        }
-        // publish this warp's 32 key columns of P_j as packed fp16 pairs of 1024*p (16 TMEM columns each)
+        // publish this warp's 32 key columns of P_j (packed fp16 pairs of 1024*p) over its own S columns
         {
           uint32_t ph[16], pl[16];
 #pragma unroll
           for (int c = 0; c < 32; c += 2) split_f16x2(s[c] * P_SCALE, s[c + 1] * P_SCALE, ph[c >> 1], pl[c >> 1]);
-          tmem_st16(lane_addr + COL_PHI + (uint32_t)(part * 16), ph);
-          tmem_st16(lane_addr + COL_PLO + (uint32_t)(part * 16), pl);
+          const uint32_t pcol = lane_addr + COL_S + (uint32_t)((gb & 1) * BKV + part * 32);
+          tmem_st16(pcol, ph);
+          tmem_st16(pcol + 16, pl);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
-        TSTAMP(6);
+        TSTAMP(5);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(p_full));
+        TSTAMP(6);
+        // fold in O_{j-1} (RN) and rescale to the new running maximum
+        if (j > 0) {
+          mbar_wait(smem_u32(o_full + ((gb - 1) & 1)), (uint32_t)(((gb - 1) >> 1) & 1));
+          tc_fence_after();
+          float t[16];
+          tmem_ld16(lane_addr + COL_O + (uint32_t)(((gb - 1) & 1) * HD + part * 16), t);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) o[c] = o[c] * alpha_prev + t[c];
+        }
+        alpha_prev = alpha;
         TSTAMP(7);
       }
-      mbar_wait(smem_u32(o_full), (uint32_t)((g + nblk - 1) & 1));
-      tc_fence_after();
       {
+        const int gl = g + nblk - 1;
+        mbar_wait(smem_u32(o_full + (gl & 1)), (uint32_t)((gl >> 1) & 1));
+        tc_fence_after();
         float t[16];
-        tmem_ld16(lane_addr + COL_O + (uint32_t)(part * 16), t);
+        tmem_ld16(lane_addr + COL_O + (uint32_t)((gl & 1) * HD + part * 16), t);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) o[c] += t[c];
+        for (int c = 0; c < 16; ++c) o[c] = o[c] * alpha_prev + t[c];
       }
       g += nblk;
       float* lsum = xchg + 8 * BQ;
