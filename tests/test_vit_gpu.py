@@ -83,7 +83,8 @@ def test_extractor_errors(u):
                                 weights=dr.build("dinov2_vits14", depth_override=4).state_dict())
 
 
-def test_pipeline_c1_end_to_end(u):
+@pytest.mark.parametrize("precision", ["tf32x3", "f16x3"])
+def test_pipeline_c1_end_to_end(u, precision):
     """BASELINE config 1 (ViT-S/14 layer-9 value, 16x224x224, K=8) end to end on the GPU vs the
     CPU oracle: extractor -> VLAD.fit vocabulary from the oracle -> descriptors -> top-k."""
     import numpy as np
@@ -91,7 +92,8 @@ def test_pipeline_c1_end_to_end(u):
     model = dr.build("dinov2_vits14", seed=0, depth_override=10)
     img = torch.randn(16, 3, 224, 224, generator=torch.Generator().manual_seed(1234))
     feats_ref = ao.extract_features(model, img, 9, "value")
-    ext = u.DinoV2ExtractFeatures("dinov2_vits14", 9, "value", device="cuda", weights=model.state_dict())
+    ext = u.DinoV2ExtractFeatures("dinov2_vits14", 9, "value", device="cuda", weights=model.state_dict(),
+                                  precision=precision)
     feats = ext(img.cuda())
     assert rel_inf(feats.cpu(), feats_ref) < TOL
     np.random.seed(42)

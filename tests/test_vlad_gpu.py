@@ -103,6 +103,23 @@ def test_vlad_full_size_properties(u):
     assert rel_inf(v.generate(x[3][perm]).cpu(), out[3].cpu()) < 1e-5
 
 
+def test_vlad_c5_shape_properties(u):
+    """BASELINE config 5 VLAD shape (N=1369, D=1024, K=128; 8 images here): exactness against the oracle on the
+    first image plus the size-independent properties on all."""
+    B, N, D, K = 8, 1369, 1024, 128
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.nn.functional.normalize(torch.randn(B, N, D, device="cuda", generator=g), dim=-1)
+    centers = 0.6 * x.reshape(-1, D)[torch.randperm(B * N, device="cuda", generator=g)[:K]].contiguous()
+    v = make_vlad(u, K, centers.cpu())
+    out = v.generate_multi(x)
+    assert torch.allclose(out.norm(dim=1), torch.ones(B, device="cuda"), atol=1e-5)
+    lab = v.kmeans.predict(x[0])
+    gap, lab64 = ao.label_margins(x[0].cpu(), centers.cpu())
+    assert torch.equal(lab.cpu()[gap > 1e-5], lab64[gap > 1e-5])
+    ref = ao.vlad_generate(x[0].cpu(), centers.cpu(), labels=lab.cpu(), dtype=torch.float64)
+    assert rel_inf(out[0].cpu(), ref) < TOL
+
+
 def test_vlad_switches_and_errors(u):
     x, centers, _ = ao.clustered_features(64, 64, 4, seed=2)
     for kw in ({"intra_norm": False}, {"norm_descs": False}, {"dist_mode": "euclidean"}):
