@@ -328,6 +328,154 @@ vlad_accumulate_kernel(const float* __restrict__ x, const int32_t* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------ soft assignment (utilities.py:862-887)
+// a[r,k] = softmax_k(temp * cos(x_r, c_k)) with F.cosine_similarity's clamps (each norm clamped at 1e-8).
+// One warp handles ROWS rows per pass over the centres (rows stay L1-resident); scores are staged in shared memory.
+template <int ROWS>
+__global__ void __launch_bounds__(256)
+vlad_soft_assign_kernel(const float* __restrict__ x, const int32_t* __restrict__ n_valid, int N_per_img, int64_t R,
+                        int D, int K, const float* __restrict__ chat /* c / max(|c|, 1e-8) */, float temp,
+                        float* __restrict__ assign /*[R,K]*/, float* __restrict__ inv_norm) {
+  extern __shared__ float sc_smem[];                 // [warps][ROWS][K]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* sc = sc_smem + (size_t)wib * ROWS * K;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int D4 = D >> 2;
+  for (int64_t r0 = warp * ROWS; r0 < R; r0 += nwarps * ROWS) {
+    const float4* xr[ROWS];
+    bool valid[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+      int64_t r = r0 + i;
+      valid[i] = r < R;
+      if (valid[i] && n_valid) valid[i] = (int)(r % N_per_img) < n_valid[(int)(r / N_per_img)];
+      xr[i] = reinterpret_cast<const float4*>(x + (r < R ? r : r0) * (int64_t)D);
+    }
+    float ss[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) ss[i] = 0.f;
+    for (int d = lane; d < D4; d += 32) {
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i) {
+        float4 v = __ldg(xr[i] + d);
+        ss[i] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+    }
+    float rx[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) { ss[i] = sqrtf(warp_sum(ss[i])); rx[i] = temp / fmaxf(ss[i], 1e-8f); }
+    for (int k = 0; k < K; ++k) {
+      const float4* cr = reinterpret_cast<const float4*>(chat + (size_t)k * D);
+      float acc[ROWS];
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i) acc[i] = 0.f;
+      for (int d = lane; d < D4; d += 32) {
+        float4 c = __ldg(cr + d);
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+          float4 v = __ldg(xr[i] + d);
+          acc[i] = fmaf(v.x, c.x, acc[i]); acc[i] = fmaf(v.y, c.y, acc[i]);
+          acc[i] = fmaf(v.z, c.z, acc[i]); acc[i] = fmaf(v.w, c.w, acc[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i) {
+        float s = warp_sum(acc[i]) * rx[i];
+        if (lane == 0) sc[i * K + k] = s;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+      int64_t r = r0 + i;
+      if (r >= R) continue;
+      float m = -INFINITY;
+      for (int k = lane; k < K; k += 32) m = fmaxf(m, sc[i * K + k]);
+      m = warp_max(m);
+      float z = 0.f;
+      for (int k = lane; k < K; k += 32) { float e = expf(sc[i * K + k] - m); sc[i * K + k] = e; z += e; }
+      z = warp_sum(z);
+      const float iz = valid[i] ? 1.0f / z : 0.f;       // padded rows of ragged batches carry no weight
+      for (int k = lane; k < K; k += 32) assign[r * K + k] = sc[i * K + k] * iz;
+      if (lane == 0 && inv_norm) inv_norm[r] = 1.0f / fmaxf(ss[i], 1e-12f);
+    }
+    __syncwarp();
+  }
+}
+
+// V[b,k,:] = sum_q a[q,k] * sum_c (x^_q - c_c) = K * sum_q a[q,k] x^_q - (sum_q a[q,k]) * sum_c c_c
+// (the reference sums cluster k's weight over the residuals to ALL centres, utilities.py:881-884).
+// CTA = (128-column slice, image); thread = column; KC cluster accumulators in registers per pass.
+constexpr int SOFT_KC = 32, SOFT_QT = 64;
+__global__ void __launch_bounds__(ACC_COLS)
+vlad_soft_accumulate_kernel(const float* __restrict__ x, const float* __restrict__ assign,
+                            const float* __restrict__ inv_norm, const float* __restrict__ centers, int N, int D, int K,
+                            int norm_descs, float* __restrict__ vlad, float* __restrict__ partial_ss) {
+  __shared__ __align__(16) float a_tile[SOFT_QT][SOFT_KC];
+  __shared__ float inv_tile[SOFT_QT];
+  __shared__ float red[ACC_COLS / 32][SOFT_KC];
+  const int t = threadIdx.x, slice = blockIdx.x, b = blockIdx.y, nslices = gridDim.x;
+  const int col = slice * ACC_COLS + t;
+  const bool colok = col < D;
+  const float* xb = x + (size_t)b * N * D;
+  const float* ab = assign + (size_t)b * N * K;
+  float csum = 0.f;
+  if (colok) for (int c = 0; c < K; ++c) csum += __ldg(centers + (size_t)c * D + col);
+  for (int k0 = 0; k0 < K; k0 += SOFT_KC) {
+    const int kc = min(SOFT_KC, K - k0);
+    float acc[SOFT_KC];
+#pragma unroll
+    for (int j = 0; j < SOFT_KC; ++j) acc[j] = 0.f;
+    float wsum = 0.f;                         // thread j < kc: sum_q a[q, k0 + j]
+    for (int q0 = 0; q0 < N; q0 += SOFT_QT) {
+      const int qn = min(SOFT_QT, N - q0);
+      __syncthreads();
+      for (int i = t; i < SOFT_QT * SOFT_KC; i += ACC_COLS) {
+        int q = i / SOFT_KC, j = i % SOFT_KC;
+        a_tile[q][j] = (q < qn && j < kc) ? __ldg(ab + (size_t)(q0 + q) * K + k0 + j) : 0.f;
+      }
+      for (int q = t; q < SOFT_QT; q += ACC_COLS)
+        inv_tile[q] = (q < qn) ? (norm_descs ? inv_norm[(size_t)b * N + q0 + q] : 1.0f) : 0.f;
+      __syncthreads();
+      if (t < SOFT_KC) for (int q = 0; q < qn; ++q) wsum += a_tile[q][t];
+      if (colok) {
+#pragma unroll 4
+        for (int q = 0; q < qn; ++q) {
+          const float xv = __ldg(xb + (size_t)(q0 + q) * D + col) * inv_tile[q];
+          const float4* ar = reinterpret_cast<const float4*>(a_tile[q]);
+#pragma unroll
+          for (int j4 = 0; j4 < SOFT_KC / 4; ++j4) {
+            float4 a = ar[j4];
+            acc[4 * j4 + 0] = fmaf(a.x, xv, acc[4 * j4 + 0]); acc[4 * j4 + 1] = fmaf(a.y, xv, acc[4 * j4 + 1]);
+            acc[4 * j4 + 2] = fmaf(a.z, xv, acc[4 * j4 + 2]); acc[4 * j4 + 3] = fmaf(a.w, xv, acc[4 * j4 + 3]);
+          }
+        }
+      }
+    }
+    // epilogue for this cluster chunk: values, then per-(image, cluster, slice) sums of squares
+    __syncthreads();
+    if (t < SOFT_KC) inv_tile[t] = wsum;      // SOFT_KC <= SOFT_QT: reuse as the weight sums
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SOFT_KC; ++j) {
+      float v = 0.f;
+      if (colok && j < kc) {
+        v = (float)K * acc[j] - inv_tile[j] * csum;
+        vlad[((size_t)b * K + k0 + j) * D + col] = v;
+      }
+      float sq = warp_sum(v * v);
+      if ((t & 31) == 0) red[t >> 5][j] = sq;
+    }
+    __syncthreads();
+    if (t < kc) {
+      float tot = 0.f;
+      for (int w = 0; w < ACC_COLS / 32; ++w) tot += red[w][t];
+      partial_ss[((size_t)b * K + k0 + t) * nslices + slice] = tot;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ normalise
 __global__ void __launch_bounds__(256)
 vlad_normalize_kernel(float* __restrict__ vlad, const float* __restrict__ partial_ss, int D, int K,
@@ -542,6 +690,73 @@ extern "C" int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, 
   ANYLOC_CHECK_LAUNCH();
   if (labels_out)
     ANYLOC_CHECK_CUDA(cudaMemcpyAsync(labels_out, labels, R * 4, cudaMemcpyDeviceToDevice, st));
+  return ANYLOC_OK;
+}
+
+// Centres for F.cosine_similarity: c / max(|c|, 1e-8)
+namespace anyloc {
+__global__ void vlad_soft_centre_prep_kernel(const float* __restrict__ c, int K, int D, float* __restrict__ chat) {
+  int k = blockIdx.x;
+  const float* row = c + (size_t)k * D;
+  float ss = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) { float v = row[d]; ss += v * v; }
+  __shared__ float red[32];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  const float den = fmaxf(sqrtf(red[0]), 1e-8f);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) chat[(size_t)k * D + d] = row[d] / den;
+}
+}  // namespace anyloc
+
+extern "C" int anyloc_vlad_generate_soft(const float* feats, const int32_t* n_valid, const float* centers,
+                                         int B, int N, int D, int K, float soft_temp, int norm_descs,
+                                         int intra_norm, float* vlad, float* assign_out, void* ws,
+                                         size_t ws_bytes, void* stream) {
+  ANYLOC_REQUIRE(feats && centers && vlad && ws, "vlad_generate_soft: null pointer");
+  ANYLOC_REQUIRE(B >= 0 && N >= 0 && D > 0 && K > 0, "vlad_generate_soft: bad dims");
+  ANYLOC_REQUIRE(D % 4 == 0, "vlad_generate_soft: D=%d must be a multiple of 4", D);
+  ANYLOC_REQUIRE(K <= 2048, "vlad_generate_soft: K=%d > 2048", K);
+  if (B == 0) return ANYLOC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0) { ANYLOC_CHECK_CUDA(cudaMemsetAsync(vlad, 0, (size_t)B * K * D * 4, st)); return ANYLOC_OK; }
+  Workspace w(ws, ws_bytes);
+  const size_t R = (size_t)B * N;
+  const int nslices = cdiv(D, ACC_COLS);
+  float* inv_norm = w.take<float>(R);
+  float* partial = w.take<float>((size_t)B * K * nslices);
+  float* chat = w.take<float>((size_t)K * D);
+  float* assign = w.take<float>(R * K);
+  if (!inv_norm || !partial || !chat || !assign) {
+    set_error("vlad_generate_soft: workspace too small (%zu bytes given)", ws_bytes);
+    return ANYLOC_ERR_WORKSPACE;
+  }
+  ProfScope ps(PC_VLAD, st, 4.0 * ((double)B * N * D + (double)B * K * D + (double)K * D));
+  vlad_soft_centre_prep_kernel<<<K, 256, 0, st>>>(centers, K, D, chat);
+  ANYLOC_CHECK_LAUNCH();
+  constexpr int ROWS = 2;
+  const size_t smem = (size_t)8 * ROWS * K * 4;
+  ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(vlad_soft_assign_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+  int blocks = (int)std::min<int64_t>(((int64_t)(R + ROWS - 1) / ROWS + 7) / 8, (int64_t)device_sm_count() * 8);
+  vlad_soft_assign_kernel<ROWS><<<std::max(blocks, 1), 256, smem, st>>>(feats, n_valid, N, (int64_t)R, D, K, chat,
+                                                                       soft_temp, assign, inv_norm);
+  ANYLOC_CHECK_LAUNCH();
+  vlad_soft_accumulate_kernel<<<dim3(nslices, B), ACC_COLS, 0, st>>>(feats, assign, inv_norm, centers, N, D, K,
+                                                                    norm_descs, vlad, partial);
+  ANYLOC_CHECK_LAUNCH();
+  int ysplit = std::max(1, std::min(64, (int)(((size_t)K * D + 256 * 16 - 1) / (256 * 16))));
+  vlad_normalize_kernel<<<dim3(B, ysplit), 256, 2 * K * sizeof(float), st>>>(vlad, partial, D, K, nslices,
+                                                                           intra_norm);
+  ANYLOC_CHECK_LAUNCH();
+  if (assign_out)
+    ANYLOC_CHECK_CUDA(cudaMemcpyAsync(assign_out, assign, R * K * 4, cudaMemcpyDeviceToDevice, st));
   return ANYLOC_OK;
 }
 

@@ -100,6 +100,47 @@ def reduce_pca(train_descs: np.ndarray, test_descs: np.ndarray, lower_dim: int, 
     return (train_descs - pca.mean_) @ basis.T, (test_descs - pca.mean_) @ basis.T
 
 
+# ------------------------------------------------------------------ image pre-processing (extension)
+IMAGENET_MEAN = (0.485, 0.456, 0.406)       # dvgl_benchmark/datasets_ws.py:22
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def center_crop_box(h: int, w: int, patch: int = 14) -> Tuple[int, int, int, int]:
+    """(top, left, h_new, w_new) of `T.CenterCrop(((h // 14) * 14, (w // 14) * 14))`
+    (scripts/dino_v2_vlad.py:174-176); torchvision places the window at int(round((h - h_new) / 2.0))."""
+    h_new, w_new = (h // patch) * patch, (w // patch) * patch
+    return int(round((h - h_new) / 2.0)), int(round((w - w_new) / 2.0)), h_new, w_new
+
+
+def preprocess_images(imgs: Union[np.ndarray, torch.Tensor], mean=IMAGENET_MEAN, std=IMAGENET_STD,
+                      patch: int = 14, device: Union[str, torch.device, None] = None) -> torch.Tensor:
+    """uint8 RGB images [B,H,W,3] (or one [H,W,3]) -> the extractor's input [B,3,H',W'] on the GPU: the reference's
+    `base_transform` (ToTensor + Normalize, dvgl_benchmark/datasets_ws.py:20-23) and its centre crop to a multiple
+    of the patch size (scripts/dino_v2_vlad.py:174-176) in one kernel; bit-identical to the torchvision pipeline,
+    a quarter of the host->device bytes of sending normalised fp32 images."""
+    if type(imgs) == np.ndarray:
+        imgs = torch.from_numpy(imgs)
+    if imgs.dtype != torch.uint8:
+        raise TypeError(f"preprocess_images expects uint8 pixels, got {imgs.dtype}")
+    if imgs.dim() == 3:
+        imgs = imgs[None]
+    if imgs.dim() != 4 or imgs.shape[-1] != 3:
+        raise ValueError(f"preprocess_images expects [B,H,W,3], got {tuple(imgs.shape)}")
+    dev = _lib.require_cuda(imgs.device if imgs.is_cuda else (torch.device(device) if device is not None else None))
+    x = imgs.to(dev, non_blocking=True).contiguous()
+    B, H, W, _ = x.shape
+    top, left, hc, wc = center_crop_box(H, W, patch)
+    if hc == 0 or wc == 0:
+        raise ValueError(f"image {H}x{W} is smaller than one {patch}x{patch} patch")
+    out = torch.empty(B, 3, hc, wc, device=dev, dtype=torch.float32)
+    m3 = (C.c_float * 3)(*[float(v) for v in mean])
+    s3 = (C.c_float * 3)(*[float(v) for v in std])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().anyloc_preprocess_u8(_lib.ptr(x), B, H, W, top, left, hc, wc, m3, s3, _lib.ptr(out),
+                                                    _lib.stream_ptr()), "anyloc_preprocess_u8")
+    return out
+
+
 # ------------------------------------------------------------------ extractor
 class _HookHandle:
     def remove(self):
@@ -223,13 +264,14 @@ class _KMeans:
 
 
 class VLAD:
-    """Hard-assignment VLAD with the reference's constructor and methods (utilities.py:624-1008).
+    """Hard- and soft-assignment VLAD with the reference's constructor and methods (utilities.py:624-1008).
 
     `generate` / `generate_multi` take what the reference takes (CPU tensors / numpy arrays /
     ragged lists) and return what it returns (CPU tensors); CUDA tensors are also accepted and
     then stay on the device (the batched fast path).  The on-disk vocabulary cache
     (`c_centers.pt`) is honoured; the reference's per-image residual cache (`*_r.pt`, >=100 MB per
-    image) is neither read nor written.  `vlad_mode="soft"` is not implemented yet."""
+    image) is neither read nor written.  `vlad_mode="soft"` follows the reference's soft branch
+    (:862-887), including its summation over the residuals to all centres."""
 
     def __init__(self, num_clusters: int, desc_dim: Union[int, None] = None, intra_norm: bool = True,
                  norm_descs: bool = True, dist_mode: str = "cosine", vlad_mode: str = "hard",
@@ -323,11 +365,10 @@ class VLAD:
         return self._centers_dev[key]
 
     def _run(self, feats, n_valid, dev, want_labels=False):
-        """feats [B,N,D] device fp32; n_valid [B] int32 device or None -> ([B,K*D], labels|None)."""
+        """feats [B,N,D] device fp32; n_valid [B] int32 device or None -> ([B,K*D], labels|None)
+        (soft mode: the [B,N,K] assignment probabilities take the place of the labels)."""
         assert self.kmeans is not None
         assert self.c_centers is not None
-        if self.vlad_mode != "hard":
-            raise NotImplementedError("anyloc_b200: soft-assignment VLAD is not implemented (hard only)")
         lib = _lib.load()
         B, N, D = feats.shape
         K = self.num_clusters
@@ -336,6 +377,16 @@ class VLAD:
             raise ValueError(f"cluster centres {tuple(centers.shape)} do not match K={K}, D={D}")
         out = torch.empty(B, K * D, device=dev, dtype=torch.float32)
         labels = torch.empty(B, N, device=dev, dtype=torch.int32) if want_labels else None
+        if self.vlad_mode == "soft":        # utilities.py:862-887
+            assign = torch.empty(B, N, K, device=dev, dtype=torch.float32) if want_labels else None
+            with torch.cuda.device(dev):
+                ws = _lib.workspaces.get(dev, lib.anyloc_vlad_workspace_bytes(B, N, D, K), "vlad")
+                rc = lib.anyloc_vlad_generate_soft(_lib.ptr(feats), _lib.ptr(n_valid), _lib.ptr(centers), B, N, D, K,
+                                                   float(self.soft_temp), int(bool(self.norm_descs)),
+                                                   int(bool(self.intra_norm)), _lib.ptr(out), _lib.ptr(assign),
+                                                   _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+            _lib.check(rc, "anyloc_vlad_generate_soft")
+            return out, assign
         with torch.cuda.device(dev):
             ws = _lib.workspaces.get(dev, lib.anyloc_vlad_workspace_bytes(B, N, D, K), "vlad")
             rc = lib.anyloc_vlad_generate(_lib.ptr(feats), _lib.ptr(n_valid), _lib.ptr(centers), B, N, D, K,
@@ -398,6 +449,29 @@ class VLAD:
             return torch.stack(res)
         except (TypeError, RuntimeError):
             return res
+
+
+# ------------------------------------------------------------------ sibling aggregators (extension)
+_POOL = {"average": 0, "avg": 0, "mean": 0, "max": 1, "gem": 2}
+
+
+def pool_descriptors(patch_descs: torch.Tensor, method: str = "gem", gem_p: float = 3.0,
+                     gem_use_abs: bool = False) -> torch.Tensor:
+    """Global descriptors [N, d_dim] from patch features [N, n_p, d_dim] the way the reference's other DINOv2
+    scripts pool them: `get_gem_descriptors` (scripts/dino_v2_gem.py:170-189; `gem_p`, `gem_use_abs`) and the
+    "average" / "max" pooling of scripts/dino_v2_gp.py:130-135.  CPU in -> CPU out, CUDA in -> CUDA out."""
+    if method not in _POOL:
+        raise NotImplementedError(f"ID: {method}")          # scripts/dino_v2_gp.py:134-135
+    assert len(patch_descs.shape) == len(("N", "n_p", "d_dim"))
+    on_dev = patch_descs.is_cuda
+    dev = _lib.require_cuda(patch_descs.device if on_dev else None)
+    x = _as_device_f32(patch_descs, dev)
+    B, N, D = x.shape
+    out = torch.empty(B, D, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().anyloc_pool(_lib.ptr(x), None, B, N, D, _POOL[method], float(gem_p),
+                                           int(bool(gem_use_abs)), _lib.ptr(out), _lib.stream_ptr()), "anyloc_pool")
+    return out if on_dev else out.cpu()
 
 
 # ------------------------------------------------------------------ retrieval

@@ -93,6 +93,14 @@ size_t anyloc_vlad_workspace_bytes(int B, int N, int D, int K);
 int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, const float* centers,
                          int B, int N, int D, int K, int dist_mode, int norm_descs, int intra_norm,
                          float* vlad, int32_t* labels, void* ws, size_t ws_bytes, void* stream);
+/* Soft assignment (vlad_mode="soft", utilities.py:862-887):
+ *   a[q,k] = softmax_k(soft_temp * cos(x_q, c_k))      (F.cosine_similarity :870-875, norms clamped at 1e-8)
+ *   V_k    = sum_q a[q,k] * sum_c (x^_q - c_c)          (the reference weights the residuals to ALL centres by
+ *                                                        cluster k's probability, :881-884)
+ *   then intra / global normalisation as above.  assign [B,N,K] (nullable) receives a; padded rows get 0. */
+int anyloc_vlad_generate_soft(const float* feats, const int32_t* n_valid, const float* centers,
+                              int B, int N, int D, int K, float soft_temp, int norm_descs, int intra_norm,
+                              float* vlad, float* assign, void* ws, size_t ws_bytes, void* stream);
 /* labels only (fpk.KMeans.predict, utilities.py:849; also one Lloyd assignment step of VLAD.fit :786) */
 int anyloc_vlad_assign(const float* feats, const float* centers, int R, int D, int K, int dist_mode,
                        int32_t* labels, void* ws, size_t ws_bytes, void* stream);
@@ -177,6 +185,26 @@ int anyloc_layernorm_split(const float* x, const float* w, const float* b, int M
 int anyloc_attention(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads,
                      void* o_hi, void* o_lo, int out_dtype, int engine, void* stream);
 int anyloc_l2_normalize_rows(const float* x, int64_t rows, int D, int64_t ld_in, float* y, void* stream);
+
+/* ------------------------------------------------------------------ sibling aggregators
+ * The pooling the reference's other DINOv2 scripts apply to the same patch features [B,N,D] -> [B,D]:
+ *   ANYLOC_POOL_AVG  torch.mean(ret, dim=1)        scripts/dino_v2_gp.py:130-131
+ *   ANYLOC_POOL_MAX  torch.max(ret, dim=1)[0]      scripts/dino_v2_gp.py:132-133
+ *   ANYLOC_POOL_GEM  m = mean(x^p) (|x|^p with gem_use_abs); sign(m)|m|^(1/p)   scripts/dino_v2_gem.py:170-189
+ * n_valid [B] nullable (ragged batches). */
+#define ANYLOC_POOL_AVG 0
+#define ANYLOC_POOL_MAX 1
+#define ANYLOC_POOL_GEM 2
+int anyloc_pool(const float* feats, const int32_t* n_valid, int B, int N, int D, int mode, float gem_p,
+                int gem_use_abs, float* out, void* stream);
+
+/* ------------------------------------------------------------------ image pre-processing
+ * Replaces `base_transform` (dvgl_benchmark/datasets_ws.py:20-23: T.ToTensor + T.Normalize) and the centre crop to a
+ * multiple of the patch size (scripts/dino_v2_vlad.py:174-176) in one pass:
+ *   out[b,c,y,x] = ((float)img[b,top+y,left+x,c] / 255 - mean[c]) / std[c]     (bit-identical to torchvision)
+ * img [B,H,W,3] uint8 (device), mean3/std3 HOST arrays of 3 floats, out [B,3,Hc,Wc] fp32 (device). */
+int anyloc_preprocess_u8(const uint8_t* img, int B, int H, int W, int top, int left, int Hc, int Wc,
+                         const float* mean3, const float* std3, float* out, void* stream);
 
 #ifdef __cplusplus
 }

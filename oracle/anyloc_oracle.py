@@ -60,6 +60,19 @@ def extract_features_full_forward(model, img, layer, facet="value", use_cls=Fals
     return res
 
 
+# --------------------------------------------------------------------- pre-processing
+def preprocess(img_u8, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), patch=14):
+    """`base_transform` (dvgl_benchmark/datasets_ws.py:20-23: ToTensor = HWC uint8 -> CHW float / 255, Normalize =
+    (x - mean) / std) then `T.CenterCrop(((h // 14) * 14, (w // 14) * 14))` (scripts/dino_v2_vlad.py:174-176;
+    torchvision puts the window at int(round((h - h_new) / 2.0))).  img_u8 [H,W,3] uint8 -> [3,h_new,w_new]."""
+    x = torch.as_tensor(img_u8).permute(2, 0, 1).to(torch.float32).div(255)
+    x = (x - torch.tensor(mean, dtype=torch.float32)[:, None, None]) / torch.tensor(std, dtype=torch.float32)[:, None, None]
+    h, w = x.shape[1:]
+    hn, wn = (h // patch) * patch, (w // patch) * patch
+    top, left = int(round((h - hn) / 2.0)), int(round((w - wn) / 2.0))
+    return x[:, top:top + hn, left:left + wn]
+
+
 # --------------------------------------------------------------------- VLAD
 def assign_similarity(x, centers, dist_mode="cosine"):
     """fpk.KMeans.max_sim as reached from utilities.py:849 (`predict` on the
@@ -115,6 +128,33 @@ def vlad_generate_faithful(x, centers, intra_norm=True, norm_descs=True, dist_mo
     return F.normalize(out, dim=0)
 
 
+def vlad_soft_assign(x, centers, soft_temp=1.0):
+    """utilities.py:870-875: softmax(soft_temp * F.cosine_similarity(x, c)) on the descriptors as passed."""
+    cos = F.cosine_similarity(x[:, None, :], centers[None, :, :], dim=2)
+    return F.softmax(soft_temp * cos, dim=1)
+
+
+def vlad_generate_soft(x, centers, soft_temp=1.0, intra_norm=True, norm_descs=True, dtype=None):
+    """utilities.py:862-887 soft branch.  For cluster k the reference sums w_k * residuals over BOTH q and c
+    (:881-884), i.e. V_k = sum_q a[q,k] * sum_c (x^_q - c_c); restated with the same [N,K,D] residual tensor
+    and the same flattened summation so that fp32 results are bit-identical."""
+    x = torch.as_tensor(x)
+    centers = torch.as_tensor(centers)
+    if dtype is not None:
+        x, centers = x.to(dtype), centers.to(dtype)
+    K, D = centers.shape
+    xn = F.normalize(x) if norm_descs else x                  # :959-960
+    residuals = xn[:, None, :] - centers[None, :, :]          # :961-962
+    a = vlad_soft_assign(x, centers, soft_temp)               # :870-875
+    out = torch.zeros(K * D, dtype=x.dtype)
+    for k in range(K):                                        # :880
+        cd = (a[:, k][:, None, None] * residuals).reshape(-1, D).sum(dim=0)   # :881-884
+        if intra_norm:
+            cd = F.normalize(cd, dim=0)                       # :885-886
+        out[k * D:(k + 1) * D] = cd
+    return F.normalize(out, dim=0)                            # :889
+
+
 def vlad_generate_multi(xs, centers, **kw):
     """utilities.py:892-926."""
     return torch.stack([vlad_generate(x, centers, **kw) for x in xs])
@@ -127,6 +167,26 @@ def label_margins(x, centers, dist_mode="cosine"):
         return torch.full((s.shape[0],), float("inf"), dtype=torch.float64), torch.zeros(s.shape[0], dtype=torch.long)
     top2 = s.topk(2, dim=1)[0]
     return top2[:, 0] - top2[:, 1], s.max(dim=1)[1]
+
+
+# ---------------------------------------------------------------- sibling aggregators
+def gem_descriptors(patch_descs, gem_p=3, gem_use_abs=False):
+    """scripts/dino_v2_gem.py:170-189 (`get_gem_descriptors`; the script is argparse-driven and cannot be
+    imported, so this restatement is PARITY UNPINNED -- it follows the cited lines)."""
+    if gem_use_abs:
+        return torch.mean(torch.abs(patch_descs) ** gem_p, dim=-2) ** (1 / gem_p)          # :173-175
+    x = torch.mean(patch_descs ** gem_p, dim=-2)                                            # :185
+    g = x.to(torch.complex128 if x.dtype == torch.float64 else torch.complex64) ** (1 / gem_p)   # :186
+    return torch.abs(g) * torch.sign(x)                                                     # :187
+
+
+def pool_descriptors(patch_descs, method):
+    """scripts/dino_v2_gp.py:130-135 (PARITY UNPINNED, same reason)."""
+    if method == "average":
+        return torch.mean(patch_descs, dim=1)
+    if method == "max":
+        return torch.max(patch_descs, dim=1)[0]
+    raise NotImplementedError(f"ID: {method}")
 
 
 # ---------------------------------------------------------------- retrieval

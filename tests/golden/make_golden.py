@@ -82,6 +82,40 @@ def make_vlad():
     print("vlad.npz", len(cases), "cases")
 
 
+def make_vlad_soft():
+    # the soft branch of VLAD.generate (utilities.py:862-887)
+    g = torch.Generator().manual_seed(321)
+    cases = {}
+    specs = [
+        ("soft_t1_n90_d48_k6", 90, 48, 6, "clustered", {"soft_temp": 1.0}),
+        ("soft_t20_n130_d64_k8", 130, 64, 8, "clustered", {"soft_temp": 20.0}),
+        ("soft_t5_nonorm_n70_d40_k5", 70, 40, 5, "random_unnorm", {"soft_temp": 5.0, "norm_descs": False}),
+        ("soft_t3_nointra_n60_d32_k37", 60, 32, 37, "random_unnorm", {"soft_temp": 3.0, "intra_norm": False}),
+        ("soft_t10_zero_n33_d36_k3", 33, 36, 3, "zero", {"soft_temp": 10.0}),
+    ]
+    for name, N, D, K, kind, kw in specs:
+        if kind in ("clustered", "zero"):
+            x, c, _ = ao.clustered_features(N, D, K, seed=len(name))
+            if kind == "zero":
+                x[5] = 0.0                   # cos = 0 to every centre -> uniform weights
+        else:
+            x = torch.randn(N, D, generator=g) * (0.5 + torch.rand(N, 1, generator=g))
+            c = torch.randn(K, D, generator=g) * 0.8
+        v = ref_vlad(K, c, vlad_mode="soft", **kw)
+        cases[name] = dict(x=x.numpy(), centers=c.numpy(), out=v.generate(x).numpy(), kw=np.array(repr(kw)))
+    x, c, _ = ao.clustered_features(3 * 40, 32, 4, seed=11)
+    v = ref_vlad(4, c, vlad_mode="soft", soft_temp=8.0)
+    xb = x.reshape(3, 40, 32)
+    cases["multi_soft_t8_b3_n40_d32_k4"] = dict(x=xb.numpy(), centers=c.numpy(), out=v.generate_multi(xb).numpy(),
+                                                kw=np.array(repr({"soft_temp": 8.0})))
+    flat = {}
+    for n, d in cases.items():
+        for k, a in d.items():
+            flat[f"{n}/{k}"] = a
+    np.savez_compressed(os.path.join(OUT, "vlad_soft.npz"), **flat)
+    print("vlad_soft.npz", len(cases), "cases")
+
+
 def make_fit():
     # VLAD.fit (utilities.py:749-791) through the restated fpk KMeans; numpy RNG seeded as the
     # reference does at import / in main (seed_everything -> np.random.seed(42)).
@@ -138,8 +172,28 @@ def make_extract():
     print("extract.npz")
 
 
+def make_preprocess():
+    # base_transform (dvgl_benchmark/datasets_ws.py:20-23) + the centre crop of scripts/dino_v2_vlad.py:174-176,
+    # run through torchvision itself on PIL images (small sizes: inputs and full outputs are stored).
+    import torchvision.transforms as T
+    from PIL import Image
+    base_transform = T.Compose([T.ToTensor(), T.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    rng = np.random.default_rng(77)
+    out = {}
+    for tag, (h, w) in {"a_45x61": (45, 61), "b_30x28": (30, 28), "c_59x43": (59, 43), "d_14x27": (14, 27)}.items():
+        img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        img[0, 0] = (0, 255, 128)
+        t = base_transform(Image.fromarray(img, "RGB"))
+        hn, wn = (h // 14) * 14, (w // 14) * 14
+        res = T.CenterCrop((hn, wn))(t)
+        out[f"{tag}/img"] = img
+        out[f"{tag}/out"] = res.numpy()
+    np.savez_compressed(os.path.join(OUT, "preprocess.npz"), **out)
+    print("preprocess.npz")
+
+
 if __name__ == "__main__":
-    make_vlad()
-    make_fit()
-    make_topk()
-    make_extract()
+    makers = {"vlad": make_vlad, "vlad_soft": make_vlad_soft, "fit": make_fit, "topk": make_topk,
+              "extract": make_extract, "preprocess": make_preprocess}
+    for name in (sys.argv[1:] or list(makers)):      # `make_golden.py vlad_soft` regenerates one file
+        makers[name]()

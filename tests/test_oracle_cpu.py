@@ -28,6 +28,38 @@ def test_vlad_multi_oracle_matches_golden():
     assert torch.equal(out, torch.from_numpy(c["out"]))
 
 
+@pytest.mark.parametrize("name", sorted(load_cases("vlad_soft.npz")))
+def test_vlad_soft_oracle_matches_golden(name):
+    """Soft branch (utilities.py:862-887): restatement bit-exact with the reference's output; the closed form the
+    CUDA path uses, V_k = K sum_q a_qk x^_q - (sum_q a_qk) sum_c c_c, agrees in fp64."""
+    c = load_cases("vlad_soft.npz")[name]
+    kw = case_kwargs(c)
+    xs, ce = torch.from_numpy(c["x"]), torch.from_numpy(c["centers"])
+    ref = torch.from_numpy(c["out"])
+    if xs.dim() == 2:
+        xs, ref = xs[None], ref[None]
+    for x, r in zip(xs, ref):
+        assert torch.equal(ao.vlad_generate_soft(x, ce, **kw), r)
+        x64, c64 = x.double(), ce.double()
+        K, D = ce.shape
+        a = ao.vlad_soft_assign(x64, c64, kw.get("soft_temp", 1.0))
+        xn = torch.nn.functional.normalize(x64) if kw.get("norm_descs", True) else x64
+        v = K * (a.T @ xn) - a.sum(0)[:, None] * c64.sum(0)[None]
+        if kw.get("intra_norm", True):
+            v = torch.nn.functional.normalize(v, dim=1)
+        v = torch.nn.functional.normalize(v.reshape(-1), dim=0)
+        assert float((v - r.double()).abs().max() / r.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("name", sorted(load_cases("preprocess.npz")))
+def test_preprocess_oracle_matches_golden(name):
+    """ToTensor + Normalize + CenterCrop restated; golden outputs come from torchvision itself."""
+    c = load_cases("preprocess.npz")[name]
+    out = ao.preprocess(torch.from_numpy(c["img"]))
+    assert out.shape == c["out"].shape
+    assert torch.equal(out, torch.from_numpy(c["out"]))
+
+
 def test_vlad_golden_properties():
     c = load_cases("vlad.npz")["emptyclusters_n10_d32_k16"]
     out = torch.from_numpy(c["out"]).reshape(16, 32)

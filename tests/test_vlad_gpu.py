@@ -130,9 +130,37 @@ def test_vlad_switches_and_errors(u):
         v.generate(x)                                   # fit not called (utilities.py:948-949)
     with pytest.raises(ValueError):
         u.VLAD(4).fit(None)                             # utilities.py:778
-    v = make_vlad(u, 4, centers, vlad_mode="soft")
-    with pytest.raises(NotImplementedError):
-        v.generate(x)
+
+
+@pytest.mark.parametrize("name", sorted(load_cases("vlad_soft.npz")))
+def test_vlad_soft_golden(u, name):
+    """vlad_mode="soft" against the reference's own outputs (tests/golden/vlad_soft.npz)."""
+    c = load_cases("vlad_soft.npz")[name]
+    kw = case_kwargs(c)
+    x, centers = torch.from_numpy(c["x"]), torch.from_numpy(c["centers"])
+    v = make_vlad(u, centers.shape[0], centers, vlad_mode="soft", **kw)
+    out = v.generate_multi(x) if x.dim() == 3 else v.generate(x)
+    assert out.device.type == "cpu" and out.shape == c["out"].shape
+    assert rel_inf(out, torch.from_numpy(c["out"])) < TOL
+
+
+@pytest.mark.parametrize("B,N,D,K,temp", [(3, 529, 1536, 32, 1.0), (2, 1369, 1024, 128, 30.0), (2, 77, 384, 200, 4.0)])
+def test_vlad_soft_sizes(u, B, N, D, K, temp):
+    """Pipeline-sized soft VLAD against the fp64 oracle, the assignment probabilities, and a ragged batch."""
+    g = torch.Generator().manual_seed(B * N + K)
+    x = torch.randn(B, N, D, generator=g) * (0.5 + torch.rand(B, N, 1, generator=g))
+    centers = 0.7 * torch.nn.functional.normalize(torch.randn(K, D, generator=g), dim=1)
+    v = make_vlad(u, K, centers, vlad_mode="soft", soft_temp=temp)
+    out, assign = v._run(x.cuda(), None, torch.device("cuda", 0), want_labels=True)
+    for b in range(B):
+        ref = ao.vlad_generate_soft(x[b], centers, soft_temp=temp, dtype=torch.float64)
+        assert rel_inf(out[b].cpu(), ref) < TOL
+        a_ref = ao.vlad_soft_assign(x[b].double(), centers.double(), temp)
+        assert float((assign[b].cpu().double() - a_ref).abs().max()) < 1e-5
+    ragged = [x[0, :N - 7], x[1, :max(1, N // 3)]]
+    outs = v.generate_multi(ragged)
+    for q, o in zip(ragged, outs):
+        assert rel_inf(o, ao.vlad_generate_soft(q, centers, soft_temp=temp, dtype=torch.float64)) < TOL
 
 
 def test_vlad_fit_cache_roundtrip(u, tmp_path):
