@@ -162,6 +162,7 @@ __device__ __forceinline__ void store_split4(const EpiParams& ep, size_t o, floa
 }
 
 __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, int N, const float* v) {
+  if (ep.mode < 0) return;                 // diagnostic: discard (ANYLOC_GEMM_DEBUG_SKIP_EPI)
   const bool vec = (n + 32 <= N) && ((ep.ldo & 3) == 0);
   if (!vec) {
     if (ep.mode == ANYLOC_EPI_SWIGLU_SPLIT) {
@@ -238,6 +239,61 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, i
       store_split4(ep, o + j, x);
     }
   }
+}
+
+// ---- coalescing epilogue: the accumulator layout is lane = row (32 rows per warp), so a direct store touches 32
+// different rows per instruction (32 partly filled sectors).  Here a warp transposes 32 rows x 16 columns through a
+// 2 KB shared-memory tile (64 B per row, 16-byte chunks XOR-swizzled by (row >> 1) & 3: conflict-free both ways) so
+// that every store instruction writes 8 rows x 64 contiguous bytes (fp32) / 8 x 32 B (fp16 pairs): full sectors.
+// Handles the row-major vector modes; returns false (nothing written) for the cases the direct path keeps
+// (SwiGLU pairs, the transposed V third, ragged N / unaligned ldo).  Must be called by all 32 lanes.
+__device__ __forceinline__ bool epi_chunk16_staged(const EpiParams& ep, float4* tile /*[32 rows][4 chunks]*/, int lane,
+                                                   int m_base, int n, int M, int N, const float* v) {
+  if (ep.mode < 0) return true;            // diagnostic: discard (ANYLOC_GEMM_DEBUG_SKIP_EPI)
+  if (n + 16 > N || (ep.ldo & 3) || ep.mode == ANYLOC_EPI_SWIGLU_SPLIT ||
+      (ep.mode == ANYLOC_EPI_QKV_SPLIT && n >= 2 * ep.qkv_D))
+    return false;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) tile[lane * 4 + (c ^ sw)] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+  __syncwarp();
+  const int ch = lane & 3, nn = n + ch * 4;
+  const float al = ep.alpha;
+  const float4 b = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + nn)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ep.mode == ANYLOC_EPI_LS_RESID) g = __ldg(reinterpret_cast<const float4*>(ep.gamma + nn));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2), m = m_base + r;
+    const float4 a = tile[r * 4 + (ch ^ ((r >> 1) & 3))];
+    if (m >= M) continue;
+    float4 x = make_float4(a.x * al + b.x, a.y * al + b.y, a.z * al + b.z, a.w * al + b.w);
+    const size_t o = (size_t)m * ep.ldo + nn;
+    if (ep.mode == ANYLOC_EPI_BIAS) {
+      *reinterpret_cast<float4*>(ep.out + o) = x;
+    } else if (ep.mode == ANYLOC_EPI_LS_RESID) {
+      const float4 rr = *reinterpret_cast<const float4*>(ep.resid + o);
+      *reinterpret_cast<float4*>(ep.out + o) = make_float4(rr.x + g.x * x.x, rr.y + g.y * x.y, rr.z + g.z * x.z, rr.w + g.w * x.w);
+    } else if (ep.mode == ANYLOC_EPI_QKV_SPLIT) {
+      if (ep.qkv_f16) {
+        uint2 h, l;
+        split_f16x2(x.x * kActScale, x.y * kActScale, h.x, l.x);
+        split_f16x2(x.z * kActScale, x.w * kActScale, h.y, l.y);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out) + o) = h;
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out_lo) + o) = l;
+      } else {
+        float4 h, l;
+        split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+        *reinterpret_cast<float4*>(ep.out + o) = h;
+        *reinterpret_cast<float4*>(ep.out_lo + o) = l;
+      }
+    } else {                               // BIAS_SPLIT / GELU_SPLIT
+      if (ep.mode == ANYLOC_EPI_GELU_SPLIT) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+      store_split4(ep, o, x);
+    }
+  }
+  __syncwarp();                            // the tile is rewritten by the next call
+  return true;
 }
 
 // F16 = false: operands are fp32 words read as tf32 (32 elements per 128 B k-block, UMMA K=8, kind::tf32)
@@ -406,7 +462,8 @@ namespace two {
 constexpr int BH_BYTES = 128 * 128;                       // half of the B tile: 128 rows x 128 B
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;    // A_hi, A_lo, Bh_hi, Bh_lo = 64 KB
 constexpr int STAGES = 3;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int EPI_TILE_BYTES = 32 * 64;                    // per epilogue warp: 32 rows x 16 fp32 (coalescing transpose)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_WARPS * EPI_TILE_BYTES;
 constexpr int BN = 256;
 }  // namespace two
 
@@ -449,7 +506,7 @@ template <bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                      const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                     int M, int N, int K, int band_n, EpiParams ep) {
+                     int M, int N, int K, int band_n, int staged_epi, EpiParams ep) {
   using namespace two;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -581,11 +638,20 @@ gemm_tc3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       const int m = m0 + q * 32 + lane;
-      if (m < M) {
+      float4* etile = reinterpret_cast<float4*>(bar_area + 256 + (warp - 4) * EPI_TILE_BYTES);
 #pragma unroll
-        for (int c = 0; c < CPT / 32; ++c) {
-          const int n = n0 + cq * CPT + c * 32;
-          if (n < N) epi_chunk32(ep, m, n, N, sum + c * 32);
+      for (int c = 0; c < CPT / 32; ++c) {
+        const int n = n0 + cq * CPT + c * 32;
+        if (n >= N) continue;                           // warp-uniform
+        const bool s0 = staged_epi && epi_chunk16_staged(ep, etile, lane, m0 + q * 32, n, M, N, sum + c * 32);
+        const bool s1 = staged_epi && epi_chunk16_staged(ep, etile, lane, m0 + q * 32, n + 16, M, N, sum + c * 32 + 16);
+        if (!(s0 && s1) && m < M) {
+          if (!s0 && !s1) epi_chunk32(ep, m, n, N, sum + c * 32);
+          else {                                        // ragged N inside the 32 columns: scalar stores for the rest
+            const int nb = s0 ? n + 16 : n;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (nb + j < N) epi_store1(ep, m, nb + j, sum[c * 32 + (s0 ? 16 : 0) + j]);
+          }
         }
       }
     }
@@ -665,8 +731,11 @@ static int launch_2cta(const void* a_hi, const void* a_lo, int lda, const void* 
   }
   const int tiles = cdiv(M, 256) * cdiv(N, two::BN);
   const int pairs = std::min(tiles, device_sm_count() / 2);
+  static int staged_epi = -1;          // ANYLOC_GEMM_STAGED_EPI=0: direct (lane = row) stores, for A/B measurements
+  if (staged_epi < 0) { const char* e = getenv("ANYLOC_GEMM_STAGED_EPI"); staged_epi = e ? atoi(e) : 1; }
   gemm_tc3_2cta_kernel<F16><<<2 * pairs, THREADS, two::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K,
-                                                                         std::min(band_n, cdiv(N, two::BN)), ep);
+                                                                         std::min(band_n, cdiv(N, two::BN)), staged_epi,
+                                                                         ep);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }
@@ -699,11 +768,22 @@ static int launch_impl(const void* a_hi, const void* a_lo, int lda, const void* 
 }
 
 int gemm_tc_launch(const void* a_hi, const void* a_lo, int lda, const void* b_hi, const void* b_lo, int ldb, int M,
-                   int N, int K, const EpiParams& ep, bool f16, cudaStream_t st) {
+                   int N, int K, const EpiParams& ep_in, bool f16, cudaStream_t st) {
   const bool lo = a_lo != nullptr || b_lo != nullptr;
   static int band_n = -1, two_cta = -1;
   if (band_n < 0) { const char* e = getenv("ANYLOC_GEMM_BAND"); band_n = e ? atoi(e) : 8; if (band_n < 1) band_n = 1 << 20; }
   if (two_cta < 0) { const char* e = getenv("ANYLOC_GEMM_2CTA"); two_cta = e ? atoi(e) : 1; }
+  // diagnostic only (tools/, never set by the product): bit m set -> GEMMs with epilogue mode m discard their result,
+  // which exposes how much of a GEMM's time is its epilogue
+  static int skip_epi = -1;
+  if (skip_epi < 0) { const char* e = getenv("ANYLOC_GEMM_DEBUG_SKIP_EPI"); skip_epi = e ? atoi(e) : 0; }
+  if (skip_epi && ((skip_epi >> ep_in.mode) & 1)) {
+    EpiParams e2 = ep_in; e2.mode = -1;
+    if (two_cta && a_lo && b_lo && M >= 512 && N >= 256)
+      return f16 ? launch_2cta<true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, e2, band_n, st)
+                 : launch_2cta<false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, e2, band_n, st);
+  }
+  const EpiParams& ep = ep_in;
   if (two_cta && a_lo && b_lo && M >= 512 && N >= 256) {
     return f16 ? launch_2cta<true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, band_n, st)
                : launch_2cta<false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, band_n, st);

@@ -155,6 +155,20 @@ def vlad_generate_soft(x, centers, soft_temp=1.0, intra_norm=True, norm_descs=Tr
     return F.normalize(out, dim=0)                            # :889
 
 
+def vlad_generate_soft_closed(x, centers, soft_temp=1.0, intra_norm=True, norm_descs=True, dtype=torch.float64):
+    """The soft branch in closed form, V_k = K sum_q a_qk x^_q - (sum_q a_qk) sum_c c_c: equal to
+    vlad_generate_soft() up to summation order (tests/test_oracle_cpu.py checks that on the golden cases) without
+    the [N,K,D] tensor -- for pipeline-sized checks."""
+    x, centers = torch.as_tensor(x).to(dtype), torch.as_tensor(centers).to(dtype)
+    K, D = centers.shape
+    a = vlad_soft_assign(x, centers, soft_temp)
+    xn = F.normalize(x) if norm_descs else x
+    v = K * (a.T @ xn) - a.sum(0)[:, None] * centers.sum(0)[None]
+    if intra_norm:
+        v = F.normalize(v, dim=1)
+    return F.normalize(v.reshape(-1), dim=0)
+
+
 def vlad_generate_multi(xs, centers, **kw):
     """utilities.py:892-926."""
     return torch.stack([vlad_generate(x, centers, **kw) for x in xs])

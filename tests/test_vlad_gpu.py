@@ -153,14 +153,14 @@ def test_vlad_soft_sizes(u, B, N, D, K, temp):
     v = make_vlad(u, K, centers, vlad_mode="soft", soft_temp=temp)
     out, assign = v._run(x.cuda(), None, torch.device("cuda", 0), want_labels=True)
     for b in range(B):
-        ref = ao.vlad_generate_soft(x[b], centers, soft_temp=temp, dtype=torch.float64)
+        ref = ao.vlad_generate_soft_closed(x[b], centers, soft_temp=temp)
         assert rel_inf(out[b].cpu(), ref) < TOL
         a_ref = ao.vlad_soft_assign(x[b].double(), centers.double(), temp)
         assert float((assign[b].cpu().double() - a_ref).abs().max()) < 1e-5
     ragged = [x[0, :N - 7], x[1, :max(1, N // 3)]]
     outs = v.generate_multi(ragged)
     for q, o in zip(ragged, outs):
-        assert rel_inf(o, ao.vlad_generate_soft(q, centers, soft_temp=temp, dtype=torch.float64)) < TOL
+        assert rel_inf(o, ao.vlad_generate_soft_closed(q, centers, soft_temp=temp)) < TOL
 
 
 def test_vlad_fit_cache_roundtrip(u, tmp_path):
