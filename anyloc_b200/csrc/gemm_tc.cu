@@ -241,58 +241,103 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, i
   }
 }
 
-// ---- coalescing epilogue: the accumulator layout is lane = row (32 rows per warp), so a direct store touches 32
-// different rows per instruction (32 partly filled sectors).  Here a warp transposes 32 rows x 16 columns through a
-// 2 KB shared-memory tile (64 B per row, 16-byte chunks XOR-swizzled by (row >> 1) & 3: conflict-free both ways) so
-// that every store instruction writes 8 rows x 64 contiguous bytes (fp32) / 8 x 32 B (fp16 pairs): full sectors.
-// Handles the row-major vector modes; returns false (nothing written) for the cases the direct path keeps
-// (SwiGLU pairs, the transposed V third, ragged N / unaligned ldo).  Must be called by all 32 lanes.
-__device__ __forceinline__ bool epi_chunk16_staged(const EpiParams& ep, float4* tile /*[32 rows][4 chunks]*/, int lane,
-                                                   int m_base, int n, int M, int N, const float* v) {
-  if (ep.mode < 0) return true;            // diagnostic: discard (ANYLOC_GEMM_DEBUG_SKIP_EPI)
-  if (n + 16 > N || (ep.ldo & 3) || ep.mode == ANYLOC_EPI_SWIGLU_SPLIT ||
-      (ep.mode == ANYLOC_EPI_QKV_SPLIT && n >= 2 * ep.qkv_D))
-    return false;
-  const int sw = (lane >> 1) & 3;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) tile[lane * 4 + (c ^ sw)] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-  __syncwarp();
+// ---- coalescing epilogue (2-CTA kernel).  The accumulator layout is lane = row (32 rows per warp), so a direct
+// store touches 32 different rows per instruction (32 partly filled sectors) and every epilogue load (bias, gamma,
+// residual) queues behind the previous group's stores.  Here:
+//  * the tile's bias / gamma slices (256 columns) are fetched into shared memory at the START of the tile, long before
+//    the epilogue needs them (double buffered by tile parity, one named barrier per tile);
+//  * a warp transposes 16 rows x 16 columns at a time through a 1 KB shared-memory tile (64 B per row, 16-byte chunks
+//    XOR-swizzled by (row >> 1) & 3: conflict-free both ways), so that every store instruction writes 8 rows x 64
+//    contiguous bytes (fp32) / 8 x 32 B (fp16 pairs): full sectors;
+//  * LayerScale+residual in place (resid == out) is a vector reduction `red.global.add.v4.f32` -- one writer per
+//    element, so the result is the same single fp32 addition, without the read round trip.
+// Handles the row-major vector modes; returns false (nothing written) for the cases the direct path keeps (the
+// transposed V third, ragged N / unaligned ldo).  Must be called by all 32 lanes.
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// v[16]: raw accumulators of columns n..n+15 (PRE: final values of OUTPUT columns n..n+15, pair store only);
+// sb / sg: shared-memory bias / gamma of those 16 columns.
+template <bool PRE>
+__device__ __forceinline__ void epi_group16(const EpiParams& ep, const float* sb, const float* sg, float4* tile, int lane,
+                                            int m_base, int n, int M, const float* v) {
   const int ch = lane & 3, nn = n + ch * 4;
   const float al = ep.alpha;
-  const float4 b = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + nn)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ep.mode == ANYLOC_EPI_LS_RESID) g = __ldg(reinterpret_cast<const float4*>(ep.gamma + nn));
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f), g = b;
+  if (!PRE) b = *reinterpret_cast<const float4*>(sb + ch * 4);
+  if (!PRE && ep.mode == ANYLOC_EPI_LS_RESID) g = *reinterpret_cast<const float4*>(sg + ch * 4);
+  const bool in_place = ep.resid == ep.out;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = i * 8 + (lane >> 2), m = m_base + r;
-    const float4 a = tile[r * 4 + (ch ^ ((r >> 1) & 3))];
-    if (m >= M) continue;
-    float4 x = make_float4(a.x * al + b.x, a.y * al + b.y, a.z * al + b.z, a.w * al + b.w);
-    const size_t o = (size_t)m * ep.ldo + nn;
-    if (ep.mode == ANYLOC_EPI_BIAS) {
-      *reinterpret_cast<float4*>(ep.out + o) = x;
-    } else if (ep.mode == ANYLOC_EPI_LS_RESID) {
-      const float4 rr = *reinterpret_cast<const float4*>(ep.resid + o);
-      *reinterpret_cast<float4*>(ep.out + o) = make_float4(rr.x + g.x * x.x, rr.y + g.y * x.y, rr.z + g.z * x.z, rr.w + g.w * x.w);
-    } else if (ep.mode == ANYLOC_EPI_QKV_SPLIT) {
-      if (ep.qkv_f16) {
-        uint2 h, l;
-        split_f16x2(x.x * kActScale, x.y * kActScale, h.x, l.x);
-        split_f16x2(x.z * kActScale, x.w * kActScale, h.y, l.y);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out) + o) = h;
-        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out_lo) + o) = l;
-      } else {
-        float4 h, l;
-        split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
-        *reinterpret_cast<float4*>(ep.out + o) = h;
-        *reinterpret_cast<float4*>(ep.out_lo + o) = l;
-      }
-    } else {                               // BIAS_SPLIT / GELU_SPLIT
-      if (ep.mode == ANYLOC_EPI_GELU_SPLIT) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
-      store_split4(ep, o, x);
+  for (int h = 0; h < 2; ++h) {
+    if ((lane >> 4) == h) {
+      const int row = lane & 15, sw = (row >> 1) & 3;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tile[row * 4 + (c ^ sw)] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
     }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = i * 8 + (lane >> 2), m = m_base + h * 16 + r;
+      const float4 a = tile[r * 4 + (ch ^ ((r >> 1) & 3))];
+      if (m >= M) continue;
+      const size_t o = (size_t)m * ep.ldo + nn;
+      if (PRE) { store_split4(ep, o, a); continue; }
+      float4 x = make_float4(a.x * al + b.x, a.y * al + b.y, a.z * al + b.z, a.w * al + b.w);
+      if (ep.mode == ANYLOC_EPI_BIAS) {
+        *reinterpret_cast<float4*>(ep.out + o) = x;
+      } else if (ep.mode == ANYLOC_EPI_LS_RESID) {
+        if (in_place) {
+          red_add_v4(ep.out + o, make_float4(g.x * x.x, g.y * x.y, g.z * x.z, g.w * x.w));
+        } else {
+          const float4 rr = *reinterpret_cast<const float4*>(ep.resid + o);
+          *reinterpret_cast<float4*>(ep.out + o) = make_float4(rr.x + g.x * x.x, rr.y + g.y * x.y, rr.z + g.z * x.z, rr.w + g.w * x.w);
+        }
+      } else if (ep.mode == ANYLOC_EPI_QKV_SPLIT) {
+        if (ep.qkv_f16) {
+          uint2 hh, ll;
+          split_f16x2(x.x * kActScale, x.y * kActScale, hh.x, ll.x);
+          split_f16x2(x.z * kActScale, x.w * kActScale, hh.y, ll.y);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out) + o) = hh;
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out_lo) + o) = ll;
+        } else {
+          float4 hh, ll;
+          split_tf32(x.x, hh.x, ll.x); split_tf32(x.y, hh.y, ll.y); split_tf32(x.z, hh.z, ll.z); split_tf32(x.w, hh.w, ll.w);
+          *reinterpret_cast<float4*>(ep.out + o) = hh;
+          *reinterpret_cast<float4*>(ep.out_lo + o) = ll;
+        }
+      } else {                               // BIAS_SPLIT / GELU_SPLIT
+        if (ep.mode == ANYLOC_EPI_GELU_SPLIT) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+        store_split4(ep, o, x);
+      }
+    }
+    __syncwarp();                            // the tile is rewritten by the next pass / call
   }
-  __syncwarp();                            // the tile is rewritten by the next call
+}
+
+// 32 accumulator columns n..n+31 of one warp (lane = row m_base + lane); nl = n - (first column of the CTA tile).
+// false = not handled here (caller falls back to the direct path).
+__device__ __forceinline__ bool epi_chunk32_staged(const EpiParams& ep, const float* sbias, const float* sgamma,
+                                                   float4* tile, int lane, int m_base, int n, int nl, int M, int N,
+                                                   const float* v) {
+  if (ep.mode < 0) return true;              // diagnostic: discard (ANYLOC_GEMM_DEBUG_SKIP_EPI)
+  if (n + 32 > N || (ep.ldo & 3) || (ep.mode == ANYLOC_EPI_QKV_SPLIT && n >= 2 * ep.qkv_D)) return false;
+  if (ep.mode == ANYLOC_EPI_SWIGLU_SPLIT) {
+    // (x1_j, x2_j) interleaved -> 16 outputs silu(x1) * x2 at columns n/2.., activated in the lane = row layout
+    // (bias reads are shared-memory broadcasts), then stored through the transposing tile
+    const float al = ep.alpha;
+    float y[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(sbias + nl + j);
+      y[(j >> 1)] = silu(v[j] * al + b.x) * (v[j + 1] * al + b.y);
+      y[(j >> 1) + 1] = silu(v[j + 2] * al + b.z) * (v[j + 3] * al + b.w);
+    }
+    epi_group16<true>(ep, nullptr, nullptr, tile, lane, m_base, n >> 1, M, y);
+    return true;
+  }
+  epi_group16<false>(ep, sbias + nl, sgamma + nl, tile, lane, m_base, n, M, v);
+  epi_group16<false>(ep, sbias + nl + 16, sgamma + nl + 16, tile, lane, m_base, n + 16, M, v + 16);
   return true;
 }
 
@@ -462,8 +507,9 @@ namespace two {
 constexpr int BH_BYTES = 128 * 128;                       // half of the B tile: 128 rows x 128 B
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;    // A_hi, A_lo, Bh_hi, Bh_lo = 64 KB
 constexpr int STAGES = 3;
-constexpr int EPI_TILE_BYTES = 32 * 64;                    // per epilogue warp: 32 rows x 16 fp32 (coalescing transpose)
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_WARPS * EPI_TILE_BYTES;
+constexpr int EPI_TILE_BYTES = 16 * 64;                    // per epilogue warp: 16 rows x 16 fp32 (coalescing transpose)
+constexpr int EPI_VEC_BYTES = 2 * 2 * 256 * 4;              // bias + gamma slices of the tile's 256 columns, double buffered
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_VEC_BYTES + EPI_WARPS * EPI_TILE_BYTES;
 constexpr int BN = 256;
 }  // namespace two
 
@@ -480,7 +526,10 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap*
       ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+  // relaxed: the signal only says "this warp's tcgen05.ld of the buffer has completed" (tcgen05.wait::ld + fence
+  // precede it); a release at cluster scope compiles to MEMBAR.ALL.GPU, which would also wait for the warp's
+  // outstanding epilogue stores of the previous tile -- 18 % of the kernel's stall samples before this change
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 template <bool F16>
 __device__ __forceinline__ void umma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -614,10 +663,34 @@ gemm_tc3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     const int cq = (warp - 4) >> 2;
     constexpr int CPT = BN / 4;
     int acc = 0; uint32_t acc_phase = 0;
+    int titer = 0;
     const uint32_t tempty_leader0 = mapa_rank0(smem_u32(tempty_bar)), tempty_leader1 = mapa_rank0(smem_u32(tempty_bar + 1));
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       int mb, nb; tile_coords(tile, num_m, num_n, band_n, mb, nb);
       const int m0 = mb * 256 + (int)rank * 128, n0 = nb * BN;
+      // bias / gamma slices of this tile -> shared memory now, while the first chunk is still being multiplied
+      float* sbias = reinterpret_cast<float*>(bar_area + 256) + (titer & 1) * 512;
+      float* sgamma = sbias + 256;
+      {
+        const int t = (int)threadIdx.x - 128;             // 0..511
+        if (t < 128) {
+          const bool isg = t >= 64;
+          const float* src = isg ? ep.gamma : ep.bias;
+          const int c = (t & 63) * 4;
+          float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (src) {
+            if (n0 + c + 4 <= N) val = __ldg(reinterpret_cast<const float4*>(src + n0 + c));
+            else {
+              if (n0 + c < N) val.x = __ldg(src + n0 + c);
+              if (n0 + c + 1 < N) val.y = __ldg(src + n0 + c + 1);
+              if (n0 + c + 2 < N) val.z = __ldg(src + n0 + c + 2);
+            }
+          }
+          *reinterpret_cast<float4*>((isg ? sgamma : sbias) + c) = val;
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+      }
+      ++titer;
       float sum[CPT];
 #pragma unroll
       for (int j = 0; j < CPT; ++j) sum[j] = 0.f;
@@ -638,21 +711,14 @@ gemm_tc3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       const int m = m0 + q * 32 + lane;
-      float4* etile = reinterpret_cast<float4*>(bar_area + 256 + (warp - 4) * EPI_TILE_BYTES);
+      float4* etile = reinterpret_cast<float4*>(bar_area + 256 + EPI_VEC_BYTES + (warp - 4) * EPI_TILE_BYTES);
 #pragma unroll
       for (int c = 0; c < CPT / 32; ++c) {
-        const int n = n0 + cq * CPT + c * 32;
+        const int nl = cq * CPT + c * 32, n = n0 + nl;
         if (n >= N) continue;                           // warp-uniform
-        const bool s0 = staged_epi && epi_chunk16_staged(ep, etile, lane, m0 + q * 32, n, M, N, sum + c * 32);
-        const bool s1 = staged_epi && epi_chunk16_staged(ep, etile, lane, m0 + q * 32, n + 16, M, N, sum + c * 32 + 16);
-        if (!(s0 && s1) && m < M) {
-          if (!s0 && !s1) epi_chunk32(ep, m, n, N, sum + c * 32);
-          else {                                        // ragged N inside the 32 columns: scalar stores for the rest
-            const int nb = s0 ? n + 16 : n;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) if (nb + j < N) epi_store1(ep, m, nb + j, sum[c * 32 + (s0 ? 16 : 0) + j]);
-          }
-        }
+        if (staged_epi && epi_chunk32_staged(ep, sbias, sgamma, etile, lane, m0 + q * 32, n, nl, M, N, sum + c * 32))
+          continue;
+        if (m < M) epi_chunk32(ep, m, n, N, sum + c * 32);
       }
     }
   }
