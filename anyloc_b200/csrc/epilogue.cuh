@@ -46,6 +46,17 @@ __device__ __forceinline__ void epi_store_vt(const EpiParams& p, int m, int n, f
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+// Same function on the special-function unit: e = 2^(-x log2 e) (ex2.approx, 2^-22 relative), 1/(1+e) by rcp.approx +
+// one Newton step.  |error| <= ~3e-7 |silu(x)|; 7 instructions instead of ~35 (the SwiGLU epilogue runs it 4 M times
+// per GEMM).  x -> -inf: e = inf, 1/(1+e) = 0 -> -0;  NaN propagates.
+__device__ __forceinline__ float silu_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  const float d = 1.0f + e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  r = (d < 3.0e38f) ? fmaf(r, fmaf(-d, r, 1.0f), r) : r;     // Newton step (skipped when d overflowed: r = 0)
+  return x * r;
+}
 
 // Apply the epilogue to one accumulator element (m, n).  For SWIGLU the caller passes the PAIR
 // (acc0 at column n even, acc1 at column n+1) and the result lands in column n/2.

@@ -161,11 +161,16 @@ __device__ __forceinline__ void store_split4(const EpiParams& ep, size_t o, floa
   }
 }
 
-__device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, int N, const float* v) {
-  if (ep.mode < 0) return;                 // diagnostic: discard (ANYLOC_GEMM_DEBUG_SKIP_EPI)
+// MODE: the epilogue mode as a compile-time constant (the 2-CTA kernel is instantiated per mode so that the code a
+// tile executes stays compact), or -2 = read ep.mode at run time.
+template <int MODE = -2>
+__device__ __forceinline__ void epi_chunk32(const EpiParams& ep_in, int m, int n, int N, const float* v) {
+  const int mode = MODE == -2 ? ep_in.mode : MODE;
+  if (mode < 0) return;                    // diagnostic: discard (ANYLOC_GEMM_DEBUG_SKIP_EPI)
+  const EpiParams& ep = ep_in;
   const bool vec = (n + 32 <= N) && ((ep.ldo & 3) == 0);
   if (!vec) {
-    if (ep.mode == ANYLOC_EPI_SWIGLU_SPLIT) {
+    if (mode == ANYLOC_EPI_SWIGLU_SPLIT) {
 #pragma unroll
       for (int j = 0; j < 32; j += 2) if (n + j + 1 < N) epi_store_pair(ep, m, n + j, v[j], v[j + 1]);
     } else {
@@ -176,7 +181,7 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, i
   }
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const float al = ep.alpha;
-  if (ep.mode == ANYLOC_EPI_QKV_SPLIT && n >= 2 * ep.qkv_D) {
+  if (mode == ANYLOC_EPI_QKV_SPLIT && n >= 2 * ep.qkv_D) {
     // V third: transposed per-head store; lanes of a warp hold consecutive rows -> coalesced along t
     const int c0 = n - 2 * ep.qkv_D, b = m / ep.qkv_T, t = m - b * ep.qkv_T;
     const size_t o0 = ((size_t)b * ep.qkv_D + c0) * ep.qkv_Tp + t;
@@ -195,30 +200,30 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, i
     }
     return;
   }
-  if (ep.mode == ANYLOC_EPI_SWIGLU_SPLIT) {
+  if (mode == ANYLOC_EPI_SWIGLU_SPLIT) {
     const size_t o = (size_t)m * ep.ldo + (n >> 1);
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
       float4 b0 = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n + j)) : zero4;
       float4 b1 = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n + j + 4)) : zero4;
       float4 x;
-      x.x = silu(v[j] * al + b0.x) * (v[j + 1] * al + b0.y);
-      x.y = silu(v[j + 2] * al + b0.z) * (v[j + 3] * al + b0.w);
-      x.z = silu(v[j + 4] * al + b1.x) * (v[j + 5] * al + b1.y);
-      x.w = silu(v[j + 6] * al + b1.z) * (v[j + 7] * al + b1.w);
+      x.x = silu_fast(v[j] * al + b0.x) * (v[j + 1] * al + b0.y);
+      x.y = silu_fast(v[j + 2] * al + b0.z) * (v[j + 3] * al + b0.w);
+      x.z = silu_fast(v[j + 4] * al + b1.x) * (v[j + 5] * al + b1.y);
+      x.w = silu_fast(v[j + 6] * al + b1.z) * (v[j + 7] * al + b1.w);
       store_split4(ep, o + (j >> 1), x);
     }
     return;
   }
   const size_t o = (size_t)m * ep.ldo + n;
-  const bool qkv = ep.mode == ANYLOC_EPI_QKV_SPLIT;
+  const bool qkv = mode == ANYLOC_EPI_QKV_SPLIT;
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     float4 b = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n + j)) : zero4;
     float4 x = make_float4(v[j] * al + b.x, v[j + 1] * al + b.y, v[j + 2] * al + b.z, v[j + 3] * al + b.w);
-    if (ep.mode == ANYLOC_EPI_BIAS) {
+    if (mode == ANYLOC_EPI_BIAS) {
       reinterpret_cast<float4*>(ep.out + o)[j >> 2] = x;
-    } else if (ep.mode == ANYLOC_EPI_LS_RESID) {
+    } else if (mode == ANYLOC_EPI_LS_RESID) {
       float4 r = reinterpret_cast<const float4*>(ep.resid + o)[j >> 2];
       float4 g = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + j));
       reinterpret_cast<float4*>(ep.out + o)[j >> 2] =
@@ -235,7 +240,7 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& ep, int m, int n, i
       reinterpret_cast<float4*>(ep.out + o)[j >> 2] = h;
       reinterpret_cast<float4*>(ep.out_lo + o)[j >> 2] = l;
     } else {            // BIAS_SPLIT / GELU_SPLIT
-      if (ep.mode == ANYLOC_EPI_GELU_SPLIT) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+      if (mode == ANYLOC_EPI_GELU_SPLIT) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
       store_split4(ep, o + j, x);
     }
   }
@@ -259,14 +264,15 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
 
 // v[16]: raw accumulators of columns n..n+15 (PRE: final values of OUTPUT columns n..n+15, pair store only);
 // sb / sg: shared-memory bias / gamma of those 16 columns.
-template <bool PRE>
+template <bool PRE, int MODE>
 __device__ __forceinline__ void epi_group16(const EpiParams& ep, const float* sb, const float* sg, float4* tile, int lane,
                                             int m_base, int n, int M, const float* v) {
+  constexpr int mode = MODE;
   const int ch = lane & 3, nn = n + ch * 4;
   const float al = ep.alpha;
   float4 b = make_float4(0.f, 0.f, 0.f, 0.f), g = b;
   if (!PRE) b = *reinterpret_cast<const float4*>(sb + ch * 4);
-  if (!PRE && ep.mode == ANYLOC_EPI_LS_RESID) g = *reinterpret_cast<const float4*>(sg + ch * 4);
+  if (!PRE && mode == ANYLOC_EPI_LS_RESID) g = *reinterpret_cast<const float4*>(sg + ch * 4);
   const bool in_place = ep.resid == ep.out;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -284,16 +290,16 @@ __device__ __forceinline__ void epi_group16(const EpiParams& ep, const float* sb
       const size_t o = (size_t)m * ep.ldo + nn;
       if (PRE) { store_split4(ep, o, a); continue; }
       float4 x = make_float4(a.x * al + b.x, a.y * al + b.y, a.z * al + b.z, a.w * al + b.w);
-      if (ep.mode == ANYLOC_EPI_BIAS) {
+      if (mode == ANYLOC_EPI_BIAS) {
         *reinterpret_cast<float4*>(ep.out + o) = x;
-      } else if (ep.mode == ANYLOC_EPI_LS_RESID) {
+      } else if (mode == ANYLOC_EPI_LS_RESID) {
         if (in_place) {
           red_add_v4(ep.out + o, make_float4(g.x * x.x, g.y * x.y, g.z * x.z, g.w * x.w));
         } else {
           const float4 rr = *reinterpret_cast<const float4*>(ep.resid + o);
           *reinterpret_cast<float4*>(ep.out + o) = make_float4(rr.x + g.x * x.x, rr.y + g.y * x.y, rr.z + g.z * x.z, rr.w + g.w * x.w);
         }
-      } else if (ep.mode == ANYLOC_EPI_QKV_SPLIT) {
+      } else if (mode == ANYLOC_EPI_QKV_SPLIT) {
         if (ep.qkv_f16) {
           uint2 hh, ll;
           split_f16x2(x.x * kActScale, x.y * kActScale, hh.x, ll.x);
@@ -307,7 +313,7 @@ __device__ __forceinline__ void epi_group16(const EpiParams& ep, const float* sb
           *reinterpret_cast<float4*>(ep.out_lo + o) = ll;
         }
       } else {                               // BIAS_SPLIT / GELU_SPLIT
-        if (ep.mode == ANYLOC_EPI_GELU_SPLIT) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+        if (mode == ANYLOC_EPI_GELU_SPLIT) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
         store_split4(ep, o, x);
       }
     }
@@ -317,12 +323,14 @@ __device__ __forceinline__ void epi_group16(const EpiParams& ep, const float* sb
 
 // 32 accumulator columns n..n+31 of one warp (lane = row m_base + lane); nl = n - (first column of the CTA tile).
 // false = not handled here (caller falls back to the direct path).
+template <int MODE>
 __device__ __forceinline__ bool epi_chunk32_staged(const EpiParams& ep, const float* sbias, const float* sgamma,
                                                    float4* tile, int lane, int m_base, int n, int nl, int M, int N,
                                                    const float* v) {
-  if (ep.mode < 0) return true;              // diagnostic: discard (ANYLOC_GEMM_DEBUG_SKIP_EPI)
-  if (n + 32 > N || (ep.ldo & 3) || (ep.mode == ANYLOC_EPI_QKV_SPLIT && n >= 2 * ep.qkv_D)) return false;
-  if (ep.mode == ANYLOC_EPI_SWIGLU_SPLIT) {
+  constexpr int mode = MODE;
+  if (mode < 0) return true;                 // diagnostic: discard (ANYLOC_GEMM_DEBUG_SKIP_EPI)
+  if (n + 32 > N || (ep.ldo & 3) || (mode == ANYLOC_EPI_QKV_SPLIT && n >= 2 * ep.qkv_D)) return false;
+  if (mode == ANYLOC_EPI_SWIGLU_SPLIT) {
     // (x1_j, x2_j) interleaved -> 16 outputs silu(x1) * x2 at columns n/2.., activated in the lane = row layout
     // (bias reads are shared-memory broadcasts), then stored through the transposing tile
     const float al = ep.alpha;
@@ -330,14 +338,14 @@ __device__ __forceinline__ bool epi_chunk32_staged(const EpiParams& ep, const fl
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 b = *reinterpret_cast<const float4*>(sbias + nl + j);
-      y[(j >> 1)] = silu(v[j] * al + b.x) * (v[j + 1] * al + b.y);
-      y[(j >> 1) + 1] = silu(v[j + 2] * al + b.z) * (v[j + 3] * al + b.w);
+      y[(j >> 1)] = silu_fast(v[j] * al + b.x) * (v[j + 1] * al + b.y);
+      y[(j >> 1) + 1] = silu_fast(v[j + 2] * al + b.z) * (v[j + 3] * al + b.w);
     }
-    epi_group16<true>(ep, nullptr, nullptr, tile, lane, m_base, n >> 1, M, y);
+    epi_group16<true, MODE>(ep, nullptr, nullptr, tile, lane, m_base, n >> 1, M, y);
     return true;
   }
-  epi_group16<false>(ep, sbias + nl, sgamma + nl, tile, lane, m_base, n, M, v);
-  epi_group16<false>(ep, sbias + nl + 16, sgamma + nl + 16, tile, lane, m_base, n + 16, M, v + 16);
+  epi_group16<false, MODE>(ep, sbias + nl, sgamma + nl, tile, lane, m_base, n, M, v);
+  epi_group16<false, MODE>(ep, sbias + nl + 16, sgamma + nl + 16, tile, lane, m_base, n + 16, M, v + 16);
   return true;
 }
 
@@ -551,7 +559,7 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {       // arrives
       ::"r"(bar) : "memory");
 }
 
-template <bool F16>
+template <bool F16, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                      const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -716,9 +724,9 @@ gemm_tc3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
       for (int c = 0; c < CPT / 32; ++c) {
         const int nl = cq * CPT + c * 32, n = n0 + nl;
         if (n >= N) continue;                           // warp-uniform
-        if (staged_epi && epi_chunk32_staged(ep, sbias, sgamma, etile, lane, m0 + q * 32, n, nl, M, N, sum + c * 32))
+        if (staged_epi && epi_chunk32_staged<MODE>(ep, sbias, sgamma, etile, lane, m0 + q * 32, n, nl, M, N, sum + c * 32))
           continue;
-        if (m < M) epi_chunk32(ep, m, n, N, sum + c * 32);
+        if (m < M) epi_chunk32<MODE>(ep, m, n, N, sum + c * 32);
       }
     }
   }
@@ -789,19 +797,34 @@ static int launch_2cta(const void* a_hi, const void* a_lo, int lda, const void* 
   if ((rc = make_map(&ma_lo, a_lo, M, K, lda, 128, F16))) return rc;
   if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, 128, F16))) return rc;
   if ((rc = make_map(&mb_lo, b_lo, N, K, ldb, 128, F16))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_2cta_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           two::SMEM_BYTES));
-    attr_set = true;
-  }
   const int tiles = cdiv(M, 256) * cdiv(N, two::BN);
   const int pairs = std::min(tiles, device_sm_count() / 2);
   static int staged_epi = -1;          // ANYLOC_GEMM_STAGED_EPI=0: direct (lane = row) stores, for A/B measurements
   if (staged_epi < 0) { const char* e = getenv("ANYLOC_GEMM_STAGED_EPI"); staged_epi = e ? atoi(e) : 1; }
-  gemm_tc3_2cta_kernel<F16><<<2 * pairs, THREADS, two::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K,
-                                                                         std::min(band_n, cdiv(N, two::BN)), staged_epi,
-                                                                         ep);
+  const int bn = std::min(band_n, cdiv(N, two::BN));
+  // one instantiation per epilogue mode (compact per-tile code); -1 = the diagnostic "discard" variant
+#define ANYLOC_LAUNCH_2CTA(MODE_)                                                                                   \
+  case MODE_: {                                                                                                     \
+    static bool attr_set = false;                                                                                   \
+    if (!attr_set) {                                                                                                \
+      ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_2cta_kernel<F16, MODE_>,                                      \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, two::SMEM_BYTES));        \
+      attr_set = true;                                                                                              \
+    }                                                                                                               \
+    gemm_tc3_2cta_kernel<F16, MODE_><<<2 * pairs, THREADS, two::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, \
+                                                                                  K, bn, staged_epi, ep);          \
+  } break;
+  switch (ep.mode) {
+    ANYLOC_LAUNCH_2CTA(-1)
+    ANYLOC_LAUNCH_2CTA(ANYLOC_EPI_BIAS)
+    ANYLOC_LAUNCH_2CTA(ANYLOC_EPI_BIAS_SPLIT)
+    ANYLOC_LAUNCH_2CTA(ANYLOC_EPI_GELU_SPLIT)
+    ANYLOC_LAUNCH_2CTA(ANYLOC_EPI_SWIGLU_SPLIT)
+    ANYLOC_LAUNCH_2CTA(ANYLOC_EPI_LS_RESID)
+    ANYLOC_LAUNCH_2CTA(ANYLOC_EPI_QKV_SPLIT)
+    default: set_error("gemm_tc: unknown epilogue mode %d", ep.mode); return ANYLOC_ERR_ARG;
+  }
+#undef ANYLOC_LAUNCH_2CTA
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }
