@@ -12,6 +12,8 @@
 //                 sum_{label=k}(x^ - c_k) in shared memory, deterministic per-slice sums of squares
 //   normalise   : intra + global L2 normalisation, in place on the [B,K*D] output
 // (The v1 FFMA assignment kernel is kept for K > 256 / D > 2048 and as the k-means assignment step.)
+#include <stdlib.h>
+#include <algorithm>
 #include "epilogue.cuh"
 
 namespace anyloc {
@@ -19,7 +21,12 @@ namespace anyloc {
 // ------------------------------------------------------------------ centre prep
 __global__ void vlad_centre_prep_kernel(const float* __restrict__ c, int K, int D, int dist_mode,
                                         float* __restrict__ chat, float* __restrict__ cbias,
-                                        float* __restrict__ chat_tf32, float* __restrict__ cnorm) {
+                                        float* __restrict__ chat_tf32, float* __restrict__ cnorm,
+                                        int32_t* __restrict__ zero_a, int zero_a_n, int32_t* __restrict__ zero_b,
+                                        int zero_b_n) {
+  // the counters of the later launches on this stream are cleared here (saves two memset nodes)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < zero_a_n; i += gridDim.x * blockDim.x) zero_a[i] = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < zero_b_n; i += gridDim.x * blockDim.x) zero_b[i] = 0;
   int k = blockIdx.x;
   const float* row = c + (size_t)k * D;
   float ss = 0.f;
@@ -264,6 +271,154 @@ vlad_accumulate2_kernel(const float* __restrict__ x, const int32_t* __restrict__
     }
     ss = warp_sum(ss);
     if (lane == 0) partial_ss[((size_t)b * K + k) * nslices + slice] = ss;
+  }
+}
+
+// ------------------------------------------------------------------ accumulate v3 (+ fused normalisation)
+// CTA = (128-column slice, image), 16 warps.  The image's rows are counting-sorted by label in shared memory (stable:
+// rows of a cluster stay in row order, so every sum has ONE fixed order -> bitwise reproducible, batch == single image),
+// then each warp takes whole clusters (dynamic grab): 8 independent 512-byte row segments in flight per warp, the
+// cluster sum lives in registers (lane = 4 columns) -- no shared-memory accumulators, no read-modify-write chains.
+// The last CTA of an image to finish (global ticket) applies the intra- and global L2 normalisation to that image's
+// descriptor while it is still in L2, which removes the separate normalisation launch.
+constexpr int ACC3_WARPS = 16;
+static inline size_t acc3_smem_bytes(int N, int K) {
+  return ((size_t)3 * N + (size_t)(K + 1) + (size_t)ACC3_WARPS * K + 2 * (size_t)K) * 4;
+}
+__global__ void __launch_bounds__(ACC3_WARPS * 32, 2)
+vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__ labels,
+                        const float* __restrict__ inv_norm, const float* __restrict__ centers, int N, int D, int K,
+                        int norm_descs, int intra_norm, float* vlad, float* partial_ss /* [B,K,nslices] */,
+                        int32_t* done /* [B], zero on entry */) {
+  extern __shared__ int sm3[];
+  int* order = sm3;                                         // [N] rows sorted by label (stable)
+  int* lab = order + N;                                     // [N]
+  float* inv = reinterpret_cast<float*>(lab + N);           // [N]
+  int* start = reinterpret_cast<int*>(inv + N);             // [K+1]
+  int* cntw = start + K + 1;                                // [ACC3_WARPS][K]
+  float* kss = reinterpret_cast<float*>(cntw + ACC3_WARPS * K);   // [K]
+  float* ksq = kss + K;                                     // [K]
+  __shared__ int next_k, s_last;
+  __shared__ float s_gnorm;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int b = blockIdx.y, slice = blockIdx.x, nslices = gridDim.x;
+  const int col = slice * 128 + lane * 4;
+  const bool colok = col < D;                               // D % 4 == 0
+  for (int n = t; n < N; n += blockDim.x) {
+    lab[n] = labels[(size_t)b * N + n];
+    inv[n] = norm_descs ? inv_norm[(size_t)b * N + n] : 1.0f;
+  }
+  for (int i = t; i < ACC3_WARPS * K; i += blockDim.x) cntw[i] = 0;
+  if (t == 0) next_k = 0;
+  __syncthreads();
+  // per-warp histograms over contiguous row chunks
+  const int chunk = (((N + ACC3_WARPS - 1) / ACC3_WARPS) + 31) & ~31;
+  const int r0 = min(N, w * chunk), r1 = min(N, r0 + chunk);
+  for (int n = r0 + lane; n < r1; n += 32) { const int l = lab[n]; if (l >= 0) atomicAdd(&cntw[w * K + l], 1); }
+  __syncthreads();
+  for (int k = t; k < K; k += blockDim.x) {                 // exclusive prefix over the warps, cluster totals
+    int tot = 0;
+    for (int ww = 0; ww < ACC3_WARPS; ++ww) { const int c = cntw[ww * K + k]; cntw[ww * K + k] = tot; tot += c; }
+    start[k] = tot;
+  }
+  __syncthreads();
+  if (w == 0) {                                             // exclusive scan of the totals -> cluster offsets
+    int running = 0;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+      const int k = k0 + lane;
+      const int c = k < K ? start[k] : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+      if (k < K) start[k] = running + incl - c;
+      running += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) start[K] = running;
+  }
+  __syncthreads();
+  for (int n0 = r0; n0 < r1; n0 += 32) {                    // stable placement
+    const int n = n0 + lane;
+    const int l = n < r1 ? lab[n] : -1;
+    const bool active = l >= 0;
+    const unsigned am = __ballot_sync(0xffffffffu, active);
+    unsigned peers = 0; int rank = 0;
+    if (active) {
+      peers = __match_any_sync(am, l);
+      rank = __popc(peers & ((1u << lane) - 1u));
+      order[start[l] + cntw[w * K + l] + rank] = n;
+    }
+    __syncwarp();
+    if (active && rank == 0) cntw[w * K + l] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  // clusters -> registers
+  const float* xb = x + (size_t)b * N * D + col;
+  for (;;) {
+    int k = 0;
+    if (lane == 0) k = atomicAdd(&next_k, 1);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    if (k >= K) break;
+    const int s = start[k], e = start[k + 1];
+    const float4 c = colok ? __ldg(reinterpret_cast<const float4*>(centers + (size_t)k * D + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (colok) {
+      constexpr int U = 8;
+      for (int i = s; i < e; i += U) {
+        float4 v[U]; float sc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int n = order[min(i + u, e - 1)];
+          sc[u] = inv[n];
+          v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)n * D));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (i + u < e) {
+            a.x += v[u].x * sc[u] - c.x; a.y += v[u].y * sc[u] - c.y; a.z += v[u].z * sc[u] - c.z; a.w += v[u].w * sc[u] - c.w;
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(vlad + ((size_t)b * K + k) * D + col) = a;
+    }
+    const float ss = warp_sum(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w);
+    if (lane == 0) kss[k] = ss;
+  }
+  __syncthreads();
+  for (int k = t; k < K; k += blockDim.x) partial_ss[((size_t)b * K + k) * nslices + slice] = kss[k];
+  __threadfence();
+  __syncthreads();
+  if (t == 0) s_last = (atomicAdd(&done[b], 1) == nslices - 1);
+  __syncthreads();
+  if (!s_last) return;
+  // ---- last CTA of this image: intra- and global normalisation (same arithmetic as vlad_normalize_kernel)
+  __threadfence();
+  for (int k = t; k < K; k += blockDim.x) {
+    float ss = 0.f;
+    for (int s = 0; s < nslices; ++s) ss += __ldcg(partial_ss + ((size_t)b * K + k) * nslices + s);
+    const float nk = sqrtf(ss);
+    const float sc = intra_norm ? 1.0f / fmaxf(nk, 1e-12f) : 1.0f;
+    kss[k] = sc;
+    const float nb = nk * sc;
+    ksq[k] = nb * nb;
+  }
+  __syncthreads();
+  if (t == 0) {
+    float tot = 0.f;
+    for (int k = 0; k < K; ++k) tot += ksq[k];
+    s_gnorm = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+    done[b] = 0;
+  }
+  __syncthreads();
+  const float g = s_gnorm;
+  float4* vb = reinterpret_cast<float4*>(vlad + (size_t)b * K * D);
+  const int D4 = D >> 2, total4 = K * D4;
+  for (int i = t; i < total4; i += blockDim.x) {
+    const float sc = kss[i / D4];
+    float4 v = __ldcg(vb + i);
+    // two separate multiplications like F.normalize(intra) then F.normalize(global)
+    v.x = (v.x * sc) * g; v.y = (v.y * sc) * g; v.z = (v.z * sc) * g; v.w = (v.w * sc) * g;
+    vb[i] = v;
   }
 }
 
@@ -571,26 +726,52 @@ int gemm_tc_launch(const void*, const void*, int, const void*, const void*, int,
                    cudaStream_t);
 bool gemm_tc_supported(const void*, const void*, int, const void*, const void*, int, int, int, int, const EpiParams&,
                        bool);
+// v3 assignment (vlad_tc.cu)
+bool vlad_assign_tc_supported(const float* feats, const float* chat_tf32, int64_t R, int D, int K);
+size_t vlad_assign_tc_ws_bytes(int64_t R);
+int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_img, int64_t R, int D, int K,
+                          const float* chat, const float* chat_tf32, const float* cbias, const float* cnorm,
+                          int32_t* labels, float* inv_norm, int32_t* amb_count, int32_t* amb_rows, uint32_t* amb_mask,
+                          cudaStream_t st);
 }  // namespace anyloc
+
+// ANYLOC_VLAD=2 selects the v2 pipeline (coarse GEMM + full rescoring pass + shared-memory accumulate + normalise
+// launch) for A/B measurements; default 3 = streaming tensor-core assignment + sorted register accumulate with the
+// normalisation fused into it.
+static int vlad_version() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ANYLOC_VLAD"); v = e ? atoi(e) : 3; }
+  return v;
+}
 
 extern "C" size_t anyloc_vlad_workspace_bytes(int B, int N, int D, int K) {
   size_t R = (size_t)B * N;
   int nslices = cdiv(D, ACC_COLS);
   return 2 * align_up((size_t)K * D * 4, 256) + 2 * align_up((size_t)K * 4, 256) + align_up(R * 4, 256) * 2 +
          align_up(R * (size_t)K * 4, 256) + align_up((size_t)B * K * nslices * 4, 256) +
-         align_up(((size_t)K * D + K) * 4, 256) + 4096;
+         align_up(((size_t)K * D + K) * 4, 256) + vlad_assign_tc_ws_bytes((int64_t)R) + align_up((size_t)B * 4, 256) +
+         4096;
 }
 
 namespace {
-struct AssignBufs { float *chat, *chat_tf32, *cbias, *cnorm, *coarse; };
+struct AssignBufs {
+  float *chat, *chat_tf32, *cbias, *cnorm, *coarse;
+  int32_t *amb_count = nullptr, *amb_rows = nullptr; uint32_t* amb_mask = nullptr;   // v3 work list (optional)
+  int32_t* done = nullptr; int n_done = 0;                                           // accumulate3 tickets (optional)
+};
 
 // labels (+ 1/|x|) for R rows: tensor-core coarse scores + exact rescoring when the shape allows it, else the
 // FFMA kernel
 int launch_assign(const float* feats, const int32_t* n_valid, int N_per_img, int64_t R, int D, int K,
                   const float* centers, int dist_mode, const AssignBufs& ab, int32_t* labels, float* inv_norm,
                   cudaStream_t st) {
-  vlad_centre_prep_kernel<<<K, 256, 0, st>>>(centers, K, D, dist_mode, ab.chat, ab.cbias, ab.chat_tf32, ab.cnorm);
+  vlad_centre_prep_kernel<<<K, 256, 0, st>>>(centers, K, D, dist_mode, ab.chat, ab.cbias, ab.chat_tf32, ab.cnorm,
+                                             ab.amb_count, ab.amb_count ? 1 : 0, ab.done, ab.done ? ab.n_done : 0);
   ANYLOC_CHECK_LAUNCH();
+  if (vlad_version() >= 3 && ab.amb_count && ab.amb_rows && ab.amb_mask &&
+      vlad_assign_tc_supported(feats, ab.chat_tf32, R, D, K))
+    return vlad_assign_tc_launch(feats, n_valid, N_per_img, R, D, K, ab.chat, ab.chat_tf32, ab.cbias, ab.cnorm, labels,
+                                 inv_norm, ab.amb_count, ab.amb_rows, ab.amb_mask, st);
   EpiParams ep{ANYLOC_EPI_BIAS, ab.cbias, nullptr, nullptr, ab.coarse, nullptr, K};
   const bool fast = ab.coarse != nullptr && D <= 2048 && R >= 256 && R < (1ll << 31) &&
                     gemm_tc_supported(feats, nullptr, D, ab.chat_tf32, nullptr, D, (int)R, K, D, ep, false);
@@ -626,6 +807,9 @@ bool take_assign_bufs(Workspace& w, int64_t R, int D, int K, AssignBufs* ab) {
   ab->cbias = w.take<float>(K);
   ab->cnorm = w.take<float>(K);
   ab->coarse = w.take<float>((size_t)R * K);        // may be null when the caller's workspace is the small one
+  ab->amb_count = w.take<int32_t>(64);
+  ab->amb_rows = w.take<int32_t>((size_t)R);
+  ab->amb_mask = w.take<uint32_t>((size_t)R * 4);
   return ab->chat && ab->chat_tf32 && ab->cbias && ab->cnorm;
 }
 }  // namespace
@@ -665,11 +849,27 @@ extern "C" int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, 
     set_error("vlad_generate: workspace too small (%zu bytes given)", ws_bytes);
     return ANYLOC_ERR_WORKSPACE;
   }
+  const size_t smem3 = acc3_smem_bytes(N, K);
+  const bool acc3 = vlad_version() >= 3 && smem3 <= 160 * 1024;
+  if (acc3) { ab.done = w.take<int32_t>((size_t)B); ab.n_done = B; }
   ProfScope ps(PC_VLAD, st, 4.0 * ((double)B * N * D + (double)B * K * D + (double)K * D));
   int rc = launch_assign(feats, n_valid, N, (int64_t)R, D, K, centers, dist_mode, ab, labels, inv_norm, st);
   if (rc) return rc;
-  // accumulate: as many row-splitting warps as shared memory allows ((1 + warps) * K * 128 floats), at most 8
-  // 4 row-splitting warps when two CTAs then fit per SM ((1 + warps) * K * 128 floats each), else what fits in one
+  if (acc3 && ab.done) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(vlad_accumulate3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr_set = true;
+    }
+    vlad_accumulate3_kernel<<<dim3(nslices, B), ACC3_WARPS * 32, smem3, st>>>(feats, labels, inv_norm, centers, N, D, K,
+                                                                             norm_descs, intra_norm, vlad, partial, ab.done);
+    ANYLOC_CHECK_LAUNCH();
+    if (labels_out)
+      ANYLOC_CHECK_CUDA(cudaMemcpyAsync(labels_out, labels, R * 4, cudaMemcpyDeviceToDevice, st));
+    return ANYLOC_OK;
+  }
+  // v2: accumulate with as many row-splitting warps as shared memory allows ((1 + warps) * K * 128 floats), at most
+  // 4 row-splitting warps when two CTAs then fit per SM, else what fits in one
   int warps = (int)std::min<size_t>(4, (200 * 1024) / ((size_t)K * 128 * 4) - 1);
   if (warps >= 1) {
     size_t smem = (size_t)(1 + warps) * K * 128 * 4;

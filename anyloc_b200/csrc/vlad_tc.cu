@@ -1,0 +1,335 @@
+// Hard-assignment VLAD, v3 assignment stage (reference: fpk.KMeans.predict called at
+// /root/reference/utilities.py:849; row norms of F.normalize at :959-960).
+//
+// vlad_assign_tc_kernel -- ONE streaming pass over the features that yields, per row,
+//   * 1/max(|x|, 1e-12)                                    (exact fp32, from the staged shared-memory tiles)
+//   * the label, when the coarse tensor-core scores decide it rigorously, else an entry in the "ambiguous" work list
+// Persistent CTA per SM, tile = 128 rows x all of D, streamed as 128-byte k-blocks through a deep TMA ring
+// (10-11 stages at K=32: ~170 KB of features in flight per SM, which is what a latency-bound HBM stream needs):
+//   warp 0    TMA producer: X box [128 rows x 32 floats] + centre box [K rows x 32 floats] (L2-resident) per stage
+//   warp 1    MMA issuer: tcgen05.mma kind::tf32 M128 x N=K x K8 straight from the raw fp32 words (the tensor core
+//             truncates to tf32), coarse scores S~ accumulate over all of D in TMEM (2 x 128 columns, double buffered)
+//   warp 2    TMEM allocator
+//   warps 4-7 thread = row: sum of squares of every staged k-block (128B-swizzled shared-memory reads, conflict free),
+//             then the tile epilogue: S~ from TMEM, candidate set {k : S~_k >= max - 2 eps} with the rigorous bound
+//             eps = 2^-9 |x| max|c^| (truncated x, rounded c^).  One candidate -> that IS the exact-fp32 argmax.
+//             Several -> (row, candidate mask) goes to the work list.
+// vlad_rescore_amb_kernel -- warp per work-list row: exact fp32 dot products for the candidates only (same arithmetic
+// as the v2 rescoring kernel), first-max argmax -> lowest index wins exact ties, all-zero rows get label 0.
+#include <cuda.h>
+#include <algorithm>
+#include "tc_common.cuh"
+
+namespace anyloc {
+namespace vtc {
+using namespace tc;
+
+constexpr int BM = 128;
+constexpr int A_BYTES = BM * 128;          // 16 KB: 128 rows x 128 B
+constexpr int THREADS = 256;
+constexpr int TMEM_COLS = 256;             // 2 accumulators x 128 columns
+constexpr int MAX_STAGES = 12;
+constexpr int MAX_K = 128;
+constexpr int BAR_BYTES = 256;             // (2*MAX_STAGES + 4) mbarriers + the TMEM slot
+constexpr int VEC_BYTES = 2 * MAX_K * 4;   // cbias + cnorm
+
+struct AssignParams {
+  const int32_t* n_valid; int n_per_img; int R; int D; int K;
+  const float* cbias; const float* cnorm;
+  int32_t* labels; float* inv_norm;
+  int32_t* amb_count; int32_t* amb_rows; uint32_t* amb_mask;
+  int stages; int stage_bytes; int n_mma;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_c,
+                      const AssignParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* bar_area = smem + p.stages * p.stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_area);          // [MAX_STAGES]
+  uint64_t* empty_bar = full_bar + MAX_STAGES;                          // [MAX_STAGES]
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;                         // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_cbias = reinterpret_cast<float*>(bar_area + BAR_BYTES);      // [MAX_K]
+  float* s_cnorm = s_cbias + MAX_K;                                     // [MAX_K]
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = (p.R + BM - 1) / BM;
+  const int num_k = (p.D + 31) / 32;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_c) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 5); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int k = threadIdx.x; k < MAX_K; k += THREADS) {
+    s_cbias[k] = k < p.K ? p.cbias[k] : 0.f;
+    s_cnorm[k] = k < p.K ? p.cnorm[k] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------ TMA producer
+      const uint32_t tx_bytes = (uint32_t)(A_BYTES + p.n_mma * 128);
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = tile * BM;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+          const uint32_t fb = smem_u32(full_bar + stage);
+          mbar_expect_tx(fb, tx_bytes);
+          const uint32_t sbase = smem_u32(smem + stage * p.stage_bytes);
+          tma_load_2d(sbase, &tm_x, fb, kb * 32, m0);
+          tma_load_2d(sbase + A_BYTES, &tm_c, fb, kb * 32, 0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------ MMA issuer (tf32 in, fp32 accumulate, M128 x n_mma x K8)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);      // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(smem_u32(full_bar + stage), phase);
+          tc_fence_after();
+          const uint32_t sbase = smem_u32(smem + stage * p.stage_bytes);
+          const uint64_t a = make_desc(sbase), b = make_desc(sbase + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+            umma<false>(d_tmem, a + adv, b + adv, idesc, (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(smem_u32(empty_bar + stage));
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(tfull_bar + acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------- row norms from the staged tiles + tile epilogue; thread = row
+    const int q = warp & 3;                          // TMEM lane quarter == row quarter of the tile
+    const int rt = q * 32 + lane;
+    const int sw = rt & 7;
+    float cmax = 0.f;
+    for (int k = 0; k < p.K; ++k) cmax = fmaxf(cmax, s_cnorm[k]);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      float ss = 0.f;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(smem_u32(full_bar + stage), phase);
+        const uint8_t* rowp = smem + stage * p.stage_bytes + rt * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ sw) << 4));
+          ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(empty_bar + stage));
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      const float xn = sqrtf(ss);
+      mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
+      float smax = -INFINITY;
+#pragma unroll
+      for (int cc = 0; cc < MAX_K / 16; ++cc) {
+        if (cc * 16 < p.n_mma) {
+          float v[16];
+          tmem_ld16(trow + (uint32_t)(cc * 16), v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int k = cc * 16 + j;
+            if (k < p.K) smax = fmaxf(smax, v[j] + s_cbias[k]);
+          }
+        }
+      }
+      // |S~_k - S_k| <= (2^-10 + 2^-11) sum|x_i c_i| < 2^-9 |x||c^_k|  (truncated x, round-to-nearest c^)
+      const float thresh = smax - 2.0f * (0.001953125f * xn * cmax) - 1e-30f;
+      uint32_t mask[MAX_K / 32];
+#pragma unroll
+      for (int i = 0; i < MAX_K / 32; ++i) mask[i] = 0u;
+      int cnt = 0, first = 0;
+#pragma unroll
+      for (int cc = 0; cc < MAX_K / 16; ++cc) {
+        if (cc * 16 < p.n_mma) {
+          float v[16];
+          tmem_ld16(trow + (uint32_t)(cc * 16), v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int k = cc * 16 + j;
+            if (k < p.K && v[j] + s_cbias[k] >= thresh) {
+              if (cnt == 0) first = k;
+              ++cnt;
+              mask[cc >> 1] |= 1u << (k & 31);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+
+      const int64_t m = (int64_t)tile * BM + rt;
+      if (m < p.R) {
+        bool valid = true;
+        if (p.n_valid) { const int b = (int)(m / p.n_per_img), n = (int)(m - (int64_t)b * p.n_per_img); valid = n < p.n_valid[b]; }
+        if (p.inv_norm) p.inv_norm[m] = 1.0f / fmaxf(xn, 1e-12f);
+        if (!valid) p.labels[m] = -1;
+        else if (cnt <= 1) p.labels[m] = first;          // cnt == 0 only with NaN scores: label 0 like the exact path
+        else {
+          const int idx = atomicAdd(p.amb_count, 1);
+          p.amb_rows[idx] = (int32_t)m;
+#pragma unroll
+          for (int i = 0; i < MAX_K / 32; ++i) p.amb_mask[(size_t)idx * (MAX_K / 32) + i] = mask[i];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// Warp per ambiguous row; the row (D <= 128 * MAXV) lives in registers.
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+vlad_rescore_amb_kernel(const float* __restrict__ x, int D, const float* __restrict__ chat,
+                        const float* __restrict__ cbias, const int32_t* amb_count, const int32_t* amb_rows,
+                        const uint32_t* amb_mask, int32_t* __restrict__ labels) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nw = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+  const int n = __ldcg(amb_count);
+  const int D4 = D >> 2;
+  for (int i = gw; i < n; i += nw) {
+    const int64_t row = __ldcg(amb_rows + i);
+    const float4* xr = reinterpret_cast<const float4*>(x + row * (int64_t)D);
+    float4 v[MAXV];
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      const int d = lane + j * 32;
+      v[j] = d < D4 ? __ldg(xr + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float best = -INFINITY; int bestk = 0;
+    for (int w = 0; w < MAX_K / 32; ++w) {
+      uint32_t mask = __ldcg(amb_mask + (size_t)i * (MAX_K / 32) + w);
+      const int k0 = w * 32;
+      while (mask) {
+        int kk[4]; int nc = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (mask) { kk[q] = k0 + __ffs(mask) - 1; mask &= mask - 1; ++nc; } else kk[q] = kk[0];
+        }
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+          const int d = lane + j * 32;
+          if (d < D4) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 c = __ldg(reinterpret_cast<const float4*>(chat + (size_t)kk[q] * D) + d);
+              acc[q] = fmaf(v[j].x, c.x, acc[q]); acc[q] = fmaf(v[j].y, c.y, acc[q]);
+              acc[q] = fmaf(v[j].z, c.z, acc[q]); acc[q] = fmaf(v[j].w, c.w, acc[q]);
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float sc = warp_sum(acc[q]) + cbias[kk[q]];
+          if (q < nc && sc > best) { best = sc; bestk = kk[q]; }   // ascending k, strict >: lowest index wins exact ties
+        }
+      }
+    }
+    if (lane == 0) labels[row] = bestk;
+  }
+}
+
+}  // namespace vtc
+
+// Shapes the tensor-core assignment handles; everything else stays on the v2 / FFMA kernels.
+bool vlad_assign_tc_supported(const float* feats, const float* chat_tf32, int64_t R, int D, int K) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return R >= 256 && R < (1ll << 31) - 256 && D >= 32 && D <= 2048 && (D % 4) == 0 && K >= 1 && K <= vtc::MAX_K &&
+         al16(feats) && al16(chat_tf32);
+}
+
+size_t vlad_assign_tc_ws_bytes(int64_t R) {
+  return align_up((size_t)R * 4, 256) + align_up((size_t)R * (vtc::MAX_K / 32) * 4, 256) + 256;
+}
+
+// feats [R,D]; chat (exact fp32 c^), chat_tf32 (rounded copy), cbias / cnorm [K] come from vlad_centre_prep_kernel;
+// amb_count must have been zeroed earlier on the stream.  labels [R], inv_norm [R] (nullable).
+int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_img, int64_t R, int D, int K,
+                          const float* chat, const float* chat_tf32, const float* cbias, const float* cnorm,
+                          int32_t* labels, float* inv_norm, int32_t* amb_count, int32_t* amb_rows, uint32_t* amb_mask,
+                          cudaStream_t st) {
+  using namespace vtc;
+  CUtensorMap mx, mc;
+  int rc;
+  const int n_mma = (K + 15) / 16 * 16;
+  if ((rc = tc::make_map(&mx, feats, (int)R, D, D, BM, false))) return rc;
+  if ((rc = tc::make_map(&mc, chat_tf32, K, D, D, n_mma, false))) return rc;
+  AssignParams p;
+  p.n_valid = n_valid; p.n_per_img = n_per_img; p.R = (int)R; p.D = D; p.K = K;
+  p.cbias = cbias; p.cnorm = cnorm; p.labels = labels; p.inv_norm = inv_norm;
+  p.amb_count = amb_count; p.amb_rows = amb_rows; p.amb_mask = amb_mask;
+  p.n_mma = n_mma;
+  p.stage_bytes = A_BYTES + n_mma * 128;
+  static int max_smem = 0;
+  if (!max_smem) {
+    int dev = 0;
+    ANYLOC_CHECK_CUDA(cudaGetDevice(&dev));
+    ANYLOC_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(vlad_assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  }
+  const int fixed = 1024 + BAR_BYTES + VEC_BYTES;
+  p.stages = std::min(MAX_STAGES, (max_smem - fixed) / p.stage_bytes);
+  const int num_k = (D + 31) / 32;
+  p.stages = std::max(2, std::min(p.stages, std::max(2, num_k)));
+  const size_t smem = (size_t)p.stages * p.stage_bytes + fixed;
+  const int tiles = (int)((R + BM - 1) / BM);
+  const int grid = std::min(tiles, device_sm_count());
+  vlad_assign_tc_kernel<<<grid, THREADS, smem, st>>>(mx, mc, p);
+  ANYLOC_CHECK_LAUNCH();
+  const int blocks = (int)std::min<int64_t>((R + 7) / 8, (int64_t)device_sm_count() * 4);
+  if (D <= 512)
+    vlad_rescore_amb_kernel<4><<<blocks, 256, 0, st>>>(feats, D, chat, cbias, amb_count, amb_rows, amb_mask, labels);
+  else if (D <= 1024)
+    vlad_rescore_amb_kernel<8><<<blocks, 256, 0, st>>>(feats, D, chat, cbias, amb_count, amb_rows, amb_mask, labels);
+  else
+    vlad_rescore_amb_kernel<16><<<blocks, 256, 0, st>>>(feats, D, chat, cbias, amb_count, amb_rows, amb_mask, labels);
+  ANYLOC_CHECK_LAUNCH();
+  return ANYLOC_OK;
+}
+
+}  // namespace anyloc

@@ -1,8 +1,17 @@
-"""VLAD-only driver for ncu / timing: c2 (B=32,N=529,D=1536,K=32) and c5 (B=64,N=1369,D=1024,K=128) shapes."""
+"""VLAD-only driver for ncu / timing: c2 (B=32,N=529,D=1536,K=32) and c5 (B=64,N=1369,D=1024,K=128) shapes.
+ANYLOC_VLAD=2|3 selects the pipeline (read once per process).  `--save tag` stores the descriptors under
+gpurun_out/, `--compare tag` reports the max difference to a stored run (v2 vs v3 cross-check)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from anyloc_b200 import utilities as u
+
+args = sys.argv[1:]
+save = args[args.index("--save") + 1] if "--save" in args else None
+comp = args[args.index("--compare") + 1] if "--compare" in args else None
+iters = int(args[args.index("--iters") + 1]) if "--iters" in args else 20
+ver = os.environ.get("ANYLOC_VLAD", "3")
+os.makedirs("gpurun_out", exist_ok=True)
 
 for (B, N, D, K) in [(32, 529, 1536, 32), (64, 1369, 1024, 128)]:
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -11,11 +20,31 @@ for (B, N, D, K) in [(32, 529, 1536, 32), (64, 1369, 1024, 128)]:
     v = u.VLAD(K); v.kmeans = u._KMeans(K, mode="cosine"); v.c_centers = v.kmeans.centroids = c; v.desc_dim = D
     for _ in range(3):
         out = v.generate_multi(x)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # (a) back to back (inputs may sit in L2 for the c2 shape: 104 MB of features vs 126 MB of L2)
     torch.cuda.synchronize(); e0.record()
-    for _ in range(10):
+    for _ in range(iters):
         out = v.generate_multi(x)
     e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
+    ms = e0.elapsed_time(e1) / iters
+    # (b) L2 flushed before every call (a 256 MB write), timed per call
+    tot = 0.0
+    for _ in range(iters):
+        flush.fill_(1)
+        e0.record(); out = v.generate_multi(x); e1.record(); torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    ms_cold = tot / iters
     by = 4.0 * (B * N * D + B * K * D + K * D)
-    print(f"B={B} N={N} D={D} K={K}: {ms*1e3:.1f} us per call, {by/ms/1e6:.0f} GB/s algorithmic ({by/1e6:.1f} MB)")
+    print(f"v{ver} B={B} N={N} D={D} K={K}: back-to-back {ms*1e3:.1f} us ({by/ms/1e6:.0f} GB/s), "
+          f"L2-flushed {ms_cold*1e3:.1f} us ({by/ms_cold/1e6:.0f} GB/s algorithmic, {by/1e6:.1f} MB)", flush=True)
+    lab = v.kmeans.predict(x.reshape(-1, D))
+    tag = f"gpurun_out/vlad_diag_{B}_{N}_{D}_{K}"
+    if save:
+        torch.save({"out": out.cpu(), "lab": lab.cpu()}, f"{tag}_{save}.pt")
+    if comp and os.path.isfile(f"{tag}_{comp}.pt"):
+        ref = torch.load(f"{tag}_{comp}.pt")
+        d = (out.cpu() - ref["out"]).abs().max().item()
+        nl = int((lab.cpu() != ref["lab"]).sum())
+        print(f"   vs {comp}: max |d descriptor| = {d:.3e} (max |ref| {ref['out'].abs().max().item():.3e}), "
+              f"labels differing: {nl} of {lab.numel()}", flush=True)

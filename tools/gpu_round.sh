@@ -1,0 +1,22 @@
+#!/bin/bash
+# One GPU session: VLAD parity + v2/v3 A/B timing + launch list + short bench + the whole GPU suite.
+mkdir -p gpurun_out
+T0=$(date +%s)
+stamp() { echo "[$(( $(date +%s) - T0 )) s] $*" | tee -a gpurun_out/round_steps.log; }
+: > gpurun_out/round_steps.log
+timeout 400 python -m pytest tests/test_vlad_gpu.py -x -q > gpurun_out/t_vlad.log 2>&1; RC=$?
+stamp "vlad tests rc=$RC: $(tail -1 gpurun_out/t_vlad.log)"
+ANYLOC_VLAD=2 timeout 150 python tools/diag_vlad.py --save v2 > gpurun_out/diag_v2.log 2>&1
+stamp "diag v2: $(grep -c GB/s gpurun_out/diag_v2.log) lines"
+timeout 150 python tools/diag_vlad.py --compare v2 > gpurun_out/diag_v3.log 2>&1
+stamp "diag v3: $(grep -c GB/s gpurun_out/diag_v3.log) lines"
+timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/vlad_launches.csv \
+  python tools/diag_vlad.py --iters 2 > gpurun_out/ncu_diag.log 2>&1
+stamp "ncu launch list done"
+if [ $RC -eq 0 ]; then
+  timeout 400 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c2.log 2>&1
+  stamp "bench: $(tail -c 300 gpurun_out/bench_c2.log | head -c 200)"
+  timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_vlad_gpu.py > gpurun_out/t_all.log 2>&1
+  stamp "all gpu tests: $(tail -1 gpurun_out/t_all.log)"
+fi
+cat gpurun_out/round_steps.log
