@@ -1,15 +1,21 @@
 // Query->database retrieval (reference: /root/reference/utilities.py:435-450, faiss IndexFlatIP /
 // IndexFlatL2 exact search).  normalise rows -> score GEMM (fp32-equivalent) -> k-best per query,
 // best first, lowest database index first among equal scores.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace anyloc {
 
+// fp16-pair scale of unit-norm rows: |s y| <= 4096 < 65504, and s*y - hi stays far above the fp16 subnormal step for
+// every element that matters (an element below 2^-12 of the row norm contributes < 2^-36 to a unit dot product).
+constexpr float kRetrievalScale = 4096.0f;
+
 // y = x / max(|x|, 1e-12) written as a tf32 (hi,lo) pair (hi+lo == fp32 value); also |y|^2 per row
 // (needed by the L2 metric).  One CTA per row.
+template <bool F16>
 __global__ void __launch_bounds__(256)
-normalize_rows_split_kernel(const float* __restrict__ x, int D, int do_norm, float* __restrict__ hi,
-                            float* __restrict__ lo, float* __restrict__ sq) {
+normalize_rows_split_kernel(const float* __restrict__ x, int D, int do_norm, void* __restrict__ hi_v,
+                            void* __restrict__ lo_v, float* __restrict__ sq) {
   const size_t row = blockIdx.x;
   const float4* xr = reinterpret_cast<const float4*>(x + row * D);
   const int D4 = D >> 2;
@@ -26,17 +32,26 @@ normalize_rows_split_kernel(const float* __restrict__ x, int D, int do_norm, flo
   if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += red[w]; tot = t; }
   __syncthreads();
   const float nrm = fmaxf(sqrtf(tot), 1e-12f);
-  float4* h4 = reinterpret_cast<float4*>(hi + row * D);
-  float4* l4 = reinterpret_cast<float4*>(lo + row * D);
+  float4* h4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(hi_v) + row * D);
+  float4* l4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(lo_v) + row * D);
+  uint2* h2 = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(hi_v) + row * D);   // 4 halves = 8 bytes
+  uint2* l2 = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(lo_v) + row * D);
   float ss2 = 0.f;
   for (int d = threadIdx.x; d < D4; d += blockDim.x) {
     float4 v = __ldg(xr + d);
     if (do_norm) { v.x = v.x / nrm; v.y = v.y / nrm; v.z = v.z / nrm; v.w = v.w / nrm; }
     ss2 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    float4 h, l;
-    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
-    split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-    h4[d] = h; l4[d] = l;
+    if constexpr (F16) {
+      uint2 h, l;
+      split_f16x2(v.x * kRetrievalScale, v.y * kRetrievalScale, h.x, l.x);
+      split_f16x2(v.z * kRetrievalScale, v.w * kRetrievalScale, h.y, l.y);
+      h2[d] = h; l2[d] = l;
+    } else {
+      float4 h, l;
+      split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
+      split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+      h4[d] = h; l4[d] = l;
+    }
   }
   if (sq) {
     ss2 = warp_sum(ss2);
@@ -137,12 +152,28 @@ extern "C" int anyloc_topk(const float* db, const float* qu, int n_db, int n_q, 
     return ANYLOC_ERR_WORKSPACE;
   }
   ProfScope ps(PC_TOPK, st, 4.0 * ((double)n_db + n_q) * Dv);
-  normalize_rows_split_kernel<<<n_db, 256, 0, st>>>(db, Dv, normalize, db_hi, db_lo, dd);
-  ANYLOC_CHECK_LAUNCH();
-  normalize_rows_split_kernel<<<n_q, 256, 0, st>>>(qu, Dv, normalize, qu_hi, qu_lo, qq);
-  ANYLOC_CHECK_LAUNCH();
-  int rc = anyloc_gemm_nt(qu_hi, qu_lo, Dv, db_hi, db_lo, Dv, n_q, n_db, Dv, ANYLOC_PAIR_TF32, 1.0f, ANYLOC_EPI_BIAS,
-                          nullptr, nullptr, nullptr, scores, nullptr, n_db, ANYLOC_PAIR_TF32, ANYLOC_GEMM_AUTO, stream);
+  // Unit-norm rows (the reference's default, norm_descs=True) go through the 2x faster kind::f16 tensor path as fp16
+  // pairs of 4096*y; un-normalised rows have no a-priori range and keep the tf32 pairs.  ANYLOC_TOPK_F16=0 disables.
+  static int f16_env = -1;
+  if (f16_env < 0) { const char* e = getenv("ANYLOC_TOPK_F16"); f16_env = e ? atoi(e) : 1; }
+  const bool f16 = f16_env && normalize && (Dv % 8) == 0;
+  int rc;
+  if (f16) {
+    normalize_rows_split_kernel<true><<<n_db, 256, 0, st>>>(db, Dv, normalize, db_hi, db_lo, dd);
+    ANYLOC_CHECK_LAUNCH();
+    normalize_rows_split_kernel<true><<<n_q, 256, 0, st>>>(qu, Dv, normalize, qu_hi, qu_lo, qq);
+    ANYLOC_CHECK_LAUNCH();
+    rc = anyloc_gemm_nt(qu_hi, qu_lo, Dv, db_hi, db_lo, Dv, n_q, n_db, Dv, ANYLOC_PAIR_F16,
+                        1.0f / (kRetrievalScale * kRetrievalScale), ANYLOC_EPI_BIAS, nullptr, nullptr, nullptr, scores,
+                        nullptr, n_db, ANYLOC_PAIR_TF32, ANYLOC_GEMM_AUTO, stream);
+  } else {
+    normalize_rows_split_kernel<false><<<n_db, 256, 0, st>>>(db, Dv, normalize, db_hi, db_lo, dd);
+    ANYLOC_CHECK_LAUNCH();
+    normalize_rows_split_kernel<false><<<n_q, 256, 0, st>>>(qu, Dv, normalize, qu_hi, qu_lo, qq);
+    ANYLOC_CHECK_LAUNCH();
+    rc = anyloc_gemm_nt(qu_hi, qu_lo, Dv, db_hi, db_lo, Dv, n_q, n_db, Dv, ANYLOC_PAIR_TF32, 1.0f, ANYLOC_EPI_BIAS,
+                        nullptr, nullptr, nullptr, scores, nullptr, n_db, ANYLOC_PAIR_TF32, ANYLOC_GEMM_AUTO, stream);
+  }
   if (rc) return rc;
   topk_select_kernel<<<n_q, 1024, 0, st>>>(scores, n_db, n_db, k, metric, qq, dd, dist, idx);
   ANYLOC_CHECK_LAUNCH();

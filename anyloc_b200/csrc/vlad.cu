@@ -22,6 +22,7 @@ namespace anyloc {
 __global__ void vlad_centre_prep_kernel(const float* __restrict__ c, int K, int D, int dist_mode,
                                         float* __restrict__ chat, float* __restrict__ cbias,
                                         float* __restrict__ chat_tf32, float* __restrict__ cnorm,
+                                        float* __restrict__ cdnorm /* |c^ - tf32(c^)|, nullable */,
                                         int32_t* __restrict__ zero_a, int zero_a_n, int32_t* __restrict__ zero_b,
                                         int zero_b_n) {
   // the counters of the later launches on this stream are cleared here (saves two memset nodes)
@@ -42,12 +43,13 @@ __global__ void vlad_centre_prep_kernel(const float* __restrict__ c, int K, int 
   }
   __syncthreads();
   ss = red[0];
+  float dd = 0.f;                                  // sum (c^ - tf32(c^))^2 over this thread's elements
   if (dist_mode == ANYLOC_DIST_COSINE) {
     const float den = sqrtf(ss) + 1e-8f;            // fpk cos_sim: b / (|b| + 1e-8)
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
       float v = row[d] / den, h, l;
       chat[(size_t)k * D + d] = v;
-      if (chat_tf32) { split_tf32(v, h, l); chat_tf32[(size_t)k * D + d] = h; }
+      if (chat_tf32) { split_tf32(v, h, l); chat_tf32[(size_t)k * D + d] = h; dd += l * l; }
     }
     if (threadIdx.x == 0) { cbias[k] = 0.f; if (cnorm) cnorm[k] = sqrtf(ss) / den; }
   } else {
@@ -55,9 +57,20 @@ __global__ void vlad_centre_prep_kernel(const float* __restrict__ c, int K, int 
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
       float v = row[d], h, l;
       chat[(size_t)k * D + d] = v;
-      if (chat_tf32) { split_tf32(v, h, l); chat_tf32[(size_t)k * D + d] = h; }
+      if (chat_tf32) { split_tf32(v, h, l); chat_tf32[(size_t)k * D + d] = h; dd += l * l; }
     }
     if (threadIdx.x == 0) { cbias[k] = -0.5f * ss; if (cnorm) cnorm[k] = sqrtf(ss); }
+  }
+  if (cdnorm) {
+    __syncthreads();
+    dd = warp_sum(dd);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dd;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+      cdnorm[k] = sqrtf(tot);
+    }
   }
 }
 
@@ -275,30 +288,42 @@ vlad_accumulate2_kernel(const float* __restrict__ x, const int32_t* __restrict__
 }
 
 // ------------------------------------------------------------------ accumulate v3 (+ fused normalisation)
-// CTA = (128-column slice, image), 16 warps.  The image's rows are counting-sorted by label in shared memory (stable:
-// rows of a cluster stay in row order, so every sum has ONE fixed order -> bitwise reproducible, batch == single image),
-// then each warp takes whole clusters (dynamic grab): 8 independent 512-byte row segments in flight per warp, the
-// cluster sum lives in registers (lane = 4 columns) -- no shared-memory accumulators, no read-modify-write chains.
-// The last CTA of an image to finish (global ticket) applies the intra- and global L2 normalisation to that image's
-// descriptor while it is still in L2, which removes the separate normalisation launch.
-constexpr int ACC3_WARPS = 16;
+// CTA = (128-column slice, image), 8 warps, 4-5 CTAs per SM (one wave at the BASELINE shapes).  The image's rows are
+// counting-sorted by label in shared memory (stable: rows of a cluster stay in row order), the sorted list is cut into
+// tasks of <= 64 rows of ONE cluster, and warps grab tasks dynamically: 8 independent 512-byte row segments in flight
+// per warp, the partial sum lives in registers (lane = 4 columns) -- no shared-memory accumulators, no
+// read-modify-write chains, and a skewed vocabulary (one cluster holding a third of the image) no longer serialises on
+// one warp.  Clusters of several tasks are combined from shared-memory slots in task order, so every sum has ONE fixed
+// order: bitwise reproducible, batch == single image.  The last CTA of an image to finish (global ticket) applies the
+// intra- and global L2 normalisation to that image's descriptor while it is still in L2 (no separate launch).
+constexpr int ACC3_WARPS = 8;
+constexpr int ACC3_SEG = 64;
+static inline int acc3_max_tasks(int N, int K) { return N / ACC3_SEG + K + 1; }
+__device__ __forceinline__ int acc3_max_tasks_dev(int N, int K) { return N / ACC3_SEG + K + 1; }
+static inline int acc3_max_slots(int N) { return 2 * (N / ACC3_SEG) + 2; }
 static inline size_t acc3_smem_bytes(int N, int K) {
-  return ((size_t)3 * N + (size_t)(K + 1) + (size_t)ACC3_WARPS * K + 2 * (size_t)K) * 4;
+  return ((size_t)3 * N + 3 * (size_t)(K + 1) + (size_t)ACC3_WARPS * K + 2 * (size_t)K + acc3_max_tasks(N, K) + 4) * 4 +
+         (size_t)acc3_max_slots(N) * 512;
 }
-__global__ void __launch_bounds__(ACC3_WARPS * 32, 2)
+__global__ void __launch_bounds__(ACC3_WARPS * 32, 4)
 vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__ labels,
                         const float* __restrict__ inv_norm, const float* __restrict__ centers, int N, int D, int K,
                         int norm_descs, int intra_norm, float* vlad, float* partial_ss /* [B,K,nslices] */,
                         int32_t* done /* [B], zero on entry */) {
-  extern __shared__ int sm3[];
+  extern __shared__ __align__(16) int sm3[];
   int* order = sm3;                                         // [N] rows sorted by label (stable)
   int* lab = order + N;                                     // [N]
   float* inv = reinterpret_cast<float*>(lab + N);           // [N]
-  int* start = reinterpret_cast<int*>(inv + N);             // [K+1]
-  int* cntw = start + K + 1;                                // [ACC3_WARPS][K]
+  int* start = reinterpret_cast<int*>(inv + N);             // [K+1] first sorted position of cluster k
+  int* tstart = start + K + 1;                              // [K+1] first task of cluster k
+  int* sbase = tstart + K + 1;                              // [K+1] first partial-sum slot of a multi-task cluster
+  int* cntw = sbase + K + 1;                                // [ACC3_WARPS][K]
   float* kss = reinterpret_cast<float*>(cntw + ACC3_WARPS * K);   // [K]
   float* ksq = kss + K;                                     // [K]
-  __shared__ int next_k, s_last;
+  int* task_k = reinterpret_cast<int*>(ksq + K);            // [max_tasks]
+  float* slots = reinterpret_cast<float*>(sm3) +
+                 (((size_t)3 * N + 3 * (size_t)(K + 1) + (size_t)ACC3_WARPS * K + 2 * (size_t)K + acc3_max_tasks_dev(N, K) + 3) & ~(size_t)3);
+  __shared__ int next_task, s_last;
   __shared__ float s_gnorm;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const int b = blockIdx.y, slice = blockIdx.x, nslices = gridDim.x;
@@ -309,7 +334,7 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
     inv[n] = norm_descs ? inv_norm[(size_t)b * N + n] : 1.0f;
   }
   for (int i = t; i < ACC3_WARPS * K; i += blockDim.x) cntw[i] = 0;
-  if (t == 0) next_k = 0;
+  if (t == 0) next_task = 0;
   __syncthreads();
   // per-warp histograms over contiguous row chunks
   const int chunk = (((N + ACC3_WARPS - 1) / ACC3_WARPS) + 31) & ~31;
@@ -322,20 +347,30 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
     start[k] = tot;
   }
   __syncthreads();
-  if (w == 0) {                                             // exclusive scan of the totals -> cluster offsets
-    int running = 0;
+  if (w == 0) {                                             // exclusive scans: rows, tasks, partial-sum slots
+    int run_r = 0, run_t = 0, run_s = 0;
     for (int k0 = 0; k0 < K; k0 += 32) {
       const int k = k0 + lane;
       const int c = k < K ? start[k] : 0;
-      int incl = c;
+      const int nt = k < K ? max(1, (c + ACC3_SEG - 1) / ACC3_SEG) : 0;
+      const int ns = nt > 1 ? nt : 0;
+      int ir = c, it = nt, is = ns;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-      if (k < K) start[k] = running + incl - c;
-      running += __shfl_sync(0xffffffffu, incl, 31);
+      for (int o = 1; o < 32; o <<= 1) {
+        const int yr = __shfl_up_sync(0xffffffffu, ir, o), yt = __shfl_up_sync(0xffffffffu, it, o),
+                  ys = __shfl_up_sync(0xffffffffu, is, o);
+        if (lane >= o) { ir += yr; it += yt; is += ys; }
+      }
+      if (k < K) { start[k] = run_r + ir - c; tstart[k] = run_t + it - nt; sbase[k] = run_s + is - ns; }
+      run_r += __shfl_sync(0xffffffffu, ir, 31);
+      run_t += __shfl_sync(0xffffffffu, it, 31);
+      run_s += __shfl_sync(0xffffffffu, is, 31);
     }
-    if (lane == 0) start[K] = running;
+    if (lane == 0) { start[K] = run_r; tstart[K] = run_t; sbase[K] = run_s; }
   }
   __syncthreads();
+  for (int k = t; k < K; k += blockDim.x)                   // task table
+    for (int q = tstart[k]; q < tstart[k + 1]; ++q) task_k[q] = k;
   for (int n0 = r0; n0 < r1; n0 += 32) {                    // stable placement
     const int n = n0 + lane;
     const int l = n < r1 ? lab[n] : -1;
@@ -352,14 +387,17 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
     __syncwarp();
   }
   __syncthreads();
-  // clusters -> registers
+  // tasks -> registers
   const float* xb = x + (size_t)b * N * D + col;
+  const int ntasks = tstart[K];
   for (;;) {
-    int k = 0;
-    if (lane == 0) k = atomicAdd(&next_k, 1);
-    k = __shfl_sync(0xffffffffu, k, 0);
-    if (k >= K) break;
-    const int s = start[k], e = start[k + 1];
+    int q = 0;
+    if (lane == 0) q = atomicAdd(&next_task, 1);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q >= ntasks) break;
+    const int k = task_k[q];
+    const int seg = q - tstart[k], nt = tstart[k + 1] - tstart[k];
+    const int s = start[k] + seg * ACC3_SEG, e = min(start[k + 1], s + ACC3_SEG);
     const float4 c = colok ? __ldg(reinterpret_cast<const float4*>(centers + (size_t)k * D + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     if (colok) {
@@ -379,8 +417,25 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
           }
         }
       }
-      *reinterpret_cast<float4*>(vlad + ((size_t)b * K + k) * D + col) = a;
     }
+    if (nt == 1) {
+      if (colok) *reinterpret_cast<float4*>(vlad + ((size_t)b * K + k) * D + col) = a;
+      const float ss = warp_sum(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w);
+      if (lane == 0) kss[k] = ss;
+    } else {
+      *reinterpret_cast<float4*>(slots + (size_t)(sbase[k] + seg) * 128 + lane * 4) = a;
+    }
+  }
+  __syncthreads();
+  for (int k = w; k < K; k += ACC3_WARPS) {                 // clusters of several tasks: combine in task order
+    const int nt = tstart[k + 1] - tstart[k];
+    if (nt <= 1) continue;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < nt; ++q) {
+      const float4 p = *reinterpret_cast<const float4*>(slots + (size_t)(sbase[k] + q) * 128 + lane * 4);
+      a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+    }
+    if (colok) *reinterpret_cast<float4*>(vlad + ((size_t)b * K + k) * D + col) = a;
     const float ss = warp_sum(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w);
     if (lane == 0) kss[k] = ss;
   }
@@ -413,12 +468,24 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
   const float g = s_gnorm;
   float4* vb = reinterpret_cast<float4*>(vlad + (size_t)b * K * D);
   const int D4 = D >> 2, total4 = K * D4;
-  for (int i = t; i < total4; i += blockDim.x) {
-    const float sc = kss[i / D4];
-    float4 v = __ldcg(vb + i);
-    // two separate multiplications like F.normalize(intra) then F.normalize(global)
-    v.x = (v.x * sc) * g; v.y = (v.y * sc) * g; v.z = (v.z * sc) * g; v.w = (v.w * sc) * g;
-    vb[i] = v;
+  constexpr int UN = 8;                                     // loads batched ahead of the stores (L2 latency chain)
+  for (int i0 = t; i0 < total4; i0 += blockDim.x * UN) {
+    float4 v[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < total4) v[u] = __ldcg(vb + i);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < total4) {
+        const float sc = kss[i / D4];
+        // two separate multiplications like F.normalize(intra) then F.normalize(global)
+        v[u].x = (v[u].x * sc) * g; v[u].y = (v[u].y * sc) * g; v[u].z = (v[u].z * sc) * g; v[u].w = (v[u].w * sc) * g;
+        vb[i] = v[u];
+      }
+    }
   }
 }
 
@@ -731,8 +798,8 @@ bool vlad_assign_tc_supported(const float* feats, const float* chat_tf32, int64_
 size_t vlad_assign_tc_ws_bytes(int64_t R);
 int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_img, int64_t R, int D, int K,
                           const float* chat, const float* chat_tf32, const float* cbias, const float* cnorm,
-                          int32_t* labels, float* inv_norm, int32_t* amb_count, int32_t* amb_rows, uint32_t* amb_mask,
-                          cudaStream_t st);
+                          const float* cdnorm, int32_t* labels, float* inv_norm, int32_t* amb_count, int32_t* amb_rows,
+                          uint32_t* amb_mask, cudaStream_t st);
 }  // namespace anyloc
 
 // ANYLOC_VLAD=2 selects the v2 pipeline (coarse GEMM + full rescoring pass + shared-memory accumulate + normalise
@@ -749,13 +816,14 @@ extern "C" size_t anyloc_vlad_workspace_bytes(int B, int N, int D, int K) {
   int nslices = cdiv(D, ACC_COLS);
   return 2 * align_up((size_t)K * D * 4, 256) + 2 * align_up((size_t)K * 4, 256) + align_up(R * 4, 256) * 2 +
          align_up(R * (size_t)K * 4, 256) + align_up((size_t)B * K * nslices * 4, 256) +
-         align_up(((size_t)K * D + K) * 4, 256) + vlad_assign_tc_ws_bytes((int64_t)R) + align_up((size_t)B * 4, 256) +
+         align_up(((size_t)K * D + K) * 4, 256) + align_up((size_t)K * 4, 256) + vlad_assign_tc_ws_bytes((int64_t)R) + align_up((size_t)B * 4, 256) +
          4096;
 }
 
 namespace {
 struct AssignBufs {
   float *chat, *chat_tf32, *cbias, *cnorm, *coarse;
+  float* cdnorm = nullptr;                                                           // v3: |c^ - tf32(c^)| per centre
   int32_t *amb_count = nullptr, *amb_rows = nullptr; uint32_t* amb_mask = nullptr;   // v3 work list (optional)
   int32_t* done = nullptr; int n_done = 0;                                           // accumulate3 tickets (optional)
 };
@@ -766,11 +834,11 @@ int launch_assign(const float* feats, const int32_t* n_valid, int N_per_img, int
                   const float* centers, int dist_mode, const AssignBufs& ab, int32_t* labels, float* inv_norm,
                   cudaStream_t st) {
   vlad_centre_prep_kernel<<<K, 256, 0, st>>>(centers, K, D, dist_mode, ab.chat, ab.cbias, ab.chat_tf32, ab.cnorm,
-                                             ab.amb_count, ab.amb_count ? 1 : 0, ab.done, ab.done ? ab.n_done : 0);
+                                             ab.cdnorm, ab.amb_count, ab.amb_count ? 1 : 0, ab.done, ab.done ? ab.n_done : 0);
   ANYLOC_CHECK_LAUNCH();
-  if (vlad_version() >= 3 && ab.amb_count && ab.amb_rows && ab.amb_mask &&
+  if (vlad_version() >= 3 && ab.amb_count && ab.amb_rows && ab.amb_mask && ab.cdnorm &&
       vlad_assign_tc_supported(feats, ab.chat_tf32, R, D, K))
-    return vlad_assign_tc_launch(feats, n_valid, N_per_img, R, D, K, ab.chat, ab.chat_tf32, ab.cbias, ab.cnorm, labels,
+    return vlad_assign_tc_launch(feats, n_valid, N_per_img, R, D, K, ab.chat, ab.chat_tf32, ab.cbias, ab.cnorm, ab.cdnorm, labels,
                                  inv_norm, ab.amb_count, ab.amb_rows, ab.amb_mask, st);
   EpiParams ep{ANYLOC_EPI_BIAS, ab.cbias, nullptr, nullptr, ab.coarse, nullptr, K};
   const bool fast = ab.coarse != nullptr && D <= 2048 && R >= 256 && R < (1ll << 31) &&
@@ -807,6 +875,7 @@ bool take_assign_bufs(Workspace& w, int64_t R, int D, int K, AssignBufs* ab) {
   ab->cbias = w.take<float>(K);
   ab->cnorm = w.take<float>(K);
   ab->coarse = w.take<float>((size_t)R * K);        // may be null when the caller's workspace is the small one
+  ab->cdnorm = w.take<float>(K);
   ab->amb_count = w.take<int32_t>(64);
   ab->amb_rows = w.take<int32_t>((size_t)R);
   ab->amb_mask = w.take<uint32_t>((size_t)R * 4);
@@ -850,7 +919,7 @@ extern "C" int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, 
     return ANYLOC_ERR_WORKSPACE;
   }
   const size_t smem3 = acc3_smem_bytes(N, K);
-  const bool acc3 = vlad_version() >= 3 && smem3 <= 160 * 1024;
+  const bool acc3 = vlad_version() >= 3 && smem3 <= 100 * 1024 && N < (1 << 30) / 4;
   if (acc3) { ab.done = w.take<int32_t>((size_t)B); ab.n_done = B; }
   ProfScope ps(PC_VLAD, st, 4.0 * ((double)B * N * D + (double)B * K * D + (double)K * D));
   int rc = launch_assign(feats, n_valid, N, (int64_t)R, D, K, centers, dist_mode, ab, labels, inv_norm, st);
@@ -858,7 +927,7 @@ extern "C" int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, 
   if (acc3 && ab.done) {
     static bool attr_set = false;
     if (!attr_set) {
-      ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(vlad_accumulate3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(vlad_accumulate3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       attr_set = true;
     }
     vlad_accumulate3_kernel<<<dim3(nslices, B), ACC3_WARPS * 32, smem3, st>>>(feats, labels, inv_norm, centers, N, D, K,

@@ -11,13 +11,15 @@
 //             truncates to tf32), coarse scores S~ accumulate over all of D in TMEM (2 x 128 columns, double buffered)
 //   warp 2    TMEM allocator
 //   warps 4-7 thread = row: sum of squares of every staged k-block (128B-swizzled shared-memory reads, conflict free),
-//             then the tile epilogue: S~ from TMEM, candidate set {k : S~_k >= max - 2 eps} with the rigorous bound
-//             eps = 2^-9 |x| max|c^| (truncated x, rounded c^).  One candidate -> that IS the exact-fp32 argmax.
+//             (and of what the tensor core's tf32 truncation drops), then the tile epilogue: S~ from TMEM, candidate set
+//             {k : S~_k >= max - 2 eps} with a rigorous per-row bound eps on |S~ - S| built from those MEASURED norms
+//             (see the epilogue).  One candidate -> that IS the exact-fp32 argmax.
 //             Several -> (row, candidate mask) goes to the work list.
 // vlad_rescore_amb_kernel -- warp per work-list row: exact fp32 dot products for the candidates only (same arithmetic
 // as the v2 rescoring kernel), first-max argmax -> lowest index wins exact ties, all-zero rows get label 0.
 #include <cuda.h>
 #include <algorithm>
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace anyloc {
@@ -31,14 +33,14 @@ constexpr int TMEM_COLS = 256;             // 2 accumulators x 128 columns
 constexpr int MAX_STAGES = 12;
 constexpr int MAX_K = 128;
 constexpr int BAR_BYTES = 256;             // (2*MAX_STAGES + 4) mbarriers + the TMEM slot
-constexpr int VEC_BYTES = 2 * MAX_K * 4;   // cbias + cnorm
+constexpr int VEC_BYTES = 3 * MAX_K * 4;   // cbias + cnorm + cdnorm
 
 struct AssignParams {
   const int32_t* n_valid; int n_per_img; int R; int D; int K;
-  const float* cbias; const float* cnorm;
+  const float* cbias; const float* cnorm; const float* cdnorm;
   int32_t* labels; float* inv_norm;
   int32_t* amb_count; int32_t* amb_rows; uint32_t* amb_mask;
-  int stages; int stage_bytes; int n_mma;
+  int stages; int stage_bytes; int n_mma; int burst;
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -54,6 +56,7 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_cbias = reinterpret_cast<float*>(bar_area + BAR_BYTES);      // [MAX_K]
   float* s_cnorm = s_cbias + MAX_K;                                     // [MAX_K]
+  float* s_cdnorm = s_cnorm + MAX_K;                                    // [MAX_K]
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -77,6 +80,7 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   for (int k = threadIdx.x; k < MAX_K; k += THREADS) {
     s_cbias[k] = k < p.K ? p.cbias[k] : 0.f;
     s_cnorm[k] = k < p.K ? p.cnorm[k] : 0.f;
+    s_cdnorm[k] = k < p.K ? p.cdnorm[k] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -86,18 +90,28 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------ TMA producer
+      // Stages are (re)filled in bursts of `burst` consecutive k-blocks: the TMA requests of one burst hit
+      // burst * 128 contiguous bytes of every row back to back, which the DRAM controller can serve from one open
+      // page (a lone 128-byte access per row every few hundred ns re-opens the page each time).
       const uint32_t tx_bytes = (uint32_t)(A_BYTES + p.n_mma * 128);
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = tile * BM;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
-          const uint32_t fb = smem_u32(full_bar + stage);
-          mbar_expect_tx(fb, tx_bytes);
-          const uint32_t sbase = smem_u32(smem + stage * p.stage_bytes);
-          tma_load_2d(sbase, &tm_x, fb, kb * 32, m0);
-          tma_load_2d(sbase + A_BYTES, &tm_c, fb, kb * 32, 0);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        for (int kb0 = 0; kb0 < num_k; kb0 += p.burst) {
+          const int g = min(p.burst, num_k - kb0);
+          for (int j = 0; j < g; ++j) {
+            int sj = stage + j; uint32_t pj = phase;
+            if (sj >= p.stages) { sj -= p.stages; pj ^= 1; }
+            mbar_wait(smem_u32(empty_bar + sj), pj ^ 1);
+          }
+          for (int j = 0; j < g; ++j) {
+            const uint32_t fb = smem_u32(full_bar + stage);
+            mbar_expect_tx(fb, tx_bytes);
+            const uint32_t sbase = smem_u32(smem + stage * p.stage_bytes);
+            tma_load_2d(sbase, &tm_x, fb, (kb0 + j) * 32, m0);
+            tma_load_2d(sbase + A_BYTES, &tm_c, fb, (kb0 + j) * 32, 0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -134,12 +148,12 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const int q = warp & 3;                          // TMEM lane quarter == row quarter of the tile
     const int rt = q * 32 + lane;
     const int sw = rt & 7;
-    float cmax = 0.f;
-    for (int k = 0; k < p.K; ++k) cmax = fmaxf(cmax, s_cnorm[k]);
+    float cmax = 0.f, dcmax = 0.f;
+    for (int k = 0; k < p.K; ++k) { cmax = fmaxf(cmax, s_cnorm[k]); dcmax = fmaxf(dcmax, s_cdnorm[k]); }
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      float ss = 0.f;
+      float ss = 0.f, dd = 0.f;                     // |x|^2 and |x - tf32_trunc(x)|^2 (what the tensor core drops)
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(smem_u32(full_bar + stage), phase);
         const uint8_t* rowp = smem + stage * p.stage_bytes + rt * 128;
@@ -147,6 +161,11 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         for (int c = 0; c < 8; ++c) {
           const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ sw) << 4));
           ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          const float dx = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          const float dy = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          const float dz = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          const float dw = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          dd += dx * dx + dy * dy + dz * dz + dw * dw;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(empty_bar + stage));
@@ -169,8 +188,15 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           }
         }
       }
-      // |S~_k - S_k| <= (2^-10 + 2^-11) sum|x_i c_i| < 2^-9 |x||c^_k|  (truncated x, round-to-nearest c^)
-      const float thresh = smax - 2.0f * (0.001953125f * xn * cmax) - 1e-30f;
+      // S~_k - S_k = -sum d_i c^_i - sum x_i e_i + sum d_i e_i + (accumulation), with d = x - trunc_tf32(x) (its norm is
+      // MEASURED per row above) and e = c^ - tf32(c^) (norm per centre from the prep kernel), so by Cauchy-Schwarz
+      //   |S~_k - S_k| <= |d||c^| + |x||e| + acc,
+      // acc <= 3e-4 |x||c^|: D/8 <= 256 tensor-core steps, each aligning 8 exact products and the accumulator to the
+      // largest exponent and truncating (<= 9 * 2^-23 of the largest addend, itself <= |x||c^|); the 1 % on top covers
+      // the fp32 evaluation of the norms and the second-order term.  Rigorous like the a-priori 2^-9 |x||c^| of v2,
+      // but ~2.4x tighter (|d| is typically 0.4 * 2^-10 |x|): fewer than half of the rows stay ambiguous.
+      const float eps = 1.01f * (sqrtf(dd) * cmax + xn * (dcmax + 3.0e-4f * cmax));
+      const float thresh = smax - 2.0f * eps - 1e-30f;
       uint32_t mask[MAX_K / 32];
 #pragma unroll
       for (int i = 0; i < MAX_K / 32; ++i) mask[i] = 0u;
@@ -291,8 +317,8 @@ size_t vlad_assign_tc_ws_bytes(int64_t R) {
 // amb_count must have been zeroed earlier on the stream.  labels [R], inv_norm [R] (nullable).
 int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_img, int64_t R, int D, int K,
                           const float* chat, const float* chat_tf32, const float* cbias, const float* cnorm,
-                          int32_t* labels, float* inv_norm, int32_t* amb_count, int32_t* amb_rows, uint32_t* amb_mask,
-                          cudaStream_t st) {
+                          const float* cdnorm, int32_t* labels, float* inv_norm, int32_t* amb_count, int32_t* amb_rows,
+                          uint32_t* amb_mask, cudaStream_t st) {
   using namespace vtc;
   CUtensorMap mx, mc;
   int rc;
@@ -301,7 +327,7 @@ int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_
   if ((rc = tc::make_map(&mc, chat_tf32, K, D, D, n_mma, false))) return rc;
   AssignParams p;
   p.n_valid = n_valid; p.n_per_img = n_per_img; p.R = (int)R; p.D = D; p.K = K;
-  p.cbias = cbias; p.cnorm = cnorm; p.labels = labels; p.inv_norm = inv_norm;
+  p.cbias = cbias; p.cnorm = cnorm; p.cdnorm = cdnorm; p.labels = labels; p.inv_norm = inv_norm;
   p.amb_count = amb_count; p.amb_rows = amb_rows; p.amb_mask = amb_mask;
   p.n_mma = n_mma;
   p.stage_bytes = A_BYTES + n_mma * 128;
@@ -316,6 +342,9 @@ int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_
   p.stages = std::min(MAX_STAGES, (max_smem - fixed) / p.stage_bytes);
   const int num_k = (D + 31) / 32;
   p.stages = std::max(2, std::min(p.stages, std::max(2, num_k)));
+  static int burst_env = -1;             // ANYLOC_VLAD_TMA_BURST: k-blocks issued back to back by the producer (A/B knob)
+  if (burst_env < 0) { const char* e = getenv("ANYLOC_VLAD_TMA_BURST"); burst_env = e ? atoi(e) : 4; }
+  p.burst = std::max(1, std::min(burst_env, p.stages / 2));
   const size_t smem = (size_t)p.stages * p.stage_bytes + fixed;
   const int tiles = (int)((R + BM - 1) / BM);
   const int grid = std::min(tiles, device_sm_count());

@@ -268,12 +268,19 @@ def run_ours(args, wl):
         ach = g_fl / (g_ms / 1e3) / 1e12
         f16 = args.precision == "f16x3"
         passes = 3.0 if f16 else 6.0       # bf16-rate-equivalent tensor passes per algorithmic product
-        roof = {"kernel": "gemm_tc3_kernel<256,%s> (tcgen05 kind::%s, 3-term split, fp32 accumulate, RN chunk "
-                          "accumulation)" % ("true", "f16") if f16 else
-                          "gemm_tc3_kernel<256,false> (tcgen05 kind::tf32, 3-term split, fp32 accumulate, RN chunk "
-                          "accumulation)",
+        two_cta = os.environ.get("ANYLOC_GEMM_2CTA", "1") != "0"
+        kname = ("gemm_tc3_2cta_kernel<%s> (tcgen05 cta_group::2 M256xN256, kind::%s" if two_cta else
+                 "gemm_tc3_kernel<256,%s> (tcgen05 cta_group::1 M128xN256, kind::%s") % (
+                     "true" if f16 else "false", "f16" if f16 else "tf32")
+        # DRAM bytes per launch of this kernel from the committed ncu --set full capture of the same command
+        # (profiles/r01_ncu_summary.md, "Final state": mean over the four per-block GEMMs w3/qkv/proj/w12); only
+        # valid for the configuration that was captured
+        traffic = 617.5e6 if (args.workload == "c2" and f16 and two_cta) else None
+        roof = {"kernel": kname + ", 3-term split, fp32 accumulate, RN chunk accumulation)",
                 "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tflops_sustained"], "traffic": None,
+                "frac": ach / peaks["tflops_sustained"], "traffic": traffic,
+                "traffic_source": "profiles/r01_ncu_summary.md (ncu --set full, dram__bytes_read+write per launch)" if traffic else None,
+                "algorithmic_bytes_per_launch": 425.5e6 if traffic else None,
                 "peak_source": f"{peaks['source']} cuBLAS bf16 sustained (MEASURED_PEAKS.json)",
                 "note": "achieved = algorithmic 2MNK FLOPs / device time; the engine issues 3 MMAs per product "
                         "(fp32-equivalent accuracy) at %s the bf16 rate, i.e. %d bf16-equivalent passes"

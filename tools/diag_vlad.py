@@ -10,10 +10,12 @@ args = sys.argv[1:]
 save = args[args.index("--save") + 1] if "--save" in args else None
 comp = args[args.index("--compare") + 1] if "--compare" in args else None
 iters = int(args[args.index("--iters") + 1]) if "--iters" in args else 20
-ver = os.environ.get("ANYLOC_VLAD", "3")
+shape = args[args.index("--shape") + 1] if "--shape" in args else None
+ver = os.environ.get("ANYLOC_VLAD", "3") + ("/burst" + os.environ["ANYLOC_VLAD_TMA_BURST"] if "ANYLOC_VLAD_TMA_BURST" in os.environ else "")
 os.makedirs("gpurun_out", exist_ok=True)
 
-for (B, N, D, K) in [(32, 529, 1536, 32), (64, 1369, 1024, 128)]:
+SHAPES = {"c2": (32, 529, 1536, 32), "c5": (64, 1369, 1024, 128)}
+for (B, N, D, K) in ([SHAPES[shape]] if shape else list(SHAPES.values())):
     g = torch.Generator(device="cuda").manual_seed(0)
     x = torch.nn.functional.normalize(torch.randn(B, N, D, device="cuda", generator=g), dim=-1)
     c = 0.7 * x.reshape(-1, D)[torch.randperm(B * N, device="cuda", generator=g)[:K]].contiguous()
