@@ -311,10 +311,10 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
                         int norm_descs, int intra_norm, float* vlad, float* partial_ss /* [B,K,nslices] */,
                         int32_t* done /* [B], zero on entry */) {
   extern __shared__ __align__(16) int sm3[];
-  int* order = sm3;                                         // [N] rows sorted by label (stable)
-  int* lab = order + N;                                     // [N]
-  float* inv = reinterpret_cast<float*>(lab + N);           // [N]
-  int* start = reinterpret_cast<int*>(inv + N);             // [K+1] first sorted position of cluster k
+  int* ooff = sm3;                                          // [N] n * D of the rows, sorted by label (stable)
+  int* lab = ooff + N;                                      // [N]
+  float* inv_s = reinterpret_cast<float*>(lab + N);         // [N] 1/|x| in the same sorted order
+  int* start = reinterpret_cast<int*>(inv_s + N);           // [K+1] first sorted position of cluster k
   int* tstart = start + K + 1;                              // [K+1] first task of cluster k
   int* sbase = tstart + K + 1;                              // [K+1] first partial-sum slot of a multi-task cluster
   int* cntw = sbase + K + 1;                                // [ACC3_WARPS][K]
@@ -326,13 +326,12 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
   __shared__ int next_task, s_last;
   __shared__ float s_gnorm;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int b = blockIdx.y, slice = blockIdx.x, nslices = gridDim.x;
+  // images in reverse order: the assignment pass streamed them in ascending order, so the last ones are the most
+  // likely to still sit in L2 when this kernel starts
+  const int b = (int)gridDim.y - 1 - (int)blockIdx.y, slice = blockIdx.x, nslices = gridDim.x;
   const int col = slice * 128 + lane * 4;
   const bool colok = col < D;                               // D % 4 == 0
-  for (int n = t; n < N; n += blockDim.x) {
-    lab[n] = labels[(size_t)b * N + n];
-    inv[n] = norm_descs ? inv_norm[(size_t)b * N + n] : 1.0f;
-  }
+  for (int n = t; n < N; n += blockDim.x) lab[n] = labels[(size_t)b * N + n];
   for (int i = t; i < ACC3_WARPS * K; i += blockDim.x) cntw[i] = 0;
   if (t == 0) next_task = 0;
   __syncthreads();
@@ -375,12 +374,15 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
     const int n = n0 + lane;
     const int l = n < r1 ? lab[n] : -1;
     const bool active = l >= 0;
+    const float iv = (active && norm_descs) ? inv_norm[(size_t)b * N + n] : 1.0f;
     const unsigned am = __ballot_sync(0xffffffffu, active);
     unsigned peers = 0; int rank = 0;
     if (active) {
       peers = __match_any_sync(am, l);
       rank = __popc(peers & ((1u << lane) - 1u));
-      order[start[l] + cntw[w * K + l] + rank] = n;
+      const int pos = start[l] + cntw[w * K + l] + rank;
+      ooff[pos] = n * D;
+      inv_s[pos] = iv;
     }
     __syncwarp();
     if (active && rank == 0) cntw[w * K + l] += __popc(peers);
@@ -401,19 +403,29 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
     const float4 c = colok ? __ldg(reinterpret_cast<const float4*>(centers + (size_t)k * D + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     if (colok) {
+      // The in-flight bytes live in registers (8 x 16 B per lane = 4 KB per warp; 4 CTAs x 8 warps -> 128 KB per SM),
+      // so the loop is kept lean: row offsets and 1/|x| were laid out in sorted order by the placement pass.
       constexpr int U = 8;
-      for (int i = s; i < e; i += U) {
-        float4 v[U]; float sc[U];
+      int i = s;
+      for (; i + U <= e; i += U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(xb + ooff[i + u]));
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int n = order[min(i + u, e - 1)];
-          sc[u] = inv[n];
-          v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)n * D));
+          const float sc = inv_s[i + u];
+          a.x += v[u].x * sc - c.x; a.y += v[u].y * sc - c.y; a.z += v[u].z * sc - c.z; a.w += v[u].w * sc - c.w;
         }
+      }
+      if (i < e) {                                           // tail: < U rows, same order
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) if (i + u < e) v[u] = __ldg(reinterpret_cast<const float4*>(xb + ooff[i + u]));
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (i + u < e) {
-            a.x += v[u].x * sc[u] - c.x; a.y += v[u].y * sc[u] - c.y; a.z += v[u].z * sc[u] - c.z; a.w += v[u].w * sc[u] - c.w;
+            const float sc = inv_s[i + u];
+            a.x += v[u].x * sc - c.x; a.y += v[u].y * sc - c.y; a.z += v[u].z * sc - c.z; a.w += v[u].w * sc - c.w;
           }
         }
       }
@@ -919,7 +931,7 @@ extern "C" int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, 
     return ANYLOC_ERR_WORKSPACE;
   }
   const size_t smem3 = acc3_smem_bytes(N, K);
-  const bool acc3 = vlad_version() >= 3 && smem3 <= 100 * 1024 && N < (1 << 30) / 4;
+  const bool acc3 = vlad_version() >= 3 && smem3 <= 100 * 1024 && (int64_t)N * D < (1ll << 31);
   if (acc3) { ab.done = w.take<int32_t>((size_t)B); ab.n_done = B; }
   ProfScope ps(PC_VLAD, st, 4.0 * ((double)B * N * D + (double)B * K * D + (double)K * D));
   int rc = launch_assign(feats, n_valid, N, (int64_t)R, D, K, centers, dist_mode, ab, labels, inv_norm, st);

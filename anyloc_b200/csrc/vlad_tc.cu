@@ -41,6 +41,7 @@ struct AssignParams {
   int32_t* labels; float* inv_norm;
   int32_t* amb_count; int32_t* amb_rows; uint32_t* amb_mask;
   int stages; int stage_bytes; int n_mma; int burst;
+  int diag;      // timing experiments only (tools/, results invalid): bit 0 = row-norm math off, bit 1 = MMAs off
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -131,10 +132,12 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           tc_fence_after();
           const uint32_t sbase = smem_u32(smem + stage * p.stage_bytes);
           const uint64_t a = make_desc(sbase), b = make_desc(sbase + A_BYTES);
+          if (!(p.diag & 2)) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adv = (uint64_t)((k * 32) >> 4);
-            umma<false>(d_tmem, a + adv, b + adv, idesc, (uint32_t)((kb | k) != 0));
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adv = (uint64_t)((k * 32) >> 4);
+              umma<false>(d_tmem, a + adv, b + adv, idesc, (uint32_t)((kb | k) != 0));
+            }
           }
           umma_commit(smem_u32(empty_bar + stage));
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -157,6 +160,7 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(smem_u32(full_bar + stage), phase);
         const uint8_t* rowp = smem + stage * p.stage_bytes + rt * 128;
+        if (!(p.diag & 1))
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ sw) << 4));
@@ -344,6 +348,11 @@ int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_
   p.stages = std::max(2, std::min(p.stages, std::max(2, num_k)));
   static int burst_env = -1;             // ANYLOC_VLAD_TMA_BURST: k-blocks issued back to back by the producer (A/B knob)
   if (burst_env < 0) { const char* e = getenv("ANYLOC_VLAD_TMA_BURST"); burst_env = e ? atoi(e) : 4; }
+  static int stages_env = -1, diag_env = -1;   // A/B and timing-experiment knobs (tools/ only)
+  if (stages_env < 0) { const char* e = getenv("ANYLOC_VLAD_STAGES"); stages_env = e ? atoi(e) : 0; }
+  if (diag_env < 0) { const char* e = getenv("ANYLOC_VLAD_DIAG"); diag_env = e ? atoi(e) : 0; }
+  if (stages_env >= 2) p.stages = std::min(p.stages, stages_env);
+  p.diag = diag_env;
   p.burst = std::max(1, std::min(burst_env, p.stages / 2));
   const size_t smem = (size_t)p.stages * p.stage_bytes + fixed;
   const int tiles = (int)((R + BM - 1) / BM);
