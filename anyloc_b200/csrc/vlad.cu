@@ -309,8 +309,11 @@ __global__ void __launch_bounds__(ACC3_WARPS * 32, 4)
 vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__ labels,
                         const float* __restrict__ inv_norm, const float* __restrict__ centers, int N, int D, int K,
                         int norm_descs, int intra_norm, float* vlad, float* partial_ss /* [B,K,nslices] */,
-                        int32_t* done /* [B], zero on entry */) {
+                        int32_t* done /* [B], zero on entry */, int32_t* reset_ctr /* nullable */) {
   extern __shared__ __align__(16) int sm3[];
+  // prepared-vocabulary calls: the work-list counter of the assignment stage (already consumed on this stream) is
+  // cleared here for the next call, so no launch is spent on it
+  if (reset_ctr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *reset_ctr = 0;
   int* ooff = sm3;                                          // [N] n * D of the rows, sorted by label (stable)
   int* lab = ooff + N;                                      // [N]
   float* inv_s = reinterpret_cast<float*>(lab + N);         // [N] 1/|x| in the same sorted order
@@ -811,7 +814,7 @@ size_t vlad_assign_tc_ws_bytes(int64_t R);
 int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_img, int64_t R, int D, int K,
                           const float* chat, const float* chat_tf32, const float* cbias, const float* cnorm,
                           const float* cdnorm, int32_t* labels, float* inv_norm, int32_t* amb_count, int32_t* amb_rows,
-                          uint32_t* amb_mask, cudaStream_t st);
+                          uint32_t* amb_mask, cudaStream_t st, int32_t* zero_ptr = nullptr, int zero_n = 0);
 }  // namespace anyloc
 
 // ANYLOC_VLAD=2 selects the v2 pipeline (coarse GEMM + full rescoring pass + shared-memory accumulate + normalise
@@ -844,7 +847,10 @@ struct AssignBufs {
 // FFMA kernel
 int launch_assign(const float* feats, const int32_t* n_valid, int N_per_img, int64_t R, int D, int K,
                   const float* centers, int dist_mode, const AssignBufs& ab, int32_t* labels, float* inv_norm,
-                  cudaStream_t st) {
+                  cudaStream_t st, bool prepared = false) {
+  if (prepared)      // c^, tf32 copy, bias, norms and a zero work-list counter already sit in ab (anyloc_vlad_prepare)
+    return vlad_assign_tc_launch(feats, n_valid, N_per_img, R, D, K, ab.chat, ab.chat_tf32, ab.cbias, ab.cnorm, ab.cdnorm,
+                                 labels, inv_norm, ab.amb_count, ab.amb_rows, ab.amb_mask, st, ab.done, ab.n_done);
   vlad_centre_prep_kernel<<<K, 256, 0, st>>>(centers, K, D, dist_mode, ab.chat, ab.cbias, ab.chat_tf32, ab.cnorm,
                                              ab.cdnorm, ab.amb_count, ab.amb_count ? 1 : 0, ab.done, ab.done ? ab.n_done : 0);
   ANYLOC_CHECK_LAUNCH();
@@ -907,10 +913,41 @@ extern "C" int anyloc_vlad_assign(const float* feats, const float* centers, int 
   return launch_assign(feats, nullptr, R, R, D, K, centers, dist_mode, ab, labels, nullptr, (cudaStream_t)stream);
 }
 
-extern "C" int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, const float* centers,
-                                    int B, int N, int D, int K, int dist_mode, int norm_descs,
-                                    int intra_norm, float* vlad, int32_t* labels_out, void* ws,
-                                    size_t ws_bytes, void* stream) {
+// Prepared vocabulary blob (anyloc_vlad_prepare): c^ [K,D] | tf32(c^) [K,D] | bias [K] | |c^| [K] | |c^ - tf32(c^)| [K] |
+// work-list counter.  Everything the per-call centre-prep launch would produce.
+struct PreparedView { float *chat, *chat_tf32, *cbias, *cnorm, *cdnorm; int32_t* amb_count; };
+static bool carve_prepared(void* blob, size_t bytes, int D, int K, PreparedView* pv) {
+  Workspace w(blob, bytes);
+  pv->chat = w.take<float>((size_t)K * D);
+  pv->chat_tf32 = w.take<float>((size_t)K * D);
+  pv->cbias = w.take<float>(K);
+  pv->cnorm = w.take<float>(K);
+  pv->cdnorm = w.take<float>(K);
+  pv->amb_count = w.take<int32_t>(64);
+  return pv->amb_count != nullptr;
+}
+
+extern "C" size_t anyloc_vlad_prepared_bytes(int D, int K) {
+  return 2 * align_up((size_t)K * D * 4, 256) + 3 * align_up((size_t)K * 4, 256) + 256;
+}
+
+extern "C" int anyloc_vlad_prepare(const float* centers, int D, int K, int dist_mode, void* prepared,
+                                   size_t prepared_bytes, void* stream) {
+  ANYLOC_REQUIRE(centers && prepared, "vlad_prepare: null pointer");
+  ANYLOC_REQUIRE(D > 0 && K > 0 && D % 4 == 0, "vlad_prepare: bad dims D=%d K=%d", D, K);
+  ANYLOC_REQUIRE(dist_mode == ANYLOC_DIST_COSINE || dist_mode == ANYLOC_DIST_EUCLIDEAN,
+                 "vlad_prepare: unknown dist_mode %d", dist_mode);
+  PreparedView pv;
+  if (!carve_prepared(prepared, prepared_bytes, D, K, &pv)) { set_error("vlad_prepare: blob too small"); return ANYLOC_ERR_WORKSPACE; }
+  vlad_centre_prep_kernel<<<K, 256, 0, (cudaStream_t)stream>>>(centers, K, D, dist_mode, pv.chat, pv.cbias, pv.chat_tf32,
+                                                               pv.cnorm, pv.cdnorm, pv.amb_count, 1, nullptr, 0);
+  ANYLOC_CHECK_LAUNCH();
+  return ANYLOC_OK;
+}
+
+static int vlad_generate_impl(const float* feats, const int32_t* n_valid, const float* centers, void* prepared,
+                              size_t prepared_bytes, int B, int N, int D, int K, int dist_mode, int norm_descs,
+                              int intra_norm, float* vlad, int32_t* labels_out, void* ws, size_t ws_bytes, void* stream) {
   ANYLOC_REQUIRE(feats && centers && vlad && ws, "vlad_generate: null pointer");
   ANYLOC_REQUIRE(B >= 0 && N >= 0 && D > 0 && K > 0, "vlad_generate: bad dims");
   ANYLOC_REQUIRE(D % 4 == 0, "vlad_generate: D=%d must be a multiple of 4", D);
@@ -933,8 +970,17 @@ extern "C" int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, 
   const size_t smem3 = acc3_smem_bytes(N, K);
   const bool acc3 = vlad_version() >= 3 && smem3 <= 100 * 1024 && (int64_t)N * D < (1ll << 31);
   if (acc3) { ab.done = w.take<int32_t>((size_t)B); ab.n_done = B; }
+  // prepared vocabulary: usable when this call takes the v3 assignment + accumulate3 route
+  PreparedView pv;
+  const bool use_prep = prepared && acc3 && ab.done && ab.amb_rows && ab.amb_mask && vlad_version() >= 3 &&
+                        carve_prepared(prepared, prepared_bytes, D, K, &pv) &&
+                        vlad_assign_tc_supported(feats, pv.chat_tf32, (int64_t)R, D, K);
+  if (use_prep) {
+    ab.chat = pv.chat; ab.chat_tf32 = pv.chat_tf32; ab.cbias = pv.cbias; ab.cnorm = pv.cnorm; ab.cdnorm = pv.cdnorm;
+    ab.amb_count = pv.amb_count;
+  }
   ProfScope ps(PC_VLAD, st, 4.0 * ((double)B * N * D + (double)B * K * D + (double)K * D));
-  int rc = launch_assign(feats, n_valid, N, (int64_t)R, D, K, centers, dist_mode, ab, labels, inv_norm, st);
+  int rc = launch_assign(feats, n_valid, N, (int64_t)R, D, K, centers, dist_mode, ab, labels, inv_norm, st, use_prep);
   if (rc) return rc;
   if (acc3 && ab.done) {
     static bool attr_set = false;
@@ -943,7 +989,8 @@ extern "C" int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, 
       attr_set = true;
     }
     vlad_accumulate3_kernel<<<dim3(nslices, B), ACC3_WARPS * 32, smem3, st>>>(feats, labels, inv_norm, centers, N, D, K,
-                                                                             norm_descs, intra_norm, vlad, partial, ab.done);
+                                                                             norm_descs, intra_norm, vlad, partial, ab.done,
+                                                                             use_prep ? ab.amb_count : nullptr);
     ANYLOC_CHECK_LAUNCH();
     if (labels_out)
       ANYLOC_CHECK_CUDA(cudaMemcpyAsync(labels_out, labels, R * 4, cudaMemcpyDeviceToDevice, st));
@@ -972,6 +1019,23 @@ extern "C" int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, 
   if (labels_out)
     ANYLOC_CHECK_CUDA(cudaMemcpyAsync(labels_out, labels, R * 4, cudaMemcpyDeviceToDevice, st));
   return ANYLOC_OK;
+}
+
+extern "C" int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, const float* centers,
+                                    int B, int N, int D, int K, int dist_mode, int norm_descs,
+                                    int intra_norm, float* vlad, int32_t* labels_out, void* ws,
+                                    size_t ws_bytes, void* stream) {
+  return vlad_generate_impl(feats, n_valid, centers, nullptr, 0, B, N, D, K, dist_mode, norm_descs, intra_norm, vlad,
+                            labels_out, ws, ws_bytes, stream);
+}
+
+extern "C" int anyloc_vlad_generate_prepared(const float* feats, const int32_t* n_valid, const float* centers,
+                                             void* prepared, size_t prepared_bytes, int B, int N, int D, int K,
+                                             int dist_mode, int norm_descs, int intra_norm, float* vlad,
+                                             int32_t* labels_out, void* ws, size_t ws_bytes, void* stream) {
+  ANYLOC_REQUIRE(prepared, "vlad_generate_prepared: null prepared blob");
+  return vlad_generate_impl(feats, n_valid, centers, prepared, prepared_bytes, B, N, D, K, dist_mode, norm_descs,
+                            intra_norm, vlad, labels_out, ws, ws_bytes, stream);
 }
 
 // Centres for F.cosine_similarity: c / max(|c|, 1e-8)

@@ -40,6 +40,7 @@ struct AssignParams {
   const float* cbias; const float* cnorm; const float* cdnorm;
   int32_t* labels; float* inv_norm;
   int32_t* amb_count; int32_t* amb_rows; uint32_t* amb_mask;
+  int32_t* zero_ptr; int zero_n;     // cleared here for a LATER launch on the stream (accumulate tickets), nullable
   int stages; int stage_bytes; int n_mma; int burst;
   int diag;      // timing experiments only (tools/, results invalid): bit 0 = row-norm math off, bit 1 = MMAs off
 };
@@ -78,6 +79,7 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                  ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int i = blockIdx.x * THREADS + threadIdx.x; i < p.zero_n; i += gridDim.x * THREADS) p.zero_ptr[i] = 0;
   for (int k = threadIdx.x; k < MAX_K; k += THREADS) {
     s_cbias[k] = k < p.K ? p.cbias[k] : 0.f;
     s_cnorm[k] = k < p.K ? p.cnorm[k] : 0.f;
@@ -235,9 +237,11 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         else if (cnt <= 1) p.labels[m] = first;          // cnt == 0 only with NaN scores: label 0 like the exact path
         else {
           const int idx = atomicAdd(p.amb_count, 1);
-          p.amb_rows[idx] = (int32_t)m;
+          if (idx >= 0 && idx < p.R) {                 // (a stale counter must never turn into a stray write)
+            p.amb_rows[idx] = (int32_t)m;
 #pragma unroll
-          for (int i = 0; i < MAX_K / 32; ++i) p.amb_mask[(size_t)idx * (MAX_K / 32) + i] = mask[i];
+            for (int i = 0; i < MAX_K / 32; ++i) p.amb_mask[(size_t)idx * (MAX_K / 32) + i] = mask[i];
+          }
         }
       }
     }
@@ -255,11 +259,11 @@ template <int MAXV>
 __global__ void __launch_bounds__(256)
 vlad_rescore_amb_kernel(const float* __restrict__ x, int D, const float* __restrict__ chat,
                         const float* __restrict__ cbias, const int32_t* amb_count, const int32_t* amb_rows,
-                        const uint32_t* amb_mask, int32_t* __restrict__ labels) {
+                        const uint32_t* amb_mask, int32_t* __restrict__ labels, int R) {
   const int lane = threadIdx.x & 31;
   const int gw = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int nw = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
-  const int n = __ldcg(amb_count);
+  const int n = min(__ldcg(amb_count), R);
   const int D4 = D >> 2;
   for (int i = gw; i < n; i += nw) {
     const int64_t row = __ldcg(amb_rows + i);
@@ -322,7 +326,7 @@ size_t vlad_assign_tc_ws_bytes(int64_t R) {
 int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_img, int64_t R, int D, int K,
                           const float* chat, const float* chat_tf32, const float* cbias, const float* cnorm,
                           const float* cdnorm, int32_t* labels, float* inv_norm, int32_t* amb_count, int32_t* amb_rows,
-                          uint32_t* amb_mask, cudaStream_t st) {
+                          uint32_t* amb_mask, cudaStream_t st, int32_t* zero_ptr, int zero_n) {
   using namespace vtc;
   CUtensorMap mx, mc;
   int rc;
@@ -333,6 +337,7 @@ int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_
   p.n_valid = n_valid; p.n_per_img = n_per_img; p.R = (int)R; p.D = D; p.K = K;
   p.cbias = cbias; p.cnorm = cnorm; p.cdnorm = cdnorm; p.labels = labels; p.inv_norm = inv_norm;
   p.amb_count = amb_count; p.amb_rows = amb_rows; p.amb_mask = amb_mask;
+  p.zero_ptr = zero_ptr; p.zero_n = zero_ptr ? zero_n : 0;
   p.n_mma = n_mma;
   p.stage_bytes = A_BYTES + n_mma * 128;
   static int max_smem = 0;
@@ -361,11 +366,11 @@ int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_
   ANYLOC_CHECK_LAUNCH();
   const int blocks = (int)std::min<int64_t>((R + 7) / 8, (int64_t)device_sm_count() * 4);
   if (D <= 512)
-    vlad_rescore_amb_kernel<4><<<blocks, 256, 0, st>>>(feats, D, chat, cbias, amb_count, amb_rows, amb_mask, labels);
+    vlad_rescore_amb_kernel<4><<<blocks, 256, 0, st>>>(feats, D, chat, cbias, amb_count, amb_rows, amb_mask, labels, (int)R);
   else if (D <= 1024)
-    vlad_rescore_amb_kernel<8><<<blocks, 256, 0, st>>>(feats, D, chat, cbias, amb_count, amb_rows, amb_mask, labels);
+    vlad_rescore_amb_kernel<8><<<blocks, 256, 0, st>>>(feats, D, chat, cbias, amb_count, amb_rows, amb_mask, labels, (int)R);
   else
-    vlad_rescore_amb_kernel<16><<<blocks, 256, 0, st>>>(feats, D, chat, cbias, amb_count, amb_rows, amb_mask, labels);
+    vlad_rescore_amb_kernel<16><<<blocks, 256, 0, st>>>(feats, D, chat, cbias, amb_count, amb_rows, amb_mask, labels, (int)R);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }

@@ -364,6 +364,22 @@ class VLAD:
             self._centers_dev = {key: _as_device_f32(self.c_centers, dev)}
         return self._centers_dev[key]
 
+    def _prepared_on(self, dev, centers):
+        """Device blob of anyloc_vlad_prepare for the current vocabulary (recomputed when c_centers is replaced or
+        modified in place, or the distance mode changes)."""
+        cc = self.c_centers
+        key = (dev.index, id(cc), getattr(cc, "_version", None), self.mode, centers.data_ptr())
+        cache = getattr(self, "_prepared_dev", None)
+        if cache is None or cache[0] != key:
+            lib = _lib.load()
+            K, D = centers.shape
+            blob = torch.empty(lib.anyloc_vlad_prepared_bytes(D, K), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.anyloc_vlad_prepare(_lib.ptr(centers), D, K, _lib.DIST[self.mode], _lib.ptr(blob),
+                                                   blob.numel(), _lib.stream_ptr()), "anyloc_vlad_prepare")
+            self._prepared_dev = cache = (key, blob)
+        return cache[1]
+
     def _run(self, feats, n_valid, dev, want_labels=False):
         """feats [B,N,D] device fp32; n_valid [B] int32 device or None -> ([B,K*D], labels|None)
         (soft mode: the [B,N,K] assignment probabilities take the place of the labels)."""
@@ -389,11 +405,13 @@ class VLAD:
             return out, assign
         with torch.cuda.device(dev):
             ws = _lib.workspaces.get(dev, lib.anyloc_vlad_workspace_bytes(B, N, D, K), "vlad")
-            rc = lib.anyloc_vlad_generate(_lib.ptr(feats), _lib.ptr(n_valid), _lib.ptr(centers), B, N, D, K,
-                                          _lib.DIST[self.mode], int(bool(self.norm_descs)),
-                                          int(bool(self.intra_norm)), _lib.ptr(out), _lib.ptr(labels),
-                                          _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
-        _lib.check(rc, "anyloc_vlad_generate")
+            prep = self._prepared_on(dev, centers)
+            rc = lib.anyloc_vlad_generate_prepared(_lib.ptr(feats), _lib.ptr(n_valid), _lib.ptr(centers), _lib.ptr(prep),
+                                                   prep.numel(), B, N, D, K, _lib.DIST[self.mode],
+                                                   int(bool(self.norm_descs)), int(bool(self.intra_norm)),
+                                                   _lib.ptr(out), _lib.ptr(labels), _lib.ptr(ws), ws.numel(),
+                                                   _lib.stream_ptr())
+        _lib.check(rc, "anyloc_vlad_generate_prepared")
         return out, labels
 
     # -- descriptors (utilities.py:819-926)

@@ -291,8 +291,14 @@ def run_ours(args, wl):
     vroof = None
     if v_n:
         gbs = v_bytes / (v_ms / 1e3) / 1e9
-        vroof = {"kernel": "vlad assign+accumulate+normalise (4 launches)", "bound": "hbm", "achieved": gbs,
-                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+        vroof = {"kernel": "VLAD v3: vlad_assign_tc_kernel (TMA + tcgen05 coarse scores + row norms) -> "
+                           "vlad_rescore_amb_kernel (ambiguous rows only) -> vlad_accumulate3_kernel (+ fused "
+                           "normalisation); prepared vocabulary, 3 launches",
+                 "bound": "hbm", "achieved": gbs,
+                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                 # ncu --set full, c2 shape (profiles/r01_vlad_v3.md): DRAM read+write of the three launches
+                 "traffic": 235.0e6 if args.workload == "c2" else None,
+                 "algorithmic_bytes_per_launch_group": v_bytes / v_n,
                  "avg_launch_ms": v_ms / v_n, "share_of_step": v_ms / ms_total}
     shares = {c: round(prof[c][0] / ms_total, 4) for c in prof if prof[c][1]}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

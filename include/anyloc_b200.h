@@ -93,6 +93,19 @@ size_t anyloc_vlad_workspace_bytes(int B, int N, int D, int K);
 int anyloc_vlad_generate(const float* feats, const int32_t* n_valid, const float* centers,
                          int B, int N, int D, int K, int dist_mode, int norm_descs, int intra_norm,
                          float* vlad, int32_t* labels, void* ws, size_t ws_bytes, void* stream);
+/* Prepared vocabulary: VLAD.generate / generate_multi are called once per image (batch) with the SAME c_centers
+ * (utilities.py:216-217 of scripts/dino_v2_vlad.py fits once, then :233-237 generates for every image), so the
+ * centre normalisation c/(|c|+1e-8) of fpk cos_sim, its tf32 copy and norms can be computed once.
+ * anyloc_vlad_prepare fills a caller-owned device blob (anyloc_vlad_prepared_bytes); anyloc_vlad_generate_prepared
+ * is anyloc_vlad_generate minus the per-call centre-prep launch.  The blob also holds a work-list counter that each
+ * call leaves at zero: calls sharing a blob must be stream-ordered, and the blob must be re-prepared whenever the
+ * centres (or dist_mode) change.  Results are bitwise identical to anyloc_vlad_generate. */
+size_t anyloc_vlad_prepared_bytes(int D, int K);
+int anyloc_vlad_prepare(const float* centers, int D, int K, int dist_mode, void* prepared, size_t prepared_bytes,
+                        void* stream);
+int anyloc_vlad_generate_prepared(const float* feats, const int32_t* n_valid, const float* centers, void* prepared,
+                                  size_t prepared_bytes, int B, int N, int D, int K, int dist_mode, int norm_descs,
+                                  int intra_norm, float* vlad, int32_t* labels, void* ws, size_t ws_bytes, void* stream);
 /* Soft assignment (vlad_mode="soft", utilities.py:862-887):
  *   a[q,k] = softmax_k(soft_temp * cos(x_q, c_k))      (F.cosine_similarity :870-875, norms clamped at 1e-8)
  *   V_k    = sum_q a[q,k] * sum_c (x^_q - c_c)          (the reference weights the residuals to ALL centres by

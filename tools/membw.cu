@@ -43,6 +43,27 @@ __global__ void __launch_bounds__(256) slice512_kernel(const float* __restrict__
   if (acc == 12345.678f) out[0] = acc;
 }
 
+// slice512 with an indirection: rows visited in the order perm[] (per image), optionally rotated per slice
+template <int U>
+__global__ void __launch_bounds__(256) slice512_perm_kernel(const float* __restrict__ x, const int* __restrict__ perm, int N, int D,
+                                                            int rotate, float* out) {
+  extern __shared__ int dyn[];             // only to limit the CTAs per SM
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float* xb = x + (size_t)blockIdx.y * N * D + blockIdx.x * 128 + lane * 4;
+  const int* pb = perm + (size_t)blockIdx.y * N;
+  const int rot = rotate ? (int)(((long long)blockIdx.x * N) / gridDim.x) : 0;
+  float acc = 0.f;
+  for (int n0 = w * U; n0 < N; n0 += 8 * U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { int n = n0 + u; n = n < N ? n : N - 1; n += rot; n = n >= N ? n - N : n;
+      v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)pb[n] * D)); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc += v[u].x + v[u].y + v[u].z + v[u].w;
+  }
+  if (acc == 12345.678f) out[0] = acc + dyn[0];
+}
+
 // CTA = (J*128-column slice, image): each warp reads J*512 contiguous bytes of a row (J loads per lane), U rows in flight
 template <int J, int U>
 __global__ void __launch_bounds__(256) slicew_kernel(const float* __restrict__ x, int N, int D, float* out) {
@@ -120,6 +141,33 @@ int main() {
   rep("slice512 U=4", time_it([&] { slice512_kernel<4><<<dim3(D / 128, B), 256>>>(x, N, D, out); }), bytes);
   rep("slice512 U=8", time_it([&] { slice512_kernel<8><<<dim3(D / 128, B), 256>>>(x, N, D, out); }), bytes);
   rep("slice512 U=16", time_it([&] { slice512_kernel<16><<<dim3(D / 128, B), 256>>>(x, N, D, out); }), bytes);
+  {
+    // identity, label-sorted (32 clusters, random labels), and fully random row orders
+    int* perm; CK(cudaMalloc(&perm, (size_t)B * N * 4));
+    int* h = (int*)malloc((size_t)B * N * 4);
+    auto run = [&](const char* name, int rotate, size_t dsm) {
+      CK(cudaMemcpy(perm, h, (size_t)B * N * 4, cudaMemcpyHostToDevice));
+      CK(cudaFuncSetAttribute(slice512_perm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      rep(name, time_it([&] { slice512_perm_kernel<4><<<dim3(D / 128, B), 256, dsm>>>(x, perm, N, D, rotate, out); }), bytes);
+    };
+    for (int b = 0; b < B; ++b) for (int n = 0; n < N; ++n) h[b * N + n] = n;
+    run("perm identity U=4", 0, 0);
+    run("perm identity, 3 CTAs/SM", 0, 70 * 1024);
+    run("perm identity, 2 CTAs/SM", 0, 100 * 1024);
+    run("perm identity, rotated/slice", 1, 0);
+    srand(1);
+    for (int b = 0; b < B; ++b) {          // stable sort by random label (32 clusters)
+      int lab[529], pos = 0;
+      for (int n = 0; n < N; ++n) lab[n] = rand() % 32;
+      for (int k = 0; k < 32; ++k) for (int n = 0; n < N; ++n) if (lab[n] == k) h[b * N + pos++] = n;
+    }
+    run("perm label-sorted", 0, 0);
+    run("perm label-sorted, 3 CTAs/SM", 0, 70 * 1024);
+    run("perm label-sorted, rotated", 1, 0);
+    for (int b = 0; b < B; ++b) for (int n = N - 1; n > 0; --n) { int j = rand() % (n + 1); int t = h[b * N + n]; h[b * N + n] = h[b * N + j]; h[b * N + j] = t; }
+    run("perm random", 0, 0);
+    run("perm random, rotated", 1, 0);
+  }
   rep("slice 2 KB (J=4) U=2", time_it([&] { slicew_kernel<4, 2><<<dim3(D / 512, B), 256>>>(x, N, D, out); }), bytes);
   rep("slice 2 KB (J=4) U=4", time_it([&] { slicew_kernel<4, 4><<<dim3(D / 512, B), 256>>>(x, N, D, out); }), bytes);
   rep("row 6 KB (J=12) U=1", time_it([&] { slicew_kernel<12, 1><<<dim3(1, B), 256>>>(x, N, D, out); }), bytes);
