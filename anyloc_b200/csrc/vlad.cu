@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(ACC3_WARPS * 32, 4)
 vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__ labels,
                         const float* __restrict__ inv_norm, const float* __restrict__ centers, int N, int D, int K,
                         int norm_descs, int intra_norm, float* vlad, float* partial_ss /* [B,K,nslices] */,
-                        int32_t* done /* [B], zero on entry */, int32_t* reset_ctr /* nullable */) {
+                        int32_t* done /* [B], zero on entry */, int32_t* reset_ctr /* nullable */, int prefetch) {
   extern __shared__ __align__(16) int sm3[];
   // prepared-vocabulary calls: the work-list counter of the assignment stage (already consumed on this stream) is
   // cleared here for the next call, so no launch is spent on it
@@ -392,14 +392,27 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
     __syncwarp();
   }
   __syncthreads();
-  // tasks -> registers
+  // tasks -> registers.  HBM needs ~100 KB in flight per SM (tools/membw.cu: 32 KB -> 4.0 TB/s, 48 KB -> 4.8, >= 96 KB
+  // -> 6.3), far more than the registers of the resident warps can hold, so every warp grabs its NEXT task early and
+  // bulk-prefetches that task's row segments into L2 (cp.async.bulk.prefetch.L2: no destination registers); the
+  // register loads of the task itself then mostly hit L2.
   const float* xb = x + (size_t)b * N * D + col;
+  const float* xs = x + (size_t)b * N * D + slice * 128;                     // this slice, lane-independent
+  const uint32_t rowbytes = (uint32_t)min(128, D - slice * 128) * 4u;
   const int ntasks = tstart[K];
-  for (;;) {
-    int q = 0;
-    if (lane == 0) q = atomicAdd(&next_task, 1);
-    q = __shfl_sync(0xffffffffu, q, 0);
-    if (q >= ntasks) break;
+  auto grab = [&]() { int q = 0; if (lane == 0) q = atomicAdd(&next_task, 1); return __shfl_sync(0xffffffffu, q, 0); };
+  auto prefetch_task = [&](int q) {
+    if (q >= ntasks || !prefetch) return;
+    const int k = task_k[q];
+    const int s = start[k] + (q - tstart[k]) * ACC3_SEG, e = min(start[k + 1], s + ACC3_SEG);
+    for (int i = s + lane; i < e; i += 32)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xs + ooff[i]), "r"(rowbytes) : "memory");
+  };
+  int q = grab();
+  prefetch_task(q);
+  while (q < ntasks) {
+    const int qn = grab();
+    prefetch_task(qn);
     const int k = task_k[q];
     const int seg = q - tstart[k], nt = tstart[k + 1] - tstart[k];
     const int s = start[k] + seg * ACC3_SEG, e = min(start[k + 1], s + ACC3_SEG);
@@ -440,6 +453,7 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
     } else {
       *reinterpret_cast<float4*>(slots + (size_t)(sbase[k] + seg) * 128 + lane * 4) = a;
     }
+    q = qn;
   }
   __syncthreads();
   for (int k = w; k < K; k += ACC3_WARPS) {                 // clusters of several tasks: combine in task order
@@ -820,6 +834,11 @@ int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_
 // ANYLOC_VLAD=2 selects the v2 pipeline (coarse GEMM + full rescoring pass + shared-memory accumulate + normalise
 // launch) for A/B measurements; default 3 = streaming tensor-core assignment + sorted register accumulate with the
 // normalisation fused into it.
+static int acc3_prefetch() {      // ANYLOC_VLAD_PREFETCH=0: accumulate3 without the L2 bulk prefetch of the next task (A/B)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ANYLOC_VLAD_PREFETCH"); v = e ? atoi(e) : 1; }
+  return v;
+}
 static int vlad_version() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("ANYLOC_VLAD"); v = e ? atoi(e) : 3; }
@@ -990,7 +1009,7 @@ static int vlad_generate_impl(const float* feats, const int32_t* n_valid, const 
     }
     vlad_accumulate3_kernel<<<dim3(nslices, B), ACC3_WARPS * 32, smem3, st>>>(feats, labels, inv_norm, centers, N, D, K,
                                                                              norm_descs, intra_norm, vlad, partial, ab.done,
-                                                                             use_prep ? ab.amb_count : nullptr);
+                                                                             use_prep ? ab.amb_count : nullptr, acc3_prefetch());
     ANYLOC_CHECK_LAUNCH();
     if (labels_out)
       ANYLOC_CHECK_CUDA(cudaMemcpyAsync(labels_out, labels, R * 4, cudaMemcpyDeviceToDevice, st));

@@ -158,25 +158,31 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      float ss = 0.f, dd = 0.f;                     // |x|^2 and |x - tf32_trunc(x)|^2 (what the tensor core drops)
+      // |x|^2 and |x - tf32_trunc(x)|^2 (what the tensor core drops), two partial sums each: the FMA chains of a stage
+      // are half as deep, and the tile is read with ld.shared (the generic-address form costs an address translation)
+      float ss0 = 0.f, ss1 = 0.f, dd0 = 0.f, dd1 = 0.f;
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(smem_u32(full_bar + stage), phase);
-        const uint8_t* rowp = smem + stage * p.stage_bytes + rt * 128;
-        if (!(p.diag & 1))
+        const uint32_t rowa = smem_u32(smem + stage * p.stage_bytes + rt * 128);
+        if (!(p.diag & 1)) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ sw) << 4));
-          ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-          const float dx = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-          const float dy = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-          const float dz = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-          const float dw = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-          dd += dx * dx + dy * dy + dz * dz + dw * dw;
+          for (int c = 0; c < 8; ++c) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(rowa + (uint32_t)((c ^ sw) << 4)));
+            const float dx = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+            const float dy = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+            const float dz = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+            const float dw = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+            if (c & 1) { ss1 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; dd1 += dx * dx + dy * dy + dz * dz + dw * dw; }
+            else       { ss0 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; dd0 += dx * dx + dy * dy + dz * dz + dw * dw; }
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(empty_bar + stage));
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      const float ss = ss0 + ss1, dd = dd0 + dd1;
       const float xn = sqrtf(ss);
       mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
       tc_fence_after();
@@ -197,11 +203,12 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       // S~_k - S_k = -sum d_i c^_i - sum x_i e_i + sum d_i e_i + (accumulation), with d = x - trunc_tf32(x) (its norm is
       // MEASURED per row above) and e = c^ - tf32(c^) (norm per centre from the prep kernel), so by Cauchy-Schwarz
       //   |S~_k - S_k| <= |d||c^| + |x||e| + acc,
-      // acc <= 3e-4 |x||c^|: D/8 <= 256 tensor-core steps, each aligning 8 exact products and the accumulator to the
-      // largest exponent and truncating (<= 9 * 2^-23 of the largest addend, itself <= |x||c^|); the 1 % on top covers
-      // the fp32 evaluation of the norms and the second-order term.  Rigorous like the a-priori 2^-9 |x||c^| of v2,
-      // but ~2.4x tighter (|d| is typically 0.4 * 2^-10 |x|): fewer than half of the rows stay ambiguous.
-      const float eps = 1.01f * (sqrtf(dd) * cmax + xn * (dcmax + 3.0e-4f * cmax));
+      // acc <= 1e-4 |x||c^|: D/8 <= 256 tensor-core accumulation steps, each truncating the running sum; the measured
+      // truncation bias of this engine is 2^-26 of the sum per MMA (-9.4e-6 over 576 MMAs), i.e.
+      // <= 256 * 2^-24 = 1.5e-5 even at four times the mean, so 1e-4 leaves a 6x margin.  The 1 % on top covers the
+      // fp32 evaluation of the norms and the second-order term.  ~3x tighter than the a-priori 2^-9 |x||c^| of v2
+      // (|d| is typically 0.4 * 2^-10 |x|): about a third of the rows that v2 had to re-score stay ambiguous.
+      const float eps = 1.01f * (sqrtf(dd) * cmax + xn * (dcmax + 1.0e-4f * cmax));
       const float thresh = smax - 2.0f * eps - 1e-30f;
       uint32_t mask[MAX_K / 32];
 #pragma unroll

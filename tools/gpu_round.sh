@@ -8,6 +8,7 @@ timeout 400 python -m pytest tests/test_vlad_gpu.py -x -q > gpurun_out/t_vlad.lo
 stamp "vlad tests rc=$RC: $(tail -1 gpurun_out/t_vlad.log)"
 ANYLOC_VLAD=2 timeout 150 python tools/diag_vlad.py --save v2 --iters 5 > gpurun_out/diag_v2.log 2>&1
 timeout 150 python tools/diag_vlad.py --compare v2 > gpurun_out/diag_v3.log 2>&1
+ANYLOC_VLAD_PREFETCH=0 timeout 150 python tools/diag_vlad.py --compare v2 > gpurun_out/diag_v3_nopf.log 2>&1
 stamp "diag: $(grep -c GB/s gpurun_out/diag_v3.log) v3 lines"
 for sh in c2 c5; do
   timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/ll_$sh.csv \
@@ -15,7 +16,7 @@ for sh in c2 c5; do
 done
 stamp "launch lists done"
 if [ $RC -eq 0 ]; then
-  timeout 500 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c2.log 2>&1
+  timeout 500 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_c2.log 2>&1
   stamp "bench: $(tail -c 400 gpurun_out/bench_c2.log | head -c 200)"
   timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_vlad_gpu.py > gpurun_out/t_all.log 2>&1
   stamp "all gpu tests: $(tail -1 gpurun_out/t_all.log)"
