@@ -14,6 +14,7 @@
 // (The v1 FFMA assignment kernel is kept for K > 256 / D > 2048 and as the k-means assignment step.)
 #include <stdlib.h>
 #include <algorithm>
+#include <vector>
 #include "epilogue.cuh"
 
 namespace anyloc {
@@ -309,7 +310,15 @@ __global__ void __launch_bounds__(ACC3_WARPS * 32, 4)
 vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__ labels,
                         const float* __restrict__ inv_norm, const float* __restrict__ centers, int N, int D, int K,
                         int norm_descs, int intra_norm, float* vlad, float* partial_ss /* [B,K,nslices] */,
-                        int32_t* done /* [B], zero on entry */, int32_t* reset_ctr /* nullable */, int prefetch) {
+                        int32_t* done /* [B], zero on entry */, int32_t* reset_ctr /* nullable */, int prefetch,
+                        unsigned long long* dbg /* ANYLOC_VLAD_TIMELINE only: 8 ns stamps per CTA, nullable */) {
+  auto stamp = [&](int i) {
+    if (dbg && threadIdx.x == 0) {
+      unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + i] = t;
+    }
+  };
+  stamp(0);
   extern __shared__ __align__(16) int sm3[];
   // prepared-vocabulary calls: the work-list counter of the assignment stage (already consumed on this stream) is
   // cleared here for the next call, so no launch is spent on it
@@ -338,6 +347,7 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
   for (int i = t; i < ACC3_WARPS * K; i += blockDim.x) cntw[i] = 0;
   if (t == 0) next_task = 0;
   __syncthreads();
+  stamp(1);
   // per-warp histograms over contiguous row chunks
   const int chunk = (((N + ACC3_WARPS - 1) / ACC3_WARPS) + 31) & ~31;
   const int r0 = min(N, w * chunk), r1 = min(N, r0 + chunk);
@@ -392,6 +402,7 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
     __syncwarp();
   }
   __syncthreads();
+  stamp(2);
   // tasks -> registers.  HBM needs ~100 KB in flight per SM (tools/membw.cu: 32 KB -> 4.0 TB/s, 48 KB -> 4.8, >= 96 KB
   // -> 6.3), far more than the registers of the resident warps can hold, so every warp grabs its NEXT task early and
   // bulk-prefetches that task's row segments into L2 (cp.async.bulk.prefetch.L2: no destination registers); the
@@ -456,6 +467,7 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
     q = qn;
   }
   __syncthreads();
+  stamp(3);
   for (int k = w; k < K; k += ACC3_WARPS) {                 // clusters of several tasks: combine in task order
     const int nt = tstart[k + 1] - tstart[k];
     if (nt <= 1) continue;
@@ -474,6 +486,7 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
   __syncthreads();
   if (t == 0) s_last = (atomicAdd(&done[b], 1) == nslices - 1);
   __syncthreads();
+  stamp(4);
   if (!s_last) return;
   // ---- last CTA of this image: intra- and global normalisation (same arithmetic as vlad_normalize_kernel)
   __threadfence();
@@ -516,6 +529,8 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
       }
     }
   }
+  __syncthreads();
+  stamp(5);
 }
 
 // ------------------------------------------------------------------ accumulate
@@ -1007,10 +1022,33 @@ static int vlad_generate_impl(const float* feats, const int32_t* n_valid, const 
       ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(vlad_accumulate3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       attr_set = true;
     }
+    static int timeline = -1;          // ANYLOC_VLAD_TIMELINE=1 (tools only): per-CTA phase stamps, summary on stderr
+    if (timeline < 0) { const char* e = getenv("ANYLOC_VLAD_TIMELINE"); timeline = e ? atoi(e) : 0; }
+    unsigned long long* dbg = nullptr;
+    const size_t nctas = (size_t)nslices * B;
+    if (timeline) { ANYLOC_CHECK_CUDA(cudaMalloc(&dbg, nctas * 64)); ANYLOC_CHECK_CUDA(cudaMemsetAsync(dbg, 0, nctas * 64, st)); }
     vlad_accumulate3_kernel<<<dim3(nslices, B), ACC3_WARPS * 32, smem3, st>>>(feats, labels, inv_norm, centers, N, D, K,
                                                                              norm_descs, intra_norm, vlad, partial, ab.done,
-                                                                             use_prep ? ab.amb_count : nullptr, acc3_prefetch());
+                                                                             use_prep ? ab.amb_count : nullptr, acc3_prefetch(), dbg);
     ANYLOC_CHECK_LAUNCH();
+    if (timeline) {
+      std::vector<unsigned long long> h(nctas * 8);
+      ANYLOC_CHECK_CUDA(cudaStreamSynchronize(st));
+      ANYLOC_CHECK_CUDA(cudaMemcpy(h.data(), dbg, nctas * 64, cudaMemcpyDeviceToHost));
+      cudaFree(dbg);
+      unsigned long long t0 = ~0ull, t_end = 0;
+      for (size_t c = 0; c < nctas; ++c) t0 = std::min(t0, h[c * 8]);
+      double sum[6] = {0}, mx[6] = {0}; size_t nlast = 0;
+      for (size_t c = 0; c < nctas; ++c) {
+        for (int i = 0; i < 5; ++i) { double v = (double)(h[c * 8 + i] - t0) * 1e-3; sum[i] += v; mx[i] = std::max(mx[i], v); }
+        if (h[c * 8 + 5]) { double v = (double)(h[c * 8 + 5] - t0) * 1e-3; sum[5] += v; mx[5] = std::max(mx[5], v); ++nlast; }
+        t_end = std::max(t_end, std::max(h[c * 8 + 4], h[c * 8 + 5]));
+      }
+      fprintf(stderr, "[accumulate3 timeline, us since first CTA start; mean / max over %zu CTAs] start %.1f/%.1f  labels-loaded %.1f/%.1f  "
+              "sorted %.1f/%.1f  tasks-done %.1f/%.1f  ticket %.1f/%.1f  normalised(%zu CTAs) %.1f/%.1f  kernel-end %.1f\n",
+              nctas, sum[0] / nctas, mx[0], sum[1] / nctas, mx[1], sum[2] / nctas, mx[2], sum[3] / nctas, mx[3], sum[4] / nctas, mx[4],
+              nlast, nlast ? sum[5] / nlast : 0.0, mx[5], (double)(t_end - t0) * 1e-3);
+    }
     if (labels_out)
       ANYLOC_CHECK_CUDA(cudaMemcpyAsync(labels_out, labels, R * 4, cudaMemcpyDeviceToDevice, st));
     return ANYLOC_OK;
