@@ -303,7 +303,7 @@ static inline int acc3_max_tasks(int N, int K) { return N / ACC3_SEG + K + 1; }
 __device__ __forceinline__ int acc3_max_tasks_dev(int N, int K) { return N / ACC3_SEG + K + 1; }
 static inline int acc3_max_slots(int N) { return 2 * (N / ACC3_SEG) + 2; }
 static inline size_t acc3_smem_bytes(int N, int K) {
-  return ((size_t)3 * N + 3 * (size_t)(K + 1) + (size_t)ACC3_WARPS * K + 2 * (size_t)K + acc3_max_tasks(N, K) + 4) * 4 +
+  return ((size_t)4 * N + 3 * (size_t)(K + 1) + (size_t)ACC3_WARPS * K + 2 * (size_t)K + acc3_max_tasks(N, K) + 4) * 4 +
          (size_t)acc3_max_slots(N) * 512;
 }
 __global__ void __launch_bounds__(ACC3_WARPS * 32, 4)
@@ -333,8 +333,9 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
   float* kss = reinterpret_cast<float*>(cntw + ACC3_WARPS * K);   // [K]
   float* ksq = kss + K;                                     // [K]
   int* task_k = reinterpret_cast<int*>(ksq + K);            // [max_tasks]
+  float* inv = reinterpret_cast<float*>(task_k + acc3_max_tasks_dev(N, K));   // [N] 1/|x| in row order (prologue only)
   float* slots = reinterpret_cast<float*>(sm3) +
-                 (((size_t)3 * N + 3 * (size_t)(K + 1) + (size_t)ACC3_WARPS * K + 2 * (size_t)K + acc3_max_tasks_dev(N, K) + 3) & ~(size_t)3);
+                 (((size_t)4 * N + 3 * (size_t)(K + 1) + (size_t)ACC3_WARPS * K + 2 * (size_t)K + acc3_max_tasks_dev(N, K) + 3) & ~(size_t)3);
   __shared__ int next_task, s_last;
   __shared__ float s_gnorm;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -343,7 +344,10 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
   const int b = (int)gridDim.y - 1 - (int)blockIdx.y, slice = blockIdx.x, nslices = gridDim.x;
   const int col = slice * 128 + lane * 4;
   const bool colok = col < D;                               // D % 4 == 0
-  for (int n = t; n < N; n += blockDim.x) lab[n] = labels[(size_t)b * N + n];
+  for (int n = t; n < N; n += blockDim.x) {
+    lab[n] = labels[(size_t)b * N + n];
+    inv[n] = norm_descs ? inv_norm[(size_t)b * N + n] : 1.0f;
+  }
   for (int i = t; i < ACC3_WARPS * K; i += blockDim.x) cntw[i] = 0;
   if (t == 0) next_task = 0;
   __syncthreads();
@@ -387,7 +391,7 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
     const int n = n0 + lane;
     const int l = n < r1 ? lab[n] : -1;
     const bool active = l >= 0;
-    const float iv = (active && norm_descs) ? inv_norm[(size_t)b * N + n] : 1.0f;
+    const float iv = active ? inv[n] : 1.0f;
     const unsigned am = __ballot_sync(0xffffffffu, active);
     unsigned peers = 0; int rank = 0;
     if (active) {
@@ -482,9 +486,12 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
   }
   __syncthreads();
   for (int k = t; k < K; k += blockDim.x) partial_ss[((size_t)b * K + k) * nslices + slice] = kss[k];
-  __threadfence();
   __syncthreads();
-  if (t == 0) s_last = (atomicAdd(&done[b], 1) == nslices - 1);
+  if (t == 0) {
+    __threadfence();      // cumulative: orders every write the barrier above made visible to this thread (the pattern of
+                          // cooperative-groups grid sync), instead of 256 per-thread fences
+    s_last = (atomicAdd(&done[b], 1) == nslices - 1);
+  }
   __syncthreads();
   stamp(4);
   if (wait_all) {

@@ -274,6 +274,10 @@ vlad_rescore_amb_kernel(const float* __restrict__ x, int D, const float* __restr
   const int D4 = D >> 2;
   for (int i = gw; i < n; i += nw) {
     const int64_t row = __ldcg(amb_rows + i);
+    if (lane == 0 && i + nw < n) {        // the warp's next row -> L2 while this one is being re-scored
+      const int64_t nrow = __ldcg(amb_rows + i + nw);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + nrow * (int64_t)D), "r"((uint32_t)D * 4u) : "memory");
+    }
     const float4* xr = reinterpret_cast<const float4*>(x + row * (int64_t)D);
     float4 v[MAXV];
 #pragma unroll
