@@ -1,19 +1,18 @@
 #!/bin/bash
-# One GPU session: VLAD parity + A/B timing + timeline + launch lists.
+# Final GPU session of the round: whole GPU suite, bench line, launch list of the bench step, ncu full capture of the VLAD kernels.
 mkdir -p gpurun_out
 T0=$(date +%s)
 stamp() { echo "[$(( $(date +%s) - T0 )) s] $*" | tee -a gpurun_out/round_steps.log; }
 : > gpurun_out/round_steps.log
-timeout 400 python -m pytest tests/test_vlad_gpu.py -x -q > gpurun_out/t_vlad.log 2>&1; RC=$?
-stamp "vlad tests rc=$RC: $(tail -1 gpurun_out/t_vlad.log)"
-ANYLOC_VLAD=2 timeout 150 python tools/diag_vlad.py --save v2 --iters 5 > gpurun_out/diag_v2.log 2>&1
-timeout 150 python tools/diag_vlad.py --compare v2 > gpurun_out/diag_v3.log 2>&1
-
-ANYLOC_VLAD_TIMELINE=1 timeout 150 python tools/diag_vlad.py --iters 1 2>&1 | grep timeline | awk 'NR%5==1' > gpurun_out/timeline.log
-stamp "diag: $(grep -c GB/s gpurun_out/diag_v3.log) v3 lines"
-for sh in c2 c5; do
-  timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/ll_$sh.csv \
-    python tools/diag_vlad.py --iters 2 --shape $sh > gpurun_out/ll_$sh.log 2>&1
-done
-stamp "launch lists done"
+timeout 110 python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1
+stamp "all gpu tests: $(tail -1 gpurun_out/t_all.log)"
+timeout 120 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_c2.log 2>&1
+stamp "bench: $(tail -c 300 gpurun_out/bench_c2.log | head -c 150)"
+timeout 45 ncu --set full --clock-control none --import-source on -k regex:vlad_ -c 3 -f -o gpurun_out/prof_vlad3_final_c2 \
+  python tools/diag_vlad.py --shape c2 --iters 1 > gpurun_out/ncu_full_c2.log 2>&1
+ncu -i gpurun_out/prof_vlad3_final_c2.ncu-rep --page raw --csv > gpurun_out/prof_vlad3_final_c2.csv 2>/dev/null
+stamp "ncu full c2 done"
+timeout 80 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_c2_final.csv \
+  python bench.py --steps 1 --warmup 1 --no-cpu-baseline --vocab random > gpurun_out/ncu_bench.log 2>&1
+stamp "bench launch list done"
 cat gpurun_out/round_steps.log
