@@ -179,3 +179,37 @@ def test_vlad_fit_cache_roundtrip(u, tmp_path):
     v2.fit(None)
     assert v2.desc_dim == 64 and torch.equal(v2.c_centers, v.c_centers.cpu())
     assert rel_inf(v2.generate(x[:100]), ao.vlad_generate(x[:100], v.c_centers.cpu())) < TOL
+
+
+def test_vlad_prepared_equals_plain(u):
+    """anyloc_vlad_prepare + anyloc_vlad_generate_prepared (centre prep once per vocabulary, the path VLAD.generate*
+    takes) is bitwise identical to the plain anyloc_vlad_generate call, and the blob is reusable across calls."""
+    from anyloc_b200 import _lib
+    lib = _lib.load()
+    B, N, D, K = 3, 300, 384, 16
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(B, N, D, generator=g) * (0.5 + torch.rand(B, N, 1, generator=g))).cuda()
+    centers = (0.5 * torch.nn.functional.normalize(torch.randn(K, D, generator=g), dim=1)).cuda()
+    res = []
+    for prepared in (False, True):
+        out = torch.empty(B, K * D, device="cuda")
+        labels = torch.empty(B, N, dtype=torch.int32, device="cuda")
+        ws = torch.empty(lib.anyloc_vlad_workspace_bytes(B, N, D, K), dtype=torch.uint8, device="cuda")
+        if prepared:
+            blob = torch.empty(lib.anyloc_vlad_prepared_bytes(D, K), dtype=torch.uint8, device="cuda")
+            _lib.check(lib.anyloc_vlad_prepare(_lib.ptr(centers), D, K, 0, _lib.ptr(blob), blob.numel(), _lib.stream_ptr()),
+                       "anyloc_vlad_prepare")
+            for _ in range(2):
+                _lib.check(lib.anyloc_vlad_generate_prepared(_lib.ptr(x), None, _lib.ptr(centers), _lib.ptr(blob), blob.numel(),
+                                                             B, N, D, K, 0, 1, 1, _lib.ptr(out), _lib.ptr(labels),
+                                                             _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                           "anyloc_vlad_generate_prepared")
+        else:
+            _lib.check(lib.anyloc_vlad_generate(_lib.ptr(x), None, _lib.ptr(centers), B, N, D, K, 0, 1, 1, _lib.ptr(out),
+                                                _lib.ptr(labels), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                       "anyloc_vlad_generate")
+        torch.cuda.synchronize()
+        res.append((out.cpu(), labels.cpu()))
+    assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][0], res[1][0])
+    ref = ao.vlad_generate(x[1].cpu(), centers.cpu(), labels=res[0][1][1].long(), dtype=torch.float64)
+    assert rel_inf(res[0][0][1], ref) < TOL
