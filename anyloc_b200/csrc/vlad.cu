@@ -407,10 +407,9 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
   }
   __syncthreads();
   stamp(2);
-  // tasks -> registers.  HBM needs ~100 KB in flight per SM (tools/membw.cu: 32 KB -> 4.0 TB/s, 48 KB -> 4.8, >= 96 KB
-  // -> 6.3), far more than the registers of the resident warps can hold, so every warp grabs its NEXT task early and
-  // bulk-prefetches that task's row segments into L2 (cp.async.bulk.prefetch.L2: no destination registers); the
-  // register loads of the task itself then mostly hit L2.
+  // tasks -> registers.  Every warp grabs its NEXT task one task early; with `prefetch` it also bulk-prefetches that
+  // task's row segments into L2 (cp.async.bulk.prefetch.L2: no destination registers).  Measured neutral: this phase
+  // already streams at 5.2-5.4 TB/s (profiles/r01_vlad_v3.md, section 4b), so the prefetch is off by default.
   const float* xb = x + (size_t)b * N * D + col;
   const float* xs = x + (size_t)b * N * D + slice * 128;                     // this slice, lane-independent
   const uint32_t rowbytes = (uint32_t)min(128, D - slice * 128) * 4u;
@@ -912,9 +911,9 @@ int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_
 // ANYLOC_VLAD=2 selects the v2 pipeline (coarse GEMM + full rescoring pass + shared-memory accumulate + normalise
 // launch) for A/B measurements; default 3 = streaming tensor-core assignment + sorted register accumulate with the
 // normalisation fused into it.
-static int acc3_prefetch() {      // ANYLOC_VLAD_PREFETCH=0: accumulate3 without the L2 bulk prefetch of the next task (A/B)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("ANYLOC_VLAD_PREFETCH"); v = e ? atoi(e) : 1; }
+static int acc3_prefetch() {      // ANYLOC_VLAD_PREFETCH=1: accumulate3 bulk-prefetches each warp's next task into L2.  Off by
+  static int v = -1;               // default: measured neutral at c2 (86.3 vs 85.7 us) and slightly negative at c5 (276 vs 270 us)
+  if (v < 0) { const char* e = getenv("ANYLOC_VLAD_PREFETCH"); v = e ? atoi(e) : 0; }
   return v;
 }
 static int vlad_version() {
