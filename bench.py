@@ -317,9 +317,10 @@ def run_ours(args, wl):
                     "d2h_bytes_per_step": world * B * K * D * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks}
     if world == 1 and not args.no_cpu_baseline:
-        ips, ms, cores = cpu_reference(wl, args.ref_images, 3, 1)
+        n_ref = max(args.ref_images, 4)        # ~14 s of timed CPU work at c2 (0.85-0.9 img/s on the box's 16 usable cores)
+        ips, ms, cores = cpu_reference(wl, n_ref, 3, 1)
         line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{args.ref_images} images x 3 steps of the same workload, batch 1 per image, "
+                                "sample": f"{n_ref} images x 3 steps of the same workload, batch 1 per image, "
                                           "all blocks + hook, CPU VLAD with [N,K,D] residuals"}
     print(json.dumps(line), flush=True)
     if world > 1:
