@@ -213,3 +213,47 @@ def test_vlad_prepared_equals_plain(u):
     assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][0], res[1][0])
     ref = ao.vlad_generate(x[1].cpu(), centers.cpu(), labels=res[0][1][1].long(), dtype=torch.float64)
     assert rel_inf(res[0][0][1], ref) < TOL
+
+
+# ---- v3 pipeline corners (tensor-core assignment needs >= 256 rows per call; these shapes take that route or, for
+# K > 128, the v2 assignment in front of the v3 accumulate kernel)
+def _check_against_oracle(v, x, centers, dist_mode="cosine", **kw):
+    out = v.generate(x)
+    lab = v.kmeans.predict(x)
+    gap, lab64 = ao.label_margins(x, centers, dist_mode)
+    safe = gap > 1e-5
+    assert torch.equal(lab[safe], lab64[safe])
+    ref = ao.vlad_generate(x, centers, labels=lab, dtype=torch.float64, dist_mode=dist_mode, **kw)
+    assert rel_inf(out, ref) < TOL
+    return out
+
+
+def test_vlad_v3_ragged_large(u):
+    g = torch.Generator().manual_seed(21)
+    centers = 0.6 * torch.nn.functional.normalize(torch.randn(16, 384, generator=g), dim=1)
+    qs = [torch.randn(n, 384, generator=g) for n in (300, 257, 1, 411)]
+    v = make_vlad(u, 16, centers)
+    outs = v.generate_multi(qs)                     # padded to [4, 411, 384] with n_valid
+    for q, o in zip(qs, outs):
+        lab = v.kmeans.predict(q)
+        ref = ao.vlad_generate(q, centers, labels=lab, dtype=torch.float64)
+        assert rel_inf(o, ref) < TOL
+
+
+@pytest.mark.parametrize("N,D,K", [(300, 384, 200), (300, 100, 8), (700, 36, 5), (260, 2048, 128)])
+def test_vlad_v3_odd_shapes(u, N, D, K):
+    g = torch.Generator().manual_seed(N + D + K)
+    x = torch.randn(N, D, generator=g) * (0.3 + torch.rand(N, 1, generator=g))
+    centers = 0.5 * torch.nn.functional.normalize(torch.randn(K, D, generator=g), dim=1) * (1 + 0.3 * torch.rand(K, 1, generator=g))
+    _check_against_oracle(make_vlad(u, K, centers), x, centers)
+
+
+def test_vlad_v3_euclidean_and_switches_large(u):
+    g = torch.Generator().manual_seed(33)
+    x = torch.randn(400, 256, generator=g) * 1.3
+    centers = torch.randn(12, 256, generator=g) * 0.4
+    for kw in ({"dist_mode": "euclidean"}, {"intra_norm": False}, {"norm_descs": False}):
+        v = make_vlad(u, 12, centers, **kw)
+        dm = kw.get("dist_mode", "cosine")
+        okw = {k: val for k, val in kw.items() if k != "dist_mode"}
+        _check_against_oracle(v, x, centers, dist_mode=dm, **okw)
