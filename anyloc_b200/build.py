@@ -17,7 +17,8 @@ NVCC_FLAGS = [
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    """every csrc/*.cu except drafts (*_draft.cu: design-stage code that only has to compile, see its header)"""
+    return sorted(f for f in glob.glob(os.path.join(CSRC, "*.cu")) if not f.endswith("_draft.cu"))
 
 
 def _headers():
