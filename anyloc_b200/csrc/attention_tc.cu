@@ -509,10 +509,9 @@ int attention_tc_launch(const float* qkv_hi, const float* qkv_lo, const float* v
   if ((rc = make_map(&lkv, qkv_lo, rows, 3 * D, BKV))) return rc;
   if ((rc = make_map(&hvt, vt_hi, (int64_t)B * D, Tp, HD))) return rc;
   if ((rc = make_map(&lvt, vt_lo, (int64_t)B * D, Tp, HD))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_seen = 0;
+  if (first_use_on_this_device(&attr_seen)) {
     ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
   }
   const int total = cdiv(T, BQ) * heads * B;
   attention_tc_kernel<<<std::min(total, device_sm_count()), THREADS, SMEM_BYTES, st>>>(

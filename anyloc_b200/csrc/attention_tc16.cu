@@ -516,10 +516,9 @@ int attention_tc16_launch(const void* qk_hi, const void* qk_lo, const void* vt_h
   if ((rc = make_map(&lqk, qk_lo, (int64_t)B * T, 3 * (int64_t)D, BQ))) return rc;
   if ((rc = make_map(&hvt, vt_hi, (int64_t)B * D, Tp, HD))) return rc;
   if ((rc = make_map(&lvt, vt_lo, (int64_t)B * D, Tp, HD))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_seen = 0;
+  if (first_use_on_this_device(&attr_seen)) {
     ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
   }
   const int total = cdiv(T, BQ) * heads * B;
   attention_tc16_kernel<<<std::min(total, device_sm_count()), THREADS, SMEM_BYTES, st>>>(hqk, lqk, hvt, lvt, B, T, D,

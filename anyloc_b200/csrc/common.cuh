@@ -96,6 +96,16 @@ __device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi2, uin
 }
 
 int device_sm_count();
+// true the first time it is called on the CURRENT device for this flag word: cudaFuncSetAttribute is per device, so a
+// process that drives several GPUs must repeat it on each of them (one bit per device ordinal)
+static inline bool first_use_on_this_device(unsigned long long* seen) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  const unsigned long long bit = 1ull << dev;
+  if (*seen & bit) return false;
+  *seen |= bit;
+  return true;
+}
 void count_launch();
 
 // Optional per-category device timing (cudaEvents on the launching stream), see anyloc_profile_*.

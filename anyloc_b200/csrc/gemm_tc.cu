@@ -720,11 +720,10 @@ static int launch_2cta(const void* a_hi, const void* a_lo, int lda, const void* 
   // one instantiation per epilogue mode (compact per-tile code); -1 = the diagnostic "discard" variant
 #define ANYLOC_LAUNCH_2CTA(MODE_)                                                                                   \
   case MODE_: {                                                                                                     \
-    static bool attr_set = false;                                                                                   \
-    if (!attr_set) {                                                                                                \
+    static unsigned long long attr_seen = 0;                                                                                   \
+    if (first_use_on_this_device(&attr_seen)) {                                                                                                \
       ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_2cta_kernel<F16, MODE_>,                                      \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, two::SMEM_BYTES));        \
-      attr_set = true;                                                                                              \
     }                                                                                                               \
     gemm_tc3_2cta_kernel<F16, MODE_><<<2 * pairs, THREADS, two::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, \
                                                                                   K, bn, staged_epi, ep);          \
@@ -755,11 +754,10 @@ static int launch_impl(const void* a_hi, const void* a_lo, int lda, const void* 
   if ((rc = make_map(&ma_lo, a_lo ? a_lo : a_hi, M, K, lda, BM, F16))) return rc;
   if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, BN, F16))) return rc;
   if ((rc = make_map(&mb_lo, b_lo ? b_lo : b_hi, N, K, ldb, BN, F16))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_seen = 0;
+  if (first_use_on_this_device(&attr_seen)) {
     ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<BN, F16, LO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg<BN, LO>::SMEM_BYTES));
-    attr_set = true;
   }
   const int tiles = cdiv(M, BM) * cdiv(N, BN);
   const int grid = std::min(tiles, device_sm_count());

@@ -1079,10 +1079,9 @@ static int vlad_generate_impl(const float* feats, const int32_t* n_valid, const 
   int rc = launch_assign(feats, n_valid, N, (int64_t)R, D, K, centers, dist_mode, ab, labels, inv_norm, st, use_prep);
   if (rc) return rc;
   if (acc3 && ab.done) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_seen = 0;
+    if (first_use_on_this_device(&attr_seen)) {
       ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(vlad_accumulate3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      attr_set = true;
     }
     // all CTAs co-resident -> the slice-CTAs of an image may wait for each other (distributed normalisation);
     // otherwise the image's last CTA normalises alone.  ANYLOC_VLAD_WAIT=0 forces the latter (A/B).

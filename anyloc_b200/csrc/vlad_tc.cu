@@ -351,13 +351,12 @@ int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_
   p.zero_ptr = zero_ptr; p.zero_n = zero_ptr ? zero_n : 0;
   p.n_mma = n_mma;
   p.stage_bytes = A_BYTES + n_mma * 128;
-  static int max_smem = 0;
-  if (!max_smem) {
-    int dev = 0;
-    ANYLOC_CHECK_CUDA(cudaGetDevice(&dev));
-    ANYLOC_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  int dev = 0, max_smem = 0;
+  ANYLOC_CHECK_CUDA(cudaGetDevice(&dev));
+  ANYLOC_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  static unsigned long long attr_seen = 0;
+  if (first_use_on_this_device(&attr_seen))
     ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(vlad_assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  }
   const int fixed = 1024 + BAR_BYTES + VEC_BYTES;
   p.stages = std::min(MAX_STAGES, (max_smem - fixed) / p.stage_bytes);
   const int num_k = (D + 31) / 32;
