@@ -287,6 +287,7 @@ class VLAD:
         self.c_centers = None
         self.kmeans = None
         self._centers_dev = {}
+        self._prepared_dev = None
         self.cache_dir = cache_dir
         if self.cache_dir is not None:
             self.cache_dir = os.path.abspath(os.path.expanduser(self.cache_dir))
@@ -321,6 +322,7 @@ class VLAD:
     def fit(self, train_descs: Union[np.ndarray, torch.Tensor, None]):
         self.kmeans = _KMeans(self.num_clusters, mode=self.mode)
         self._centers_dev = {}
+        self._prepared_dev = None
         if self.can_use_cache_vlad():
             print("Using cached cluster centers")
             self.c_centers = torch.load(f"{self.cache_dir}/c_centers.pt")
