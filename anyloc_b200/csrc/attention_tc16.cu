@@ -11,6 +11,7 @@
 // warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-19 = softmax (four warps per 32-row lane quarter:
 // 32-key quarters of S / 16-wide head-dim quarters of O -- the softmax, not the UMMAs, bounds this kernel).
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace anyloc {
@@ -142,6 +143,12 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {      // a -> l
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 
+// SKIP (ANYLOC_ATTN_SKIP=1, off by default, NOT yet measured): at T = 530 both the last key block and the last query
+// tile hold 18 valid entries of 128, so only (530/640)^2 = 69 % of the softmax work is useful.  With SKIP the softmax
+// warps whose 32 keys or 32 query rows lie entirely beyond T skip scale / max / ex2 / pair split (they keep taking part
+// in the barriers and publish zero probabilities), and the P.V of the last key block issues only the k-steps that hold
+// valid keys.  SKIP = false compiles to exactly the kernel measured in round 1.
+template <bool SKIP>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid_constant__ CUtensorMap tm_lo_qk,
                       const __grid_constant__ CUtensorMap tm_hi_vt, const __grid_constant__ CUtensorMap tm_lo_vt,
@@ -294,8 +301,10 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
           const uint32_t vb = smem_u32(sV + st * VSTAGE);
           const uint32_t d = tmem_base + COL_O + (uint32_t)((gb & 1) * HD);
           const uint32_t pbuf = tmem_base + COL_S + (uint32_t)((gb & 1) * BKV);
+          const int ksteps = (SKIP && j == nblk - 1) ? ((T - j * BKV + 15) >> 4) : BKV / 16;
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k) {                // 8 k-steps of 16 keys
+            if (SKIP && k >= ksteps) break;
             const uint32_t voff = (uint32_t)((k >> 2) * V_BOX + (k & 3) * 32);
             const uint64_t v_hi = desc_kmajor(vb + voff), v_lo = desc_kmajor(vb + 2 * V_BOX + voff);
             // keys [16k,16k+16) live in the 32-column group of softmax part k/2: hi at +8*(k&1), lo at +16+8*(k&1)
@@ -323,6 +332,7 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int qt = w % q_tiles, h = (w / q_tiles) % heads, b = w / (q_tiles * heads);
       const int qrow = qt * BQ + row;
+      const bool dead_rows = SKIP && (qt * BQ + qd * 32 >= T);            // none of this warp's 32 query rows exists
       const bool tdump = dbg != nullptr && w == (int)gridDim.x && blockIdx.x == 0 && warp == 4 && lane == 0;
       const long long tb = tdump ? clock64() : 0;
 #define TSTAMP(slot) do { if (tdump) dbg[j * 16 + (slot)] = (float)(clock64() - tb); } while (0)
@@ -337,18 +347,21 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
         mbar_wait(smem_u32(s_full + (gb & 1)), (uint32_t)((gb >> 1) & 1));
         tc_fence_after();
         TSTAMP(1);
+        const bool dead = SKIP && (dead_rows || j * BKV + part * 32 >= T);   // warp-uniform: nothing to exponentiate
         float s[32];
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        if (!dead) {
         tmem_ld32(lane_addr + COL_S + (uint32_t)((gb & 1) * BKV + part * 32), s);
         TSTAMP(2);
         if (j == nblk - 1) {
 #pragma unroll
           for (int c = 0; c < 32; ++c) if (j * BKV + part * 32 + c >= T) s[c] = -INFINITY;
         }
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
           s[c] *= kScale; s[c + 1] *= kScale; s[c + 2] *= kScale; s[c + 3] *= kScale;
           mx0 = fmaxf(mx0, s[c]); mx1 = fmaxf(mx1, s[c + 1]); mx2 = fmaxf(mx2, s[c + 2]); mx3 = fmaxf(mx3, s[c + 3]);
+        }
         }
         const float pm = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
         float* slot = xchg + (gb & 1) * 4 * BQ;
@@ -356,22 +369,29 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
         asm volatile("bar.sync %0, 128;" ::"r"(1 + qd) : "memory");      // the four warps of this lane quarter
         const float mx = fmaxf(fmaxf(m, slot[row]), fmaxf(fmaxf(slot[BQ + row], slot[2 * BQ + row]), slot[3 * BQ + row]));
         TSTAMP(3);
-        const float alpha = ex2(m - mx);
+        const float alpha = (SKIP && dead_rows) ? 1.0f : ex2(m - mx);
         float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+        if (!dead) {
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
           s[c] = ex2(s[c] - mx); s[c + 1] = ex2(s[c + 1] - mx);
           s[c + 2] = ex2(s[c + 2] - mx); s[c + 3] = ex2(s[c + 3] - mx);
           r0 += s[c]; r1 += s[c + 1]; r2 += s[c + 2]; r3 += s[c + 3];
         }
+        }
         l = l * alpha + ((r0 + r1) + (r2 + r3));
         m = mx;
         TSTAMP(4);
         // publish this warp's 32 key columns of P_j (packed fp16 pairs of 1024*p) over its own S columns
-        {
+        if (!(SKIP && dead_rows)) {             // rows that do not exist may keep whatever the S columns hold
           uint32_t ph[16], pl[16];
+          if (!dead) {
 #pragma unroll
           for (int c = 0; c < 32; c += 2) split_f16x2(s[c] * P_SCALE, s[c + 1] * P_SCALE, ph[c >> 1], pl[c >> 1]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { ph[c] = 0u; pl[c] = 0u; }
+          }
           const uint32_t pcol = lane_addr + COL_S + (uint32_t)((gb & 1) * BKV + part * 32);
           tmem_st16(pcol, ph);
           tmem_st16(pcol + 16, pl);
@@ -383,7 +403,7 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
         if (lane == 0) mbar_arrive(smem_u32(p_full));
         TSTAMP(6);
         // fold in O_{j-1} (RN) and rescale to the new running maximum
-        if (j > 0) {
+        if (j > 0 && !(SKIP && dead_rows)) {
           mbar_wait(smem_u32(o_full + ((gb - 1) & 1)), (uint32_t)(((gb - 1) >> 1) & 1));
           tc_fence_after();
           float t[16];
@@ -394,7 +414,7 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
         alpha_prev = alpha;
         TSTAMP(7);
       }
-      {
+      if (!(SKIP && dead_rows)) {
         const int gl = g + nblk - 1;
         mbar_wait(smem_u32(o_full + (gl & 1)), (uint32_t)((gl >> 1) & 1));
         tc_fence_after();
@@ -518,11 +538,18 @@ int attention_tc16_launch(const void* qk_hi, const void* qk_lo, const void* vt_h
   if ((rc = make_map(&lvt, vt_lo, (int64_t)B * D, Tp, HD))) return rc;
   static unsigned long long attr_seen = 0;
   if (first_use_on_this_device(&attr_seen)) {
-    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   }
+  static int skip_env = -1;             // ANYLOC_ATTN_SKIP=1: the tail-skipping variant (see the kernel's header); default off
+  if (skip_env < 0) { const char* e = getenv("ANYLOC_ATTN_SKIP"); skip_env = e ? atoi(e) : 0; }
   const int total = cdiv(T, BQ) * heads * B;
-  attention_tc16_kernel<<<std::min(total, device_sm_count()), THREADS, SMEM_BYTES, st>>>(hqk, lqk, hvt, lvt, B, T, D,
-                                                                                         o_hi, o_lo, out_f16 ? 1 : 0, g_attn16_dbg);
+  if (skip_env)
+    attention_tc16_kernel<true><<<std::min(total, device_sm_count()), THREADS, SMEM_BYTES, st>>>(hqk, lqk, hvt, lvt, B, T, D,
+                                                                                               o_hi, o_lo, out_f16 ? 1 : 0, g_attn16_dbg);
+  else
+    attention_tc16_kernel<false><<<std::min(total, device_sm_count()), THREADS, SMEM_BYTES, st>>>(hqk, lqk, hvt, lvt, B, T, D,
+                                                                                                o_hi, o_lo, out_f16 ? 1 : 0, g_attn16_dbg);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }
