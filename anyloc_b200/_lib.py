@@ -63,6 +63,10 @@ _SIGS = {
     "anyloc_preprocess_u8": (C.c_int, [C.c_void_p] + [C.c_int] * 7 + [C.POINTER(C.c_float)] * 2 +
                              [C.c_void_p, C.c_void_p]),
     "anyloc_pool": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
+    "anyloc_vlad_residuals": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
+    "anyloc_vlad_from_residuals_workspace_bytes": (C.c_size_t, [C.c_int] * 2),
+    "anyloc_vlad_from_residuals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 +
+                                   [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "anyloc_vlad_assign": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 +
                            [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "anyloc_kmeans_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 3 +
@@ -70,6 +74,12 @@ _SIGS = {
     "anyloc_topk_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "anyloc_topk": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 +
                     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "anyloc_index_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
+    "anyloc_index_add": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p]),
+    "anyloc_index_search_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int, C.c_int]),
+    "anyloc_index_search": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int64, C.c_int64, C.c_void_p] + [C.c_int] * 5 +
+                            [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "anyloc_vit_patch_k": (C.c_int, [C.c_int]),
     "anyloc_vit_workspace_bytes": (C.c_size_t, [C.POINTER(VitCfg), C.c_int, C.c_int, C.c_int]),
     "anyloc_vit_extract": (C.c_int, [C.POINTER(VitCfg), C.POINTER(VitWeightsStruct), C.c_void_p,

@@ -62,54 +62,122 @@ normalize_rows_split_kernel(const float* __restrict__ x, int D, int do_norm, voi
   }
 }
 
-// k-best selection per query row by k rounds of block arg-best (n_db up to ~1e6, k <= 128).
-// metric IP: larger is better; metric L2: score := qq - 2 s + dd, smaller is better.
-__global__ void __launch_bounds__(1024)
-topk_select_kernel(float* __restrict__ scores, int n_db, int64_t ld, int k, int metric,
-                   const float* __restrict__ qq, const float* __restrict__ dd,
-                   float* __restrict__ dist, int64_t* __restrict__ idx) {
-  const int q = blockIdx.x;
-  float* s = scores + (size_t)q * ld;
-  if (metric == ANYLOC_METRIC_L2) {
-    const float a = qq[q];
-    for (int j = threadIdx.x; j < n_db; j += blockDim.x) s[j] = -((a - 2.0f * s[j]) + dd[j]);  // negate: larger=better
-    __syncthreads();
+// k-best selection per query row, best first, lowest index first among equal scores (metric IP: larger is better;
+// metric L2: key := -(qq - 2 s + dd)).  O(n_db) per query:
+//   A: every thread keeps the best score of its strided share of the row;
+//   B: tau = the k-th best of the 1024 thread bests (k rounds of block arg-best over 1024 values): those are k DISTINCT
+//      row elements, so the row's true k-th best is >= tau and every member of the true top-k is >= tau;
+//   C: second sweep, the elements >= tau (usually k .. a few k of them) are compacted into a shared-memory list;
+//   D: k rounds of arg-best over the list (score descending, lowest index first among equal scores).
+// More than SEL_CAP candidates (a row with thousands of equal scores) -> k ordered sweeps over the row (read-only).
+constexpr int SEL_CAP = 4096;
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
+
+__device__ __forceinline__ void block_argbest(float& best, int& besti, float* bv, int* bi) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (better(ov, oi, best, besti)) { best = ov; besti = oi; }
   }
-  __shared__ float bv[32];
-  __shared__ int bi[32];
-  for (int r = 0; r < k; ++r) {
-    float best = -INFINITY; int besti = 0x7fffffff;
-    for (int j = threadIdx.x; j < n_db; j += blockDim.x) {
-      float v = s[j];
-      if (v > best || (v == best && j < besti)) { best = v; besti = j; }
-    }
+  if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = besti; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    best = threadIdx.x < nw ? bv[threadIdx.x] : -INFINITY;
+    besti = threadIdx.x < nw ? bi[threadIdx.x] : 0x7fffffff;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       float ov = __shfl_xor_sync(0xffffffffu, best, o);
       int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-      if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+      if (better(ov, oi, best, besti)) { best = ov; besti = oi; }
     }
-    if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = besti; }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      int nw = blockDim.x >> 5;
-      best = threadIdx.x < nw ? bv[threadIdx.x] : -INFINITY;
-      besti = threadIdx.x < nw ? bi[threadIdx.x] : 0x7fffffff;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-        if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+    if (threadIdx.x == 0) { bv[32] = best; bi[32] = besti; }
+  }
+  __syncthreads();
+  best = bv[32]; besti = bi[32];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024)
+topk_select2_kernel(const float* __restrict__ scores, int n_db, int64_t ld, int k, int metric,
+                    const float* __restrict__ qq, const float* __restrict__ dd,
+                    float* __restrict__ dist, int64_t* __restrict__ idx) {
+  const int q = blockIdx.x;
+  const float* s = scores + (size_t)q * ld;
+  const bool l2 = metric == ANYLOC_METRIC_L2;
+  const float a = l2 ? qq[q] : 0.f;
+  auto key = [&](int j) { const float v = s[j]; return l2 ? -((a - 2.0f * v) + dd[j]) : v; };   // larger = better
+  __shared__ float bv[33];
+  __shared__ int bi[33];
+  __shared__ float cv[SEL_CAP];
+  __shared__ int ci[SEL_CAP];
+  __shared__ int count;
+  if (threadIdx.x == 0) count = 0;
+  // A
+  float mine = -INFINITY; int minei = 0x7fffffff;
+  for (int j = threadIdx.x; j < n_db; j += blockDim.x) {
+    const float v = key(j);
+    if (better(v, j, mine, minei)) { mine = v; minei = j; }
+  }
+  // B
+  float tau = -INFINITY;
+  {
+    float v = mine; int vi = minei;
+    for (int r = 0; r < k; ++r) {
+      float b = v; int bidx = vi;
+      block_argbest(b, bidx, bv, bi);
+      if (bidx == 0x7fffffff) { tau = -INFINITY; break; }   // fewer than k elements in the row
+      tau = b;
+      if (vi == bidx) { v = -INFINITY; vi = 0x7fffffff; }    // the winner leaves the pool
+    }
+  }
+  __syncthreads();
+  // C
+  for (int j = threadIdx.x; j < n_db; j += blockDim.x) {
+    const float v = key(j);
+    if (v >= tau) {
+      const int slot = atomicAdd(&count, 1);
+      if (slot < SEL_CAP) { cv[slot] = v; ci[slot] = j; }
+    }
+  }
+  __syncthreads();
+  const int n_c = count;
+  if (n_c > SEL_CAP) {
+    // thousands of (near-)equal scores: k ordered sweeps over the row itself -- round r takes the best element that
+    // comes strictly after round r-1's winner in (score descending, index ascending) order
+    float pv = INFINITY; int pj = -1;
+    for (int r = 0; r < k; ++r) {
+      float b = -INFINITY; int bidx = 0x7fffffff;
+      for (int j = threadIdx.x; j < n_db; j += blockDim.x) {
+        const float v = key(j);
+        if ((v < pv || (v == pv && j > pj)) && better(v, j, b, bidx)) { b = v; bidx = j; }
       }
+      block_argbest(b, bidx, bv, bi);
       if (threadIdx.x == 0) {
-        if (r < n_db && besti != 0x7fffffff) {
-          dist[(size_t)q * k + r] = metric == ANYLOC_METRIC_L2 ? -best : best;
-          idx[(size_t)q * k + r] = besti;
-          s[besti] = -INFINITY;      // exclude from later rounds
-        } else {
-          dist[(size_t)q * k + r] = metric == ANYLOC_METRIC_L2 ? INFINITY : -INFINITY;
-          idx[(size_t)q * k + r] = -1;   // faiss pads with -1 when k > ntotal
-        }
+        dist[(size_t)q * k + r] = bidx != 0x7fffffff ? (l2 ? -b : b) : (l2 ? INFINITY : -INFINITY);
+        idx[(size_t)q * k + r] = bidx != 0x7fffffff ? bidx : -1;
+      }
+      pv = b; pj = bidx;
+      if (bidx == 0x7fffffff) pv = -INFINITY;      // exhausted: every later round pads
+    }
+    return;
+  }
+  // D
+  for (int r = 0; r < k; ++r) {
+    float b = -INFINITY; int bidx = 0x7fffffff; int bslot = -1;
+    for (int c = threadIdx.x; c < n_c; c += blockDim.x)
+      if (better(cv[c], ci[c], b, bidx)) { b = cv[c]; bidx = ci[c]; bslot = c; }
+    float wb = b; int wi = bidx;
+    block_argbest(wb, wi, bv, bi);
+    if (bslot >= 0 && wi == bidx && wi != 0x7fffffff) { cv[bslot] = -INFINITY; ci[bslot] = 0x7fffffff; }
+    if (threadIdx.x == 0) {
+      if (wi != 0x7fffffff) {
+        dist[(size_t)q * k + r] = l2 ? -wb : wb;
+        idx[(size_t)q * k + r] = wi;
+      } else {
+        dist[(size_t)q * k + r] = l2 ? INFINITY : -INFINITY;
+        idx[(size_t)q * k + r] = -1;          // faiss pads with -1 when k > ntotal
       }
     }
     __syncthreads();
@@ -121,12 +189,117 @@ topk_select_kernel(float* __restrict__ scores, int n_db, int64_t ld, int k, int 
 using namespace anyloc;
 
 
+// ---- prepared database ("index"): what faiss' index.add(db) leaves behind (utilities.py:449).
+// Layout of the caller-owned blob for `capacity` rows of Dv columns:
+//   hi [capacity, Dv] | lo [capacity, Dv] | sq [capacity] fp32 (|y|^2 per row, the L2 metric needs it)
+// with hi/lo either fp16 pairs of 4096*y (unit rows: normalize != 0, Dv % 8 == 0 -- the 2x faster kind::f16 tensor
+// path) or tf32 pairs of y (rows of unknown range).  ANYLOC_TOPK_F16=0 forces the tf32 pairs (A/B).
+static bool index_uses_f16(int Dv, int normalize) {
+  static int f16_env = -1;
+  if (f16_env < 0) { const char* e = getenv("ANYLOC_TOPK_F16"); f16_env = e ? atoi(e) : 1; }
+  return f16_env && normalize && (Dv % 8) == 0;
+}
+struct IndexView { void* hi; void* lo; float* sq; bool f16; };
+static bool carve_index(void* blob, size_t bytes, int64_t capacity, int Dv, int normalize, IndexView* v) {
+  v->f16 = index_uses_f16(Dv, normalize);
+  const size_t esz = v->f16 ? 2 : 4;
+  Workspace w(blob, bytes);
+  v->hi = w.take<char>((size_t)capacity * Dv * esz);
+  v->lo = w.take<char>((size_t)capacity * Dv * esz);
+  v->sq = w.take<float>((size_t)capacity);
+  return v->hi && v->lo && v->sq;
+}
+
+extern "C" size_t anyloc_index_bytes(int64_t capacity, int Dv, int normalize) {
+  const size_t esz = index_uses_f16(Dv, normalize) ? 2 : 4;
+  return 2 * align_up((size_t)capacity * Dv * esz, 256) + align_up((size_t)capacity * 4, 256) + 256;
+}
+
+extern "C" int anyloc_index_add(void* index, size_t index_bytes, int64_t capacity, int64_t row_offset, const float* rows,
+                                int n_rows, int Dv, int normalize, void* stream) {
+  ANYLOC_REQUIRE(index && (rows || n_rows == 0), "index_add: null pointer");
+  ANYLOC_REQUIRE(n_rows >= 0 && Dv > 0 && Dv % 4 == 0 && row_offset >= 0 && row_offset + n_rows <= capacity,
+                 "index_add: bad dims n_rows=%d Dv=%d offset=%lld capacity=%lld", n_rows, Dv, (long long)row_offset,
+                 (long long)capacity);
+  IndexView v;
+  if (!carve_index(index, index_bytes, capacity, Dv, normalize, &v)) {
+    set_error("index_add: blob too small (%zu given, %zu needed)", index_bytes, anyloc_index_bytes(capacity, Dv, normalize));
+    return ANYLOC_ERR_WORKSPACE;
+  }
+  if (n_rows == 0) return ANYLOC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(PC_TOPK, st, (v.f16 ? 8.0 : 12.0) * (double)n_rows * Dv);
+  const size_t off = (size_t)row_offset * Dv;
+  if (v.f16)
+    normalize_rows_split_kernel<true><<<n_rows, 256, 0, st>>>(rows, Dv, normalize, (__half*)v.hi + off, (__half*)v.lo + off,
+                                                              v.sq + row_offset);
+  else
+    normalize_rows_split_kernel<false><<<n_rows, 256, 0, st>>>(rows, Dv, normalize, (float*)v.hi + off, (float*)v.lo + off,
+                                                               v.sq + row_offset);
+  ANYLOC_CHECK_LAUNCH();
+  return ANYLOC_OK;
+}
+
+// workspace of one search: query pairs + |q|^2 + the [n_q, n_db] score matrix
+extern "C" size_t anyloc_index_search_workspace_bytes(int64_t n_db, int n_q, int Dv, int normalize) {
+  const size_t esz = index_uses_f16(Dv, normalize) ? 2 : 4;
+  return 2 * align_up((size_t)n_q * Dv * esz, 256) + align_up((size_t)n_q * 4, 256) +
+         align_up((size_t)n_q * (size_t)n_db * 4, 256) + 1024;
+}
+
+extern "C" int anyloc_index_search(const void* index, size_t index_bytes, int64_t capacity, int64_t n_db, const float* qu,
+                                   int n_q, int Dv, int k, int metric, int normalize, float* dist, int64_t* idx, void* ws,
+                                   size_t ws_bytes, void* stream) {
+  ANYLOC_REQUIRE(index && qu && dist && idx && ws, "index_search: null pointer");
+  ANYLOC_REQUIRE(n_db > 0 && n_db <= capacity && n_db < (1ll << 31) && n_q >= 0 && Dv > 0 && k > 0,
+                 "index_search: bad dims n_db=%lld n_q=%d Dv=%d k=%d", (long long)n_db, n_q, Dv, k);
+  ANYLOC_REQUIRE(Dv % 4 == 0, "index_search: Dv=%d must be a multiple of 4", Dv);
+  ANYLOC_REQUIRE(metric == ANYLOC_METRIC_IP || metric == ANYLOC_METRIC_L2, "index_search: unknown metric %d", metric);
+  if (n_q == 0) return ANYLOC_OK;
+  IndexView v;
+  if (!carve_index(const_cast<void*>(index), index_bytes, capacity, Dv, normalize, &v)) {
+    set_error("index_search: index blob too small");
+    return ANYLOC_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t esz = v.f16 ? 2 : 4;
+  Workspace w(ws, ws_bytes);
+  void* qu_hi = w.take<char>((size_t)n_q * Dv * esz);
+  void* qu_lo = w.take<char>((size_t)n_q * Dv * esz);
+  float* qq = w.take<float>(n_q);
+  float* scores = w.take<float>((size_t)n_q * (size_t)n_db);
+  if (!qu_hi || !qu_lo || !qq || !scores) {
+    set_error("index_search: workspace too small (%zu given, %zu needed)", ws_bytes,
+              anyloc_index_search_workspace_bytes(n_db, n_q, Dv, normalize));
+    return ANYLOC_ERR_WORKSPACE;
+  }
+  int rc;
+  {
+    ProfScope ps(PC_TOPK, st, (v.f16 ? 8.0 : 12.0) * (double)n_q * Dv);
+    if (v.f16) normalize_rows_split_kernel<true><<<n_q, 256, 0, st>>>(qu, Dv, normalize, qu_hi, qu_lo, qq);
+    else normalize_rows_split_kernel<false><<<n_q, 256, 0, st>>>(qu, Dv, normalize, qu_hi, qu_lo, qq);
+    ANYLOC_CHECK_LAUNCH();
+  }
+  // score GEMM on the tcgen05 engine (gemm_dispatch records it under PC_GEMM_TC with 2*n_q*n_db*Dv FLOPs)
+  rc = anyloc_gemm_nt(qu_hi, qu_lo, Dv, v.hi, v.lo, Dv, n_q, (int)n_db, Dv, v.f16 ? ANYLOC_PAIR_F16 : ANYLOC_PAIR_TF32,
+                      v.f16 ? 1.0f / (kRetrievalScale * kRetrievalScale) : 1.0f, ANYLOC_EPI_BIAS, nullptr, nullptr, nullptr,
+                      scores, nullptr, (int)n_db, ANYLOC_PAIR_TF32, ANYLOC_GEMM_AUTO, stream);
+  if (rc) return rc;
+  {
+    ProfScope ps(PC_TOPK, st, 8.0 * (double)n_q * (double)n_db);
+    topk_select2_kernel<<<n_q, 1024, 0, st>>>(scores, (int)n_db, n_db, k, metric, qq, v.sq, dist, idx);
+    ANYLOC_CHECK_LAUNCH();
+  }
+  return ANYLOC_OK;
+}
+
+// One-shot form (get_top_k_recall builds the index and searches it once, utilities.py:449-450): a temporary index in
+// the caller's workspace, then the search above.
 extern "C" size_t anyloc_topk_workspace_bytes(int n_db, int n_q, int Dv, int k) {
   (void)k;
-  size_t Dp = align_up((size_t)Dv, 4);
-  return 2 * align_up((size_t)n_db * Dp * 4, 256) + 2 * align_up((size_t)n_q * Dp * 4, 256) +
-         align_up((size_t)n_db * 4, 256) + align_up((size_t)n_q * 4, 256) +
-         align_up((size_t)n_q * (size_t)n_db * 4, 256) + 4096;
+  // sized for the larger (tf32-pair) layout so that the same buffer serves normalize = 0 / 1
+  return anyloc_index_bytes(n_db, (int)align_up((size_t)Dv, 4), 0) +
+         anyloc_index_search_workspace_bytes(n_db, n_q, (int)align_up((size_t)Dv, 4), 0) + 512;
 }
 
 extern "C" int anyloc_topk(const float* db, const float* qu, int n_db, int n_q, int Dv, int k, int metric,
@@ -137,45 +310,15 @@ extern "C" int anyloc_topk(const float* db, const float* qu, int n_db, int n_q, 
   ANYLOC_REQUIRE(Dv % 4 == 0, "topk: Dv=%d must be a multiple of 4", Dv);
   ANYLOC_REQUIRE(metric == ANYLOC_METRIC_IP || metric == ANYLOC_METRIC_L2, "topk: unknown metric %d", metric);
   if (n_q == 0) return ANYLOC_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  Workspace w(ws, ws_bytes);
-  float* db_hi = w.take<float>((size_t)n_db * Dv);
-  float* db_lo = w.take<float>((size_t)n_db * Dv);
-  float* qu_hi = w.take<float>((size_t)n_q * Dv);
-  float* qu_lo = w.take<float>((size_t)n_q * Dv);
-  float* dd = w.take<float>(n_db);
-  float* qq = w.take<float>(n_q);
-  float* scores = w.take<float>((size_t)n_q * n_db);
-  if (!db_hi || !db_lo || !qu_hi || !qu_lo || !dd || !qq || !scores) {
-    set_error("topk: workspace too small (%zu given, %zu needed)", ws_bytes,
-              anyloc_topk_workspace_bytes(n_db, n_q, Dv, k));
+  const size_t ib = anyloc_index_bytes(n_db, Dv, normalize);
+  const size_t need = align_up(ib, 256) + anyloc_index_search_workspace_bytes(n_db, n_q, Dv, normalize);
+  if (ws_bytes < need) {
+    set_error("topk: workspace too small (%zu given, %zu needed)", ws_bytes, need);
     return ANYLOC_ERR_WORKSPACE;
   }
-  ProfScope ps(PC_TOPK, st, 4.0 * ((double)n_db + n_q) * Dv);
-  // Unit-norm rows (the reference's default, norm_descs=True) go through the 2x faster kind::f16 tensor path as fp16
-  // pairs of 4096*y; un-normalised rows have no a-priori range and keep the tf32 pairs.  ANYLOC_TOPK_F16=0 disables.
-  static int f16_env = -1;
-  if (f16_env < 0) { const char* e = getenv("ANYLOC_TOPK_F16"); f16_env = e ? atoi(e) : 1; }
-  const bool f16 = f16_env && normalize && (Dv % 8) == 0;
-  int rc;
-  if (f16) {
-    normalize_rows_split_kernel<true><<<n_db, 256, 0, st>>>(db, Dv, normalize, db_hi, db_lo, dd);
-    ANYLOC_CHECK_LAUNCH();
-    normalize_rows_split_kernel<true><<<n_q, 256, 0, st>>>(qu, Dv, normalize, qu_hi, qu_lo, qq);
-    ANYLOC_CHECK_LAUNCH();
-    rc = anyloc_gemm_nt(qu_hi, qu_lo, Dv, db_hi, db_lo, Dv, n_q, n_db, Dv, ANYLOC_PAIR_F16,
-                        1.0f / (kRetrievalScale * kRetrievalScale), ANYLOC_EPI_BIAS, nullptr, nullptr, nullptr, scores,
-                        nullptr, n_db, ANYLOC_PAIR_TF32, ANYLOC_GEMM_AUTO, stream);
-  } else {
-    normalize_rows_split_kernel<false><<<n_db, 256, 0, st>>>(db, Dv, normalize, db_hi, db_lo, dd);
-    ANYLOC_CHECK_LAUNCH();
-    normalize_rows_split_kernel<false><<<n_q, 256, 0, st>>>(qu, Dv, normalize, qu_hi, qu_lo, qq);
-    ANYLOC_CHECK_LAUNCH();
-    rc = anyloc_gemm_nt(qu_hi, qu_lo, Dv, db_hi, db_lo, Dv, n_q, n_db, Dv, ANYLOC_PAIR_TF32, 1.0f, ANYLOC_EPI_BIAS,
-                        nullptr, nullptr, nullptr, scores, nullptr, n_db, ANYLOC_PAIR_TF32, ANYLOC_GEMM_AUTO, stream);
-  }
+  int rc = anyloc_index_add(ws, ib, n_db, 0, db, n_db, Dv, normalize, stream);
   if (rc) return rc;
-  topk_select_kernel<<<n_q, 1024, 0, st>>>(scores, n_db, n_db, k, metric, qq, dd, dist, idx);
-  ANYLOC_CHECK_LAUNCH();
-  return ANYLOC_OK;
+  char* rest = (char*)ws + align_up(ib, 256);
+  return anyloc_index_search(ws, ib, n_db, n_db, qu, n_q, Dv, k, metric, normalize, dist, idx, rest,
+                             ws_bytes - align_up(ib, 256), stream);
 }

@@ -1252,3 +1252,137 @@ extern "C" int anyloc_kmeans_update(const float* x, const int32_t* labels, const
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }
+
+// ====================================================================================================================
+// Residual tensors and the per-image cache path (utilities.py:928-972, :843-852, :864-878).  Off the hot path: the
+// reference materialises x^ - c for ALL (patch, centre) pairs ([N,K,D] fp32, 104 MB per image at c2) and, with a
+// cache directory, re-builds descriptors from cached residuals / labels / soft assignments without the features.
+// ====================================================================================================================
+namespace anyloc {
+
+// out[q,k,:] = x_q / max(|x_q|, 1e-12) - c_k (F.normalize when norm_descs, utilities.py:959-962).  CTA per row;
+// HBM-bound on the N*K*D*4 bytes written.
+__global__ void __launch_bounds__(256)
+vlad_residuals_kernel(const float* __restrict__ x, const float* __restrict__ centers, int D, int K, int norm_descs,
+                      float* __restrict__ out) {
+  const size_t q = blockIdx.x;
+  const float4* xr = reinterpret_cast<const float4*>(x + q * D);
+  const int D4 = D >> 2;
+  __shared__ float red[8];
+  __shared__ float s_nrm;
+  float ss = 0.f;
+  if (norm_descs) {
+    for (int d = threadIdx.x; d < D4; d += blockDim.x) { float4 v = __ldg(xr + d); ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += red[w]; s_nrm = fmaxf(sqrtf(t), 1e-12f); }
+    __syncthreads();
+  }
+  const float nrm = norm_descs ? s_nrm : 1.0f;
+  float4* o = reinterpret_cast<float4*>(out + q * (size_t)K * D);
+  for (int d = threadIdx.x; d < D4; d += blockDim.x) {
+    float4 v = __ldg(xr + d);
+    if (norm_descs) { v.x /= nrm; v.y /= nrm; v.z /= nrm; v.w /= nrm; }
+    for (int k = 0; k < K; ++k) {
+      const float4 c = __ldg(reinterpret_cast<const float4*>(centers + (size_t)k * D) + d);
+      o[(size_t)k * D4 + d] = make_float4(v.x - c.x, v.y - c.y, v.z - c.z, v.w - c.w);
+    }
+  }
+}
+
+// hard: V[k,col] = sum_{q: label_q = k} R[q,k,col] (utilities.py:858); CTA = (column slice, cluster), thread = column,
+// rows in index order.  Unused clusters stay zero (:840).
+__global__ void __launch_bounds__(ACC_COLS)
+vlad_from_residuals_hard_kernel(const float* __restrict__ resid, const int32_t* __restrict__ labels, int N, int D, int K,
+                                float* __restrict__ vlad, float* __restrict__ partial_ss) {
+  const int slice = blockIdx.x, k = blockIdx.y, t = threadIdx.x, nslices = gridDim.x;
+  const int col = slice * ACC_COLS + t;
+  const bool colok = col < D;
+  float acc = 0.f;
+  for (int q = 0; q < N; ++q)
+    if (__ldg(labels + q) == k && colok) acc += __ldg(resid + ((size_t)q * K + k) * D + col);
+  if (colok) vlad[(size_t)k * D + col] = acc;
+  __shared__ float red[ACC_COLS / 32];
+  const float s = warp_sum(colok ? acc * acc : 0.f);
+  if ((t & 31) == 0) red[t >> 5] = s;
+  __syncthreads();
+  if (t == 0) { float tot = 0.f; for (int w = 0; w < ACC_COLS / 32; ++w) tot += red[w]; partial_ss[(size_t)k * nslices + slice] = tot; }
+}
+
+// soft: V[k,col] = sum_q a[q,k] * sum_c R[q,c,col] (utilities.py:879-884: cluster k's weight on the residuals to ALL
+// centres).  CTA = column slice, thread = column, 32 cluster accumulators per pass.
+__global__ void __launch_bounds__(ACC_COLS)
+vlad_from_residuals_soft_kernel(const float* __restrict__ resid, const float* __restrict__ assign, int N, int D, int K,
+                                float* __restrict__ vlad, float* __restrict__ partial_ss) {
+  const int slice = blockIdx.x, t = threadIdx.x, nslices = gridDim.x;
+  const int col = slice * ACC_COLS + t;
+  const bool colok = col < D;
+  __shared__ float red[ACC_COLS / 32][32];
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    const int kc = min(32, K - k0);
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    if (colok) {
+      for (int q = 0; q < N; ++q) {
+        float s = 0.f;
+        for (int c = 0; c < K; ++c) s += __ldg(resid + ((size_t)q * K + c) * D + col);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < kc) acc[j] = fmaf(__ldg(assign + (size_t)q * K + k0 + j), s, acc[j]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float v = (colok && j < kc) ? acc[j] : 0.f;
+      if (colok && j < kc) vlad[(size_t)(k0 + j) * D + col] = v;
+      const float sq = warp_sum(v * v);
+      if ((t & 31) == 0) red[t >> 5][j] = sq;
+    }
+    __syncthreads();
+    if (t < kc) {
+      float tot = 0.f;
+      for (int w = 0; w < ACC_COLS / 32; ++w) tot += red[w][t];
+      partial_ss[(size_t)(k0 + t) * nslices + slice] = tot;
+    }
+  }
+}
+
+}  // namespace anyloc
+
+extern "C" int anyloc_vlad_residuals(const float* feats, const float* centers, int N, int D, int K, int norm_descs,
+                                     float* out, void* stream) {
+  ANYLOC_REQUIRE(feats && centers && out, "vlad_residuals: null pointer");
+  ANYLOC_REQUIRE(N >= 0 && D > 0 && K > 0 && D % 4 == 0, "vlad_residuals: bad dims N=%d D=%d K=%d", N, D, K);
+  if (N == 0) return ANYLOC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(PC_VLAD, st, 4.0 * ((double)N * D + (double)K * D + (double)N * K * D));
+  vlad_residuals_kernel<<<N, 256, 0, st>>>(feats, centers, D, K, norm_descs, out);
+  ANYLOC_CHECK_LAUNCH();
+  return ANYLOC_OK;
+}
+
+extern "C" size_t anyloc_vlad_from_residuals_workspace_bytes(int D, int K) {
+  return align_up((size_t)K * cdiv(D, ACC_COLS) * 4, 256) + 256;
+}
+
+extern "C" int anyloc_vlad_from_residuals(const float* resid, const int32_t* labels, const float* assign, int N, int D,
+                                          int K, int intra_norm, float* vlad, void* ws, size_t ws_bytes, void* stream) {
+  ANYLOC_REQUIRE(resid && vlad && ws, "vlad_from_residuals: null pointer");
+  ANYLOC_REQUIRE((labels != nullptr) != (assign != nullptr), "vlad_from_residuals: pass labels (hard) OR assign (soft)");
+  ANYLOC_REQUIRE(N >= 0 && D > 0 && K > 0, "vlad_from_residuals: bad dims N=%d D=%d K=%d", N, D, K);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nslices = cdiv(D, ACC_COLS);
+  Workspace w(ws, ws_bytes);
+  float* partial = w.take<float>((size_t)K * nslices);
+  if (!partial) { set_error("vlad_from_residuals: workspace too small"); return ANYLOC_ERR_WORKSPACE; }
+  ProfScope ps(PC_VLAD, st, 4.0 * ((double)N * K * D + (double)K * D));
+  if (labels) vlad_from_residuals_hard_kernel<<<dim3(nslices, K), ACC_COLS, 0, st>>>(resid, labels, N, D, K, vlad, partial);
+  else vlad_from_residuals_soft_kernel<<<nslices, ACC_COLS, 0, st>>>(resid, assign, N, D, K, vlad, partial);
+  ANYLOC_CHECK_LAUNCH();
+  int ysplit = std::max(1, std::min(64, (int)(((size_t)K * D + 256 * 16 - 1) / (256 * 16))));
+  vlad_normalize_kernel<<<dim3(1, ysplit), 256, 2 * K * sizeof(float), st>>>(vlad, partial, D, K, nslices, intra_norm);
+  ANYLOC_CHECK_LAUNCH();
+  return ANYLOC_OK;
+}

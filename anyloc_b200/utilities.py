@@ -155,10 +155,13 @@ class DinoV2ExtractFeatures:
     its qkv projection), which is output-identical to the reference's full forward + hook.
     Extra keyword-only arguments: `weights` (an upstream state_dict, else see
     vit.resolve_state_dict), `gemm_engine` ("auto" | "tc3" | "simt") and `precision`: how fp32
-    operands are fed to the tensor cores -- "tf32x3" (tf32 (hi,lo) pairs, full fp32 exponent range)
-    or "f16x3" (fp16 (hi,lo) pairs with power-of-two scaling: same ~22-bit products on the 2x faster
+    operands are fed to the tensor cores -- "tf32x3" (tf32 (hi,lo) pairs, full fp32 exponent range),
+    "f16x3" (fp16 (hi,lo) pairs with power-of-two scaling: same ~22-bit products on the 2x faster
     kind::f16 path; operands beyond the fp16 range overflow to inf/NaN instead of losing accuracy
-    silently).  Both accumulate in fp32 with round-to-nearest chunk accumulation."""
+    silently, and the call raises) or "auto" (the default: f16x3 until a call overflows, then that
+    call is redone and the extractor stays in tf32x3 -- trained DINOv2 checkpoints have outlier
+    activations that random-init weights do not).  All accumulate in fp32 with round-to-nearest
+    chunk accumulation."""
 
     def __init__(self, dino_model: _DINO_V2_MODELS, layer: int, facet: _DINO_FACETS = "token",
                  use_cls=False, norm_descs=True, device: str = "cpu", *, weights=None,
@@ -170,12 +173,14 @@ class DinoV2ExtractFeatures:
             raise ValueError(f"facet must be one of {sorted(_lib.FACET)}, got {facet!r}")
         sd = weights if weights is not None else _vit.resolve_state_dict(dino_model, dev)
         # only blocks 0..layer are ever executed (early exit), so only those are uploaded
-        precision = precision or os.environ.get("ANYLOC_B200_PRECISION", "tf32x3")
-        if precision not in ("tf32x3", "f16x3"):
-            raise ValueError(f"precision must be 'tf32x3' or 'f16x3', got {precision!r}")
-        self.precision = precision
+        precision = precision or os.environ.get("ANYLOC_B200_PRECISION", "auto")
+        if precision not in ("tf32x3", "f16x3", "auto"):
+            raise ValueError(f"precision must be 'auto', 'tf32x3' or 'f16x3', got {precision!r}")
+        self._auto = precision == "auto"
+        self._state_dict = sd if self._auto else None     # kept for the tf32x3 re-upload on an fp16-range overflow
+        self.precision = "f16x3" if self._auto else precision
         self.dino_model = _vit.VitWeights(dino_model, sd, dev, depth=layer + 1,
-                                          pair="f16" if precision == "f16x3" else "tf32")
+                                          pair="f16" if self.precision == "f16x3" else "tf32")
         self.layer: int = layer
         self.facet = facet
         self.use_cls = use_cls
@@ -183,9 +188,49 @@ class DinoV2ExtractFeatures:
         self.gemm_engine = gemm_engine
         self.fh_handle = _HookHandle()
         self._hook_out = None
+        # fp16-range guard of the f16x3 format: "sync" = checked before __call__ returns (one host sync per call),
+        # "deferred" = the flag of call i is read at call i+1 / raise_if_overflowed() (no sync on the hot loop),
+        # "off".  precision="auto" always checks synchronously (it has to decide before returning).
+        self.check_finite = os.environ.get("ANYLOC_B200_CHECK_FINITE", "sync")
+        if self.check_finite in ("1", "0"):
+            self.check_finite = "sync" if self.check_finite == "1" else "off"
+        self._pending_flag = None
+
+    _OVERFLOW_MSG = ("f16x3 precision overflowed the fp16 operand range (|8*x| > 65504 somewhere in the network); "
+                     "construct the extractor with precision='tf32x3' (or 'auto')")
+
+    def raise_if_overflowed(self):
+        """Deferred mode: reads the finite-flag of the last call (one host sync)."""
+        flag, self._pending_flag = self._pending_flag, None
+        if flag is not None and not bool(flag):
+            raise _lib.AnylocError(self._OVERFLOW_MSG)
+
+    def _switch_to_tf32(self):
+        print("anyloc_b200: f16x3 operands overflowed the fp16 range -- switching this extractor to tf32x3 "
+              "(full fp32 exponent range, ~2x slower)")
+        dev, name = self.dino_model.device, self.dino_model.name
+        self.dino_model = None
+        torch.cuda.empty_cache()
+        self.dino_model = _vit.VitWeights(name, self._state_dict, dev, depth=self.layer + 1, pair="tf32")
+        self.precision, self._auto, self._state_dict = "tf32x3", False, None
 
     def __call__(self, img: torch.Tensor) -> torch.Tensor:
         with torch.no_grad():
+            if self.check_finite == "deferred" and not self._auto:
+                self.raise_if_overflowed()
+            out = self.dino_model.extract(img, self.layer, self.facet, self.use_cls, self.norm_descs,
+                                          self.gemm_engine)
+            if self.precision != "f16x3" or (self.check_finite == "off" and not self._auto):
+                return out
+            flag = torch.isfinite(out).all()
+            if self.check_finite == "deferred" and not self._auto:
+                self._pending_flag = flag
+                return out
+            if bool(flag):
+                return out
+            if not self._auto:
+                raise _lib.AnylocError(self._OVERFLOW_MSG)
+            self._switch_to_tf32()
             return self.dino_model.extract(img, self.layer, self.facet, self.use_cls, self.norm_descs,
                                            self.gemm_engine)
 
@@ -198,6 +243,15 @@ def _as_device_f32(x, device):
     if type(x) == np.ndarray:
         x = torch.from_numpy(x)
     return x.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def _normalize_rows_dev(x):
+    """F.normalize(x) of a device matrix [R,D] (utilities.py:782-783)."""
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().anyloc_l2_normalize_rows(_lib.ptr(x), x.shape[0], x.shape[1], x.shape[1],
+                                                        _lib.ptr(y), _lib.stream_ptr()), "l2_normalize_rows")
+    return y
 
 
 class _KMeans:
@@ -224,6 +278,20 @@ class _KMeans:
                        "anyloc_vlad_assign")
         return labels
 
+    def _update(self, x, labels, c):
+        """one Lloyd centroid update (anyloc_kmeans_update) -> (new centres, sum of squared centre shifts)"""
+        lib = _lib.load()
+        n, D = x.shape
+        K = c.shape[0]
+        new_c = torch.empty_like(c)
+        err = torch.zeros(1, device=x.device)
+        with torch.cuda.device(x.device):
+            ws = _lib.workspaces.get(x.device, lib.anyloc_vlad_workspace_bytes(1, 1, D, K), "kmeans_upd")
+            _lib.check(lib.anyloc_kmeans_update(_lib.ptr(x), _lib.ptr(labels), _lib.ptr(c), n, D, K,
+                                                _lib.ptr(new_c), _lib.ptr(err), _lib.ptr(ws), ws.numel(),
+                                                _lib.stream_ptr()), "anyloc_kmeans_update")
+        return new_c, float(err.item())
+
     def predict(self, X):
         dev = _lib.require_cuda(X.device if isinstance(X, torch.Tensor) and X.is_cuda else None)
         was_cpu = not (isinstance(X, torch.Tensor) and X.is_cuda)
@@ -241,20 +309,12 @@ class _KMeans:
             c = x[torch.from_numpy(init).to(dev)].contiguous()
         else:
             c = _as_device_f32(centroids, dev)
-        lib = _lib.load()
-        new_c = torch.empty_like(c)
-        err = torch.zeros(1, device=dev)
         labels = None
-        with torch.cuda.device(dev):
-            ws = _lib.workspaces.get(dev, lib.anyloc_vlad_workspace_bytes(1, 1, D, K), "kmeans_upd")
-            for _ in range(self.max_iter):
-                labels = self._assign(x, c)
-                _lib.check(lib.anyloc_kmeans_update(_lib.ptr(x), _lib.ptr(labels), _lib.ptr(c), n, D, K,
-                                                    _lib.ptr(new_c), _lib.ptr(err), _lib.ptr(ws), ws.numel(),
-                                                    _lib.stream_ptr()), "anyloc_kmeans_update")
-                c, new_c = new_c, c
-                if float(err.item()) <= self.tol:
-                    break
+        for _ in range(self.max_iter):
+            labels = self._assign(x, c)
+            c, err = self._update(x, labels, c)
+            if err <= self.tol:
+                break
         self.centroids = c.cpu() if was_cpu else c
         labels = labels.to(torch.int64)
         return labels.cpu() if was_cpu else labels
@@ -263,14 +323,22 @@ class _KMeans:
         self.fit_predict(X, centroids)
 
 
+VLAD_KERNEL_DESCRIPTION = ("VLAD v3: vlad_assign_tc_kernel (TMA + tcgen05 coarse scores + row norms) -> "
+                           "vlad_rescore_amb_kernel (ambiguous rows only) -> vlad_accumulate3_kernel (+ fused "
+                           "normalisation); prepared vocabulary, 3 launches")
+
+
 class VLAD:
     """Hard- and soft-assignment VLAD with the reference's constructor and methods (utilities.py:624-1008).
 
     `generate` / `generate_multi` take what the reference takes (CPU tensors / numpy arrays /
     ragged lists) and return what it returns (CPU tensors); CUDA tensors are also accepted and
-    then stay on the device (the batched fast path).  The on-disk vocabulary cache
-    (`c_centers.pt`) is honoured; the reference's per-image residual cache (`*_r.pt`, >=100 MB per
-    image) is neither read nor written.  `vlad_mode="soft"` follows the reference's soft branch
+    then stay on the device (the batched fast path).  The on-disk caches are honoured in the
+    reference's own file formats: the vocabulary (`c_centers.pt`), and per image the labels
+    (`<id>_l.pt`) / soft assignment (`<id>_s.pt`) and residual tensor (`<id>_r.pt`) are READ when
+    present; labels / soft assignments are written like the reference does, the residual tensor
+    (>=100 MB per image at ViT-G, K=32) only when `self.cache_residuals = True` or through
+    `generate_res_vec(..., cache_id)`.  `vlad_mode="soft"` follows the reference's soft branch
     (:862-887), including its summation over the residuals to all centres."""
 
     def __init__(self, num_clusters: int, desc_dim: Union[int, None] = None, intra_norm: bool = True,
@@ -288,6 +356,7 @@ class VLAD:
         self.kmeans = None
         self._centers_dev = {}
         self._prepared_dev = None
+        self.cache_residuals = False     # extension: write `<id>_r.pt` like the reference (104 MB per image at c2)
         self.cache_dir = cache_dir
         if self.cache_dir is not None:
             self.cache_dir = os.path.abspath(os.path.expanduser(self.cache_dir))
@@ -341,11 +410,7 @@ class VLAD:
         was_cpu = not train_descs.is_cuda
         x = _as_device_f32(train_descs, dev)
         if self.norm_descs:
-            y = torch.empty_like(x)
-            with torch.cuda.device(dev):
-                _lib.check(_lib.load().anyloc_l2_normalize_rows(_lib.ptr(x), x.shape[0], x.shape[1], x.shape[1],
-                                                                _lib.ptr(y), _lib.stream_ptr()), "l2_normalize_rows")
-            x = y
+            x = _normalize_rows_dev(x)
         self.kmeans.fit(x)
         self.c_centers = self.kmeans.centroids.cpu() if was_cpu else self.kmeans.centroids
         self.kmeans.centroids = self.c_centers
@@ -361,7 +426,8 @@ class VLAD:
 
     # -- device plumbing
     def _centers_on(self, dev):
-        key = (dev.index, id(self.c_centers))
+        cc = self.c_centers
+        key = (dev.index, id(cc), getattr(cc, "_version", None), cc.data_ptr() if isinstance(cc, torch.Tensor) else None)
         if key not in self._centers_dev:
             self._centers_dev = {key: _as_device_f32(self.c_centers, dev)}
         return self._centers_dev[key]
@@ -416,17 +482,105 @@ class VLAD:
         _lib.check(rc, "anyloc_vlad_generate_prepared")
         return out, labels
 
+    # -- per-image cache (utilities.py:843-852 labels, :864-878 soft assignment, :951-970 residuals)
+    def _cache_path(self, cache_id, suffix):
+        return f"{self.cache_dir}/{cache_id}_{suffix}.pt"
+
+    def _cache_active(self, cache_id):
+        return cache_id is not None and self.can_use_cache_vlad()
+
+    def _residuals_dev(self, x, dev):
+        """x [N,D] device fp32 -> residual tensor [N,K,D] on the device (anyloc_vlad_residuals)."""
+        centers = self._centers_on(dev)
+        N, D = x.shape
+        K = centers.shape[0]
+        if centers.shape[1] != D:
+            raise ValueError(f"cluster centres {tuple(centers.shape)} do not match descriptor dim {D}")
+        out = torch.empty(N, K, D, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().anyloc_vlad_residuals(_lib.ptr(x), _lib.ptr(centers), N, D, K,
+                                                         int(bool(self.norm_descs)), _lib.ptr(out), _lib.stream_ptr()),
+                       "anyloc_vlad_residuals")
+        return out
+
+    def _from_residuals_dev(self, resid, labels, assign, dev):
+        """descriptor [K*D] (device) of one image from its residual tensor + hard labels | soft assignment"""
+        lib = _lib.load()
+        N, K, D = resid.shape
+        out = torch.empty(K * D, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            ws = _lib.workspaces.get(dev, lib.anyloc_vlad_from_residuals_workspace_bytes(D, K), "vlad_cache")
+            _lib.check(lib.anyloc_vlad_from_residuals(_lib.ptr(resid), _lib.ptr(labels), _lib.ptr(assign), N, D, K,
+                                                      int(bool(self.intra_norm)), _lib.ptr(out), _lib.ptr(ws),
+                                                      ws.numel(), _lib.stream_ptr()), "anyloc_vlad_from_residuals")
+        return out
+
+    def _generate_cached(self, query_descs, cache_id, dev):
+        """The reference's cache-aware path, file for file: residuals from `<id>_r.pt` when present (else computed
+        from the features; written back only when `self.cache_residuals`), labels from `<id>_l.pt` / soft assignment
+        from `<id>_s.pt` when present (else computed AND saved, like the reference).  Files are CPU tensors in the
+        reference's own format, so a directory populated by either implementation serves both.  -> [K*D] device."""
+        suffix = "l" if self.vlad_mode == "hard" else "s"
+        have_r = os.path.isfile(self._cache_path(cache_id, "r"))
+        have_a = os.path.isfile(self._cache_path(cache_id, suffix))
+        x = None
+        if query_descs is not None:
+            x = _as_device_f32(query_descs, dev)
+        elif not (have_r and have_a):
+            raise ValueError(f"no descriptors given and the cache of {cache_id!r} is incomplete")
+        if not have_r and not have_a and not getattr(self, "cache_residuals", False):
+            # nothing cached yet: the fused fast path, keeping the assignment for the next run
+            out, assign = self._run(x.unsqueeze(0), None, dev, want_labels=True)
+            self._save_assignment(cache_id, suffix, assign[0])
+            return out[0]
+        if have_r:
+            resid = torch.load(self._cache_path(cache_id, "r")).to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            resid = self._residuals_dev(x, dev)
+            if getattr(self, "cache_residuals", False):
+                cid_dir = f"{self.cache_dir}/{os.path.split(cache_id)[0]}"
+                if not os.path.isdir(cid_dir):
+                    os.makedirs(cid_dir)
+                    print(f"Created directory: {cid_dir}")
+                torch.save(resid.cpu(), self._cache_path(cache_id, "r"))
+        if have_a:
+            assign = torch.load(self._cache_path(cache_id, suffix)).to(dev)
+        else:
+            _, assign = self._run(x.unsqueeze(0), None, dev, want_labels=True)
+            assign = assign[0]
+            self._save_assignment(cache_id, suffix, assign)
+        if self.vlad_mode == "hard":
+            return self._from_residuals_dev(resid, assign.to(torch.int32).contiguous(), None, dev)
+        return self._from_residuals_dev(resid, None, assign.to(torch.float32).contiguous(), dev)
+
+    def _save_assignment(self, cache_id, suffix, assign):
+        cid_dir = f"{self.cache_dir}/{os.path.split(cache_id)[0]}"
+        if not os.path.isdir(cid_dir):
+            os.makedirs(cid_dir)
+            print(f"Created directory: {cid_dir}")
+        # the reference stores kmeans.predict's int64 labels / the fp32 [q, c] soft assignment, on the CPU
+        a = assign.to(torch.int64) if suffix == "l" else assign
+        torch.save(a.cpu(), self._cache_path(cache_id, suffix))
+
     # -- descriptors (utilities.py:819-926)
-    def generate(self, query_descs: Union[np.ndarray, torch.Tensor], cache_id: Union[str, None] = None) \
+    def generate(self, query_descs: Union[np.ndarray, torch.Tensor, None], cache_id: Union[str, None] = None) \
             -> torch.Tensor:
         on_dev = isinstance(query_descs, torch.Tensor) and query_descs.is_cuda
         dev = _lib.require_cuda(query_descs.device if on_dev else None)
+        if self._cache_active(cache_id):
+            out = self._generate_cached(query_descs, cache_id, dev)
+            return out if on_dev else out.cpu()
         x = _as_device_f32(query_descs, dev)
         out, _ = self._run(x.unsqueeze(0), None, dev)
         return out[0] if on_dev else out[0].cpu()
 
     def generate_multi(self, multi_query: Union[np.ndarray, torch.Tensor, list],
                        cache_ids: Union[List[str], None] = None) -> Union[torch.Tensor, list]:
+        if cache_ids is not None and self.can_use_cache_vlad() and any(c is not None for c in cache_ids):
+            # cache-aware: image by image like the reference (:917-918); `multi_query` may be [None] * n when
+            # can_use_cache_ids() said the cache is complete (scripts/dino_v2_vlad.py:224-228)
+            res = [self.generate(q, c) for (q, c) in zip(multi_query, cache_ids)]
+            return torch.stack(res)
         if isinstance(multi_query, (list, tuple)):
             if len(multi_query) == 0:
                 return torch.stack([])      # same failure as the reference on an empty list
@@ -444,31 +598,44 @@ class VLAD:
         was_np = type(multi_query) == np.ndarray
         on_dev = isinstance(multi_query, torch.Tensor) and multi_query.is_cuda
         dev = _lib.require_cuda(multi_query.device if on_dev else None)
-        if not on_dev and not was_np and multi_query.numel() * 4 > (1 << 30):
+        if not on_dev and not was_np and multi_query.numel() * 4 > self._host_chunk_bytes:
             # large host batches (the driver hands over [n_imgs, n_patches, D] on the CPU): stream chunks
-            step = max(1, (1 << 30) // (multi_query[0].numel() * 4))
+            step = max(1, self._host_chunk_bytes // (multi_query[0].numel() * 4))
             return torch.cat([self._run(_as_device_f32(multi_query[i:i + step], dev), None, dev)[0].cpu()
                               for i in range(0, multi_query.shape[0], step)])
         out, _ = self._run(_as_device_f32(multi_query, dev), None, dev)
         return out if on_dev else out.cpu()
 
-    # -- residual tensors (utilities.py:928-1008); off the hot path, plain tensor algebra
+    _host_chunk_bytes = 1 << 30
+
+    # -- residual tensors (utilities.py:928-1008)
     def generate_res_vec(self, query_descs: Union[np.ndarray, torch.Tensor],
                          cache_id: Union[str, None] = None) -> torch.Tensor:
         assert self.kmeans is not None
         assert self.c_centers is not None
-        if type(query_descs) == np.ndarray:
-            query_descs = torch.from_numpy(query_descs).to(torch.float32)
-        if self.norm_descs:
-            query_descs = torch.nn.functional.normalize(query_descs)
-        return query_descs[:, None, :] - self.c_centers.to(query_descs.device)[None, :, :]
+        if self._cache_active(cache_id) and os.path.isfile(self._cache_path(cache_id, "r")):
+            return torch.load(self._cache_path(cache_id, "r"))
+        on_dev = isinstance(query_descs, torch.Tensor) and query_descs.is_cuda
+        dev = _lib.require_cuda(query_descs.device if on_dev else None)
+        resid = self._residuals_dev(_as_device_f32(query_descs, dev), dev)
+        resid = resid if on_dev else resid.cpu()
+        if self._cache_active(cache_id):           # explicit request for the residual tensor: cache it as the reference does
+            cid_dir = f"{self.cache_dir}/{os.path.split(cache_id)[0]}"
+            if not os.path.isdir(cid_dir):
+                os.makedirs(cid_dir)
+                print(f"Created directory: {cid_dir}")
+            torch.save(resid.cpu(), self._cache_path(cache_id, "r"))
+        return resid
 
-    def generate_multi_res_vec(self, multi_query, cache_ids=None):
-        res = [self.generate_res_vec(q) for q in multi_query]
+    def generate_multi_res_vec(self, multi_query: Union[np.ndarray, torch.Tensor, list],
+                               cache_ids: Union[List[str], None] = None) -> Union[torch.Tensor, list]:
+        if cache_ids is None:
+            cache_ids = [None] * len(multi_query)
+        res = [self.generate_res_vec(q, c) for (q, c) in zip(multi_query, cache_ids)]
         try:
             return torch.stack(res)
         except (TypeError, RuntimeError):
-            return res
+            return res              # ragged inputs stay a list
 
 
 # ------------------------------------------------------------------ sibling aggregators (extension)
@@ -495,30 +662,98 @@ def pool_descriptors(patch_descs: torch.Tensor, method: str = "gem", gem_p: floa
 
 
 # ------------------------------------------------------------------ retrieval
+TOPK_KERNEL_DESCRIPTION = ("retrieval score GEMM: gemm_tc3_2cta_kernel<true, BIAS> (tcgen05 cta_group::2, fp16 pairs of the "
+                           "unit rows, 3-term split, fp32 RN chunk accumulation) over a prepared database index, then "
+                           "topk_select2_kernel (one pass + candidate list)")
+
+
+class FlatIndex:
+    """GPU stand-in for `faiss.IndexFlatIP` / `IndexFlatL2` as get_top_k_recall drives them (utilities.py:439-450):
+    `add(db)` normalises the rows (when `norm_descs`) and stores them once as the operand pairs of the score GEMM
+    (anyloc_index_add); `search(qu, k)` is exact -- k best per query, best first, lowest database index first among
+    equal scores.  Rows may be added in chunks (e.g. descriptor batches as they leave the all-gather)."""
+
+    def __init__(self, d: int, method: str = "cosine", norm_descs: bool = True, capacity: int = 0, device=None):
+        if method not in _lib.METRIC:
+            raise NotImplementedError(f"Method: {method}")
+        self.d, self.method, self.norm_descs = int(d), method, bool(norm_descs)
+        self.dp = self.d + (-self.d) % 4            # zero columns change neither norms nor scores
+        self.ntotal, self.capacity = 0, 0
+        self._blob, self._dev = None, (torch.device(device) if device is not None else None)
+        if capacity:
+            self._reserve(int(capacity), _lib.require_cuda(self._dev))
+
+    def _reserve(self, capacity, dev):
+        lib = _lib.load()
+        blob = torch.empty(lib.anyloc_index_bytes(capacity, self.dp, int(self.norm_descs)), dtype=torch.uint8, device=dev)
+        if self.ntotal:         # growth: re-pack the used rows of the three sections into the larger blob
+            for (o_old, per_row), (o_new, _) in zip(self._sections(self.capacity), self._sections(capacity)):
+                blob[o_new:o_new + per_row * self.ntotal].copy_(self._blob[o_old:o_old + per_row * self.ntotal])
+        self._blob, self.capacity, self._dev = blob, capacity, dev
+
+    def _sections(self, cap):
+        """(byte offset, bytes per row) of the hi, lo and |y|^2 sections of a blob of `cap` rows (csrc/topk.cu)."""
+        f16 = self.norm_descs and self.dp % 8 == 0 and os.environ.get("ANYLOC_TOPK_F16", "1") != "0"
+        per_row = self.dp * (2 if f16 else 4)
+        pair = (cap * per_row + 255) // 256 * 256
+        return [(0, per_row), (pair, per_row), (2 * pair, 4)]
+
+    def add(self, x: Union[np.ndarray, torch.Tensor]):
+        on_dev = isinstance(x, torch.Tensor) and x.is_cuda
+        dev = _lib.require_cuda(x.device if on_dev else self._dev)
+        n = x.shape[0]
+        if x.shape[1] != self.d:
+            raise ValueError(f"index dimension {self.d}, got rows of {x.shape[1]}")
+        if self.ntotal + n > self.capacity:
+            self._reserve(max(self.ntotal + n, 2 * self.capacity if self.ntotal else 0), dev)
+        lib = _lib.load()
+        # host rows are streamed in chunks of <= 1 GiB so that no second full copy of the database sits in HBM
+        step = n if on_dev else max(1, (1 << 30) // (self.dp * 4))
+        with torch.cuda.device(dev):
+            for i in range(0, n, step):
+                rows = _as_device_f32(x[i:i + step], dev)
+                if self.dp != self.d:
+                    rows = torch.nn.functional.pad(rows, (0, self.dp - self.d))
+                _lib.check(lib.anyloc_index_add(_lib.ptr(self._blob), self._blob.numel(), self.capacity,
+                                                self.ntotal + i, _lib.ptr(rows), rows.shape[0], self.dp,
+                                                int(self.norm_descs), _lib.stream_ptr()), "anyloc_index_add")
+        self.ntotal += n
+
+    def search(self, qu: Union[np.ndarray, torch.Tensor], k: int, n_q_chunk: int = 4096):
+        if self.ntotal == 0:
+            raise ValueError("search on an empty index")
+        on_dev = isinstance(qu, torch.Tensor) and qu.is_cuda
+        dev = self._dev
+        q = _as_device_f32(qu, dev)
+        if self.dp != self.d:
+            q = torch.nn.functional.pad(q, (0, self.dp - self.d))
+        lib = _lib.load()
+        n_q = q.shape[0]
+        dist = torch.empty(n_q, k, device=dev, dtype=torch.float32)
+        idx = torch.empty(n_q, k, device=dev, dtype=torch.int64)
+        with torch.cuda.device(dev):
+            for i in range(0, n_q, n_q_chunk):          # bounds the [n_q, n_db] score matrix
+                m = min(n_q_chunk, n_q - i)
+                ws = _lib.workspaces.get(dev, lib.anyloc_index_search_workspace_bytes(self.ntotal, m, self.dp,
+                                                                                     int(self.norm_descs)), "topk")
+                rc = lib.anyloc_index_search(_lib.ptr(self._blob), self._blob.numel(), self.capacity, self.ntotal,
+                                             _lib.ptr(q[i:i + m]), m, self.dp, k, _lib.METRIC[self.method],
+                                             int(self.norm_descs), _lib.ptr(dist[i:i + m]), _lib.ptr(idx[i:i + m]),
+                                             _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+                _lib.check(rc, "anyloc_index_search")
+        return (dist, idx) if on_dev else (dist.cpu(), idx.cpu())
+
+
 def top_k_search(db: torch.Tensor, qu: torch.Tensor, k: int, method: str = "cosine",
                  norm_descs: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Exact k-nearest search on the GPU (the `faiss.IndexFlatIP/L2.search` part of
-    get_top_k_recall, utilities.py:435-450).  Device tensors in, device tensors out."""
+    """Exact k-nearest search on the GPU (the `faiss.IndexFlatIP/L2` `add` + `search` of get_top_k_recall,
+    utilities.py:435-450).  Device tensors in, device tensors out."""
     if method not in _lib.METRIC:
         raise NotImplementedError(f"Method: {method}")
     dev = _lib.require_cuda(db.device)
-    lib = _lib.load()
-    n_db, Dv = db.shape
-    n_q = qu.shape[0]
-    pad = (-Dv) % 4
-    if pad:     # zero columns change neither norms nor scores
-        db = torch.nn.functional.pad(db, (0, pad))
-        qu = torch.nn.functional.pad(qu, (0, pad))
-        Dv += pad
-    dist = torch.empty(n_q, k, device=dev, dtype=torch.float32)
-    idx = torch.empty(n_q, k, device=dev, dtype=torch.int64)
-    with torch.cuda.device(dev):
-        ws = _lib.workspaces.get(dev, lib.anyloc_topk_workspace_bytes(n_db, n_q, Dv, k), "topk")
-        rc = lib.anyloc_topk(_lib.ptr(db), _lib.ptr(qu), n_db, n_q, Dv, k, _lib.METRIC[method],
-                             int(bool(norm_descs)), _lib.ptr(dist), _lib.ptr(idx), _lib.ptr(ws), ws.numel(),
-                             _lib.stream_ptr())
-    _lib.check(rc, "anyloc_topk")
-    return dist, idx
+    index = FlatIndex(db.shape[1], method, norm_descs, capacity=db.shape[0], device=dev)
+    index.add(db)
+    return index.search(qu.to(dev), k)
 
 
 def get_top_k_recall(top_k: List[int], db: torch.Tensor, qu: torch.Tensor, gt_pos: np.ndarray,
@@ -536,8 +771,9 @@ def get_top_k_recall(top_k: List[int], db: torch.Tensor, qu: torch.Tensor, gt_po
         qu = qu.unsqueeze(0)
     on_dev = db.is_cuda
     dev = _lib.require_cuda(db.device if on_dev else None)
-    distances, indices = top_k_search(_as_device_f32(db, dev), _as_device_f32(qu, dev), max(top_k), method,
-                                      norm_descs)
+    index = FlatIndex(db.shape[1], method, norm_descs, capacity=db.shape[0], device=dev)
+    index.add(db)                                   # host rows are streamed in <= 1 GiB chunks
+    distances, indices = index.search(_as_device_f32(qu, dev), max(top_k))
     idx_host = indices.cpu().numpy()
     recalls = dict(zip(top_k, [0] * len(top_k)))
     for i_qu, qu_retr in enumerate(idx_host):

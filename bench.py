@@ -1,14 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- images/s of the DINOv2 -> hard-VLAD descriptor pipeline (BASELINE.json metric).
+"""bench.py -- the BASELINE.json metric (images/s of the DINOv2 -> hard-VLAD descriptor pipeline) plus the
+retrieval configurations, on N GPUs of one node.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+    python bench.py --gpus N --steps K --warmup W                  # this repo (CUDA, sm_100a), workload c2
+    python bench.py --impl reference --gpus N --steps K ...         # the reference's CPU path (oracle port)
+    python bench.py --workload c3|c4 ...                            # retrieval: 10k / 100k-image database, 1k queries
 
-A step = one pass of the hot path over one batch of synthetic images per GPU:
-DinoV2ExtractFeatures.__call__ (ViT forward, early exit at the hooked layer) -> VLAD.generate_multi.
-Workload at N=1 is BASELINE.json configs[1]: ViT-G/14 layer-31 'value', 322x322, K=32, batch 32.
-Under torchrun (N>1) every rank runs the same per-GPU batch on its own images (weak scaling, no
-data-path collective inside the step; the descriptor all-gather belongs to the retrieval configs).
+Pipeline workloads (c1 / c2 / c5).  A step = one pass of the hot path over one batch of synthetic images per
+GPU -- DinoV2ExtractFeatures.__call__ (ViT forward, early exit at the hooked layer) -> VLAD.generate_multi --
+followed by the pipeline's one data-path collective: the all-gather of that batch's [B, K*D] descriptors into the
+database every rank keeps for retrieval (BASELINE config 4: "NCCL all-gather of the 49152-D descriptors before
+top-k"; scripts/dino_v2_vlad.py:219-264 builds the database VLADs, utilities.py:435-450 searches them).  The
+all-gather of step i is enqueued asynchronously and overlaps the ViT of step i+1; the timed region ends when every
+gather has landed.  N=1: the gather degenerates to the copy into the database buffer.  Weak scaling: per-GPU batch
+fixed.  After the timed loops the gathered database is checked bitwise against the local descriptors and searched
+with both sharded top-k strategies (anyloc_b200/dist.py).
+
+Retrieval workloads (c3 / c4).  A step = descriptor all-gather (c4) + database index build + 1k-query top-5
+search, queries sharded over the ranks, results gathered.
+
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -24,15 +34,21 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    "c1": dict(model="dinov2_vits14", layer=9, facet="value", H=224, W=224, K=8, B=16,
+    "c1": dict(kind="pipeline", model="dinov2_vits14", layer=9, facet="value", H=224, W=224, K=8, B=16,
                name="c1: ViT-S/14 layer-9 value, 224x224, K=8 VLAD, batch 16"),
-    "c2": dict(model="dinov2_vitg14", layer=31, facet="value", H=322, W=322, K=32, B=32,
+    "c2": dict(kind="pipeline", model="dinov2_vitg14", layer=31, facet="value", H=322, W=322, K=32, B=32,
                name="c2: ViT-G/14 layer-31 value, 322x322, K=32 VLAD, batch 32"),
-    "c5": dict(model="dinov2_vitl14", layer=20, facet="value", H=518, W=518, K=128, B=64,
+    "c5": dict(kind="pipeline", model="dinov2_vitl14", layer=20, facet="value", H=518, W=518, K=128, B=64,
                name="c5: ViT-L/14 layer-20 value, 518x518, K=128 VLAD, batch 64"),
+    "c3": dict(kind="retrieval", n_db_per_rank=10000, n_q=1000, Dv=49152, k=5,
+               name="c3: 10k-image database of 49152-D (ViT-G K=32) VLADs, 1k-query cosine top-5, 1 GPU"),
+    "c4": dict(kind="retrieval", n_db_per_rank=12500, n_q=1000, Dv=49152, k=5,
+               name="c4: 12.5k-image database shard per GPU (100k images at 8 GPUs) of 49152-D VLADs, NCCL all-gather, "
+                    "1k-query cosine top-5"),
 }
 METRIC = "images/sec end-to-end DINOv2-VLAD descriptors"
 UNIT = "images/s"
+NVLINK_GBS_PER_DIR = 900.0      # B200 NVLink 5 per GPU per direction (B200_PROFILING.md / task statement)
 
 
 def vit_flops_per_image(model, layer, H, W):
@@ -73,6 +89,38 @@ def usable_cores():
         except Exception:
             pass
     return n
+
+
+def ncu_traffic(kernel_substr, tag=None):
+    """DRAM bytes (read + write) per launch of the kernels whose name contains `kernel_substr`, from the committed
+    `ncu --set full ... --page raw --csv` exports under profiles/ (newest round first).  -> (bytes, file) or (None, None)."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*raw*.csv")), reverse=True)
+    for path in files:
+        if tag and tag not in os.path.basename(path):
+            continue
+        try:
+            rows = list(csv.reader(open(path, newline="")))
+        except Exception:
+            continue
+        hdr = next((i for i, r in enumerate(rows) if "Kernel Name" in r), None)
+        if hdr is None:
+            continue
+        h = rows[hdr]
+        try:
+            kn, rd, wr = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+        except ValueError:
+            continue
+        units = rows[hdr + 1] if len(rows) > hdr + 1 else []
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+        def val(r, c):
+            return float(r[c].replace(",", "")) * scale.get(units[c] if c < len(units) else "byte", 1.0)
+        vals = [val(r, rd) + val(r, wr) for r in rows[hdr + 2:] if len(r) > max(kn, rd, wr) and kernel_substr in r[kn]]
+        if vals:
+            return sum(vals) / len(vals), os.path.relpath(path, ROOT)
+    return None, None
 
 
 class ClockSampler:
@@ -116,18 +164,27 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ reference arm / cpu baseline
+_REF_MODELS = {}
+
+
+def _ref_model(name, seed=0):
+    """the restated hub model with ALL blocks (the reference runs them all), built once per process"""
+    from oracle import dinov2_restated as dr
+    if (name, seed) not in _REF_MODELS:
+        _REF_MODELS[(name, seed)] = dr.build(name, seed=seed)
+    return _REF_MODELS[(name, seed)]
+
+
 def cpu_reference(wl, n_images, steps, warmup, seed=0):
     """The reference's own CPU path, restated (oracle/): per image, batch 1, the FULL model forward
     with the facet hook (scripts/dino_v2_vlad.py:164-188 -> utilities.py:263-285), then
     VLAD.generate per image with the [N,K,D] residual tensor (utilities.py:819-890, :956-962).
     Returns (images_per_s, ms_per_step, cores)."""
-    import numpy as np
     import torch
     from oracle import anyloc_oracle as ao
-    from oracle import dinov2_restated as dr
     cores = usable_cores()
     torch.set_num_threads(cores)
-    model = dr.build(wl["model"], seed=seed)                 # all blocks: the reference runs them all
+    model = _ref_model(wl["model"], seed)
     D = model.embed_dim
     g = torch.Generator().manual_seed(1234)
     imgs = torch.randn(n_images, 3, wl["H"], wl["W"], generator=g)
@@ -147,9 +204,47 @@ def cpu_reference(wl, n_images, steps, warmup, seed=0):
     return n_images * steps / dt, dt / steps * 1e3, cores
 
 
+def gpu_reference(wl, n_images, seed=0):
+    """The north star's 10x denominator -- 'the reference GPU PyTorch path' on this GPU: the loop of
+    scripts/dino_v2_vlad.py:164-188,233-237 with the restated hub model .cuda() in fp32 (TF32 off, as torch's
+    defaults), ONE image per forward (all blocks + hook), `.cpu()` per image, then the CPU VLAD.generate per image
+    (oracle restatement with the [N,K,D] residuals).  torch / cuBLAS kernels only -- none of this repo's.
+    Returns (images_per_s, ms_per_image_vit_part)."""
+    import torch
+    from oracle import anyloc_oracle as ao
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.set_num_threads(usable_cores())
+    model = _ref_model(wl["model"], seed).cuda()
+    try:
+        g = torch.Generator().manual_seed(1234)
+        imgs = torch.randn(n_images, 3, wl["H"], wl["W"], generator=g)
+        centers = 0.6 * torch.nn.functional.normalize(torch.randn(wl["K"], model.embed_dim, generator=g), dim=1)
+
+        def path(n, vlad=True):
+            feats = [ao.extract_features_full_forward(model, imgs[i:i + 1].cuda(), wl["layer"], wl["facet"]).cpu()
+                     for i in range(n)]
+            return torch.stack([ao.vlad_generate_faithful(f, centers) for f in torch.cat(feats)]) if vlad else None
+
+        path(2)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        path(n_images)
+        torch.cuda.synchronize(); t_all = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        path(n_images, vlad=False)
+        torch.cuda.synchronize(); t_vit = time.perf_counter() - t0
+    finally:
+        model.cpu()
+        torch.cuda.empty_cache()
+    return n_images / t_all, t_vit / n_images * 1e3
+
+
 def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if wl["kind"] != "pipeline":
+        print(json.dumps({"impl": "reference", "unavailable": "the reference arm times the descriptor pipeline (c1/c2/c5) only"}))
         return
     n = args.ref_images
     ips, ms, cores = cpu_reference(wl, n, args.steps, max(args.warmup, 1))
@@ -164,29 +259,91 @@ def run_reference_arm(args, wl):
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------ this repo
-def run_ours(args, wl):
+# ------------------------------------------------------------------ shared plumbing of our arms
+class Ranks:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (anyloc_b200 has no CPU fallback); use --impl reference")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_ms(self, ms):
+        if self.world == 1:
+            return ms
+        t = self.torch.tensor([ms], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(self, flag):
+        if self.world == 1:
+            return bool(flag)
+        t = self.torch.tensor([1 if flag else 0], device=self.dev, dtype=self.torch.int32)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def timed(self, fn, steps):
+        """barrier + synchronize on both sides, CUDA events on the current stream, max over ranks -> total ms"""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        self.barrier()
+        return self.max_ms(e0.elapsed_time(e1))
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def collective_alone(R, shape, iters=10):
+    """the step's all-gather timed on its own: -> (us per call, bus GB/s per rank = received bytes / time)"""
+    torch, dist = R.torch, R.dist
+    if R.world == 1:
+        return None, None
+    src = torch.randn(*shape, device=R.dev)
+    dst = torch.empty((R.world * shape[0],) + tuple(shape[1:]), device=R.dev)
+    for _ in range(3):
+        dist.all_gather_into_tensor(dst, src)
+    ms = R.timed(lambda i: dist.all_gather_into_tensor(dst, src), iters) / iters
+    recv = (R.world - 1) * src.numel() * 4
+    return ms * 1e3, recv / (ms / 1e3) / 1e9
+
+
+# ------------------------------------------------------------------ descriptor pipeline (c1 / c2 / c5)
+def run_pipeline(args, wl):
     import numpy as np
-    import torch
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (anyloc_b200 has no CPU fallback); use --impl reference")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    from anyloc_b200 import _lib, utilities as u
+    R = Ranks()
+    torch, dist, dev, world, rank = R.torch, R.dist, R.dev, R.world, R.rank
+    from anyloc_b200 import _lib, dist as adist, utilities as u
     from anyloc_b200.vit import random_state_dict, ARCHS
 
     B, H, W, K = wl["B"], wl["H"], wl["W"], wl["K"]
     D = ARCHS[wl["model"]][0]
+    Dv = K * D
     sd = random_state_dict(wl["model"], seed=0, device=dev, depth=wl["layer"] + 1)
     ext = u.DinoV2ExtractFeatures(wl["model"], wl["layer"], wl["facet"], device=dev, weights=sd,
                                   gemm_engine=args.engine, precision=args.precision)
+    ext.check_finite = "deferred"            # fp16-range guard without a host sync per call; checked after the loops
+    sd_host = None
+    if rank == 0 and world == 1 and not args.no_parity_check:
+        sd_host = {k: v.cpu() for k, v in sd.items()}
     del sd
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     img_dev = torch.randn(B, 3, H, W, device=dev, generator=g)
@@ -196,66 +353,108 @@ def run_ours(args, wl):
     vlad = u.VLAD(K)
     if args.vocab == "fit":
         vlad.fit(feats.reshape(-1, D))      # vocabulary on this batch's features (GPU k-means)
+        if world > 1:                       # replicated vocabulary: rank 0's
+            c = vlad.c_centers.contiguous()
+            dist.broadcast(c, 0)
+            vlad.c_centers = vlad.kmeans.centroids = c
     else:                                   # profiling runs: skip the k-means launches
         vlad.kmeans = u._KMeans(K, mode="cosine")
         idx = torch.randperm(feats.shape[0] * feats.shape[1], device=dev, generator=g)[:K]
         vlad.c_centers = vlad.kmeans.centroids = 0.7 * feats.reshape(-1, D)[idx].contiguous()
         vlad.desc_dim = D
-    out_host = [torch.empty(B, K * D, dtype=torch.float32).pin_memory() for _ in range(2)]
+    del feats
+    out_host = [torch.empty(B, Dv, dtype=torch.float32).pin_memory() for _ in range(2)]
+    # the database every rank keeps for retrieval: a ring of the last SLOTS gathered step chunks [world*B, Dv]
+    SLOTS = 4
+    db_ring = torch.zeros(SLOTS, world * B, Dv, device=dev)
+    pending = []
 
-    def step_device():
-        return vlad.generate_multi(ext(img_dev))
+    def gather(desc, i):
+        """the pipeline's one collective: this step's [B, Dv] descriptors of every rank -> database chunk i"""
+        slot = db_ring[i % SLOTS]
+        if world == 1:
+            slot.copy_(desc)
+            return
+        while len(pending) >= SLOTS - 1:      # chunk i reuses the slot of chunk i - SLOTS: that gather must be done
+            pending.pop(0).wait()
+        pending.append(dist.all_gather_into_tensor(slot, desc, async_op=True))
+
+    def drain():
+        while pending:
+            pending.pop(0).wait()
+
+    def step_device(i):
+        desc = vlad.generate_multi(ext(img_dev))
+        gather(desc, i)
+        return desc
 
     def step_e2e(i):
         x = img_host.to(dev, non_blocking=True)                    # H2D of this step's inputs
-        out_host[i & 1].copy_(vlad.generate_multi(ext(x)), non_blocking=True)   # D2H of the result
+        desc = vlad.generate_multi(ext(x))
+        gather(desc, i)
+        out_host[i & 1].copy_(desc, non_blocking=True)             # D2H of the result
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+    def loop(fn):
+        def body(i):
+            fn(i)
+            if i == loop.n - 1:
+                drain()                                             # every gather has landed inside the timed region
+        return body
 
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    sampler = ClockSampler(local_rank)
+    for i in range(args.warmup):
+        step_device(i)
+    drain()
+    sampler = ClockSampler(R.local)
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
-    _lib.profile_enable(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step_device()
-    e1.record()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    prof = _lib.profile_read()
-    _lib.profile_enable(False)
+    loop.n = args.steps
+    ms_total = R.timed(loop(step_device), args.steps)               # un-instrumented: this is `value`
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
     # end-to-end through the public API with host buffers (pinned), copies inside the timed region
     for i in range(max(1, args.warmup // 2)):
         step_e2e(i)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        step_e2e(i)
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    drain()
+    ms_e2e = R.timed(loop(step_e2e), args.steps)
+
+    # separate instrumented pass (a cudaEvent pair per launch group): time shares and the kernels' live durations
+    n_prof = min(args.steps, 3)
+    _lib.profile_enable(True)
+    loop.n = n_prof
+    ms_prof = R.timed(loop(step_device), n_prof)
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    ext.raise_if_overflowed()
+
+    # ---- checks after the timed loops (untimed)
+    desc = step_device(0)
+    drain()
+    torch.cuda.synchronize()
+    chk = {"allgather_bitwise": R.all_true(torch.equal(db_ring[0, rank * B:(rank + 1) * B], desc))}
+    for i in range(1, SLOTS):
+        step_device(i)
+    drain()
+    db_all = db_ring.reshape(-1, Dv)
+    # queries: noisy copies of this rank's rows of chunk 0 -> the global index of the source row is known
+    nq_loc = 4
+    qn = torch.randn(nq_loc, Dv, device=dev, generator=g)
+    qu_loc = desc[:nq_loc] + 0.1 * qn / qn.norm(dim=1, keepdim=True)
+    truth = torch.arange(nq_loc, device=dev) + rank * B
+    res = {}
+    for strategy in ("gather_db", "gather_queries"):
+        s, e = adist.shard_range(db_all.shape[0])
+        d_, i_ = adist.sharded_top_k(db_all[s:e].contiguous(), qu_loc, 3, strategy=strategy)
+        res[strategy] = (d_, i_)
+    i_db = res["gather_db"][1]
+    chk["topk_strategies_equal"] = R.all_true(torch.equal(i_db, res["gather_queries"][1]))
+    # identical images every step -> chunks 1..3 hold duplicates of chunk 0's rows; the lowest index must win
+    chk["top1_is_source_row"] = R.all_true(torch.equal(i_db[rank * nq_loc:(rank + 1) * nq_loc, 0], truth))
+    coll_us, coll_gbs = collective_alone(R, (B, Dv))
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        R.finish()
         return
     peaks = measured_peaks()
     ms_step = ms_total / args.steps
@@ -263,68 +462,245 @@ def run_ours(args, wl):
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     g_ms, g_n, g_fl = prof["gemm_tc"]
     flops_img = vit_flops_per_image(wl["model"], wl["layer"], H, W)
+    f16 = ext.precision == "f16x3"
     roof = None
     if g_n:
         ach = g_fl / (g_ms / 1e3) / 1e12
-        f16 = args.precision == "f16x3"
         passes = 3.0 if f16 else 6.0       # bf16-rate-equivalent tensor passes per algorithmic product
         two_cta = os.environ.get("ANYLOC_GEMM_2CTA", "1") != "0"
         kname = ("gemm_tc3_2cta_kernel<%s> (tcgen05 cta_group::2 M256xN256, kind::%s" if two_cta else
                  "gemm_tc3_kernel<256,%s> (tcgen05 cta_group::1 M128xN256, kind::%s") % (
                      "true" if f16 else "false", "f16" if f16 else "tf32")
-        # DRAM bytes per launch of this kernel from the committed ncu --set full capture of the same command
-        # (profiles/r01_ncu_summary.md, "Final state": mean over the four per-block GEMMs w3/qkv/proj/w12); only
-        # valid for the configuration that was captured
-        traffic = 617.5e6 if (args.workload == "c2" and f16 and two_cta) else None
+        traffic, tsrc = (ncu_traffic("gemm_tc3_2cta_kernel", "gemm") if (args.workload == "c2" and f16 and two_cta)
+                         else (None, None))
         roof = {"kernel": kname + ", 3-term split, fp32 accumulate, RN chunk accumulation)",
                 "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tflops_sustained"], "traffic": traffic,
-                "traffic_source": "profiles/r01_ncu_summary.md (ncu --set full, dram__bytes_read+write per launch)" if traffic else None,
-                "algorithmic_bytes_per_launch": 425.5e6 if traffic else None,
+                "frac": ach / peaks["tflops_sustained"], "traffic": traffic, "traffic_source": tsrc,
+                "algorithmic_flops_per_launch": g_fl / g_n,
                 "peak_source": f"{peaks['source']} cuBLAS bf16 sustained (MEASURED_PEAKS.json)",
-                "note": "achieved = algorithmic 2MNK FLOPs / device time; the engine issues 3 MMAs per product "
-                        "(fp32-equivalent accuracy) at %s the bf16 rate, i.e. %d bf16-equivalent passes"
+                "contract_ceiling": 1.0 / passes,
+                "note": "achieved = algorithmic 2MNK FLOPs / live device time of the launches (CUDA events, separate "
+                        "instrumented pass); fp32-equivalent results need 3 MMAs per product at %s the bf16 rate = %d "
+                        "bf16-equivalent passes, so frac <= contract_ceiling on this precision contract; "
+                        "frac / contract_ceiling estimates the tensor-pipe utilisation"
                         % ("1x" if f16 else "0.5x", int(passes)),
                 "tensor_pipe_frac_est": passes * ach / peaks["tflops_sustained"],
-                "launches": g_n, "avg_launch_ms": g_ms / g_n, "share_of_step": g_ms / ms_total}
+                "launches": g_n, "avg_launch_ms": g_ms / g_n, "share_of_step": g_ms / ms_prof}
     v_ms, v_n, v_bytes = prof["vlad"]
     vroof = None
     if v_n:
         gbs = v_bytes / (v_ms / 1e3) / 1e9
-        vroof = {"kernel": "VLAD v3: vlad_assign_tc_kernel (TMA + tcgen05 coarse scores + row norms) -> "
-                           "vlad_rescore_amb_kernel (ambiguous rows only) -> vlad_accumulate3_kernel (+ fused "
-                           "normalisation); prepared vocabulary, 3 launches",
-                 "bound": "hbm", "achieved": gbs,
-                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                 # ncu --set full, c2 shape (profiles/r01_vlad_v3.md): DRAM read+write of the three launches
-                 "traffic": 235.0e6 if args.workload == "c2" else None,
+        vtraffic, vsrc = ncu_traffic("vlad_", "vlad_" + args.workload)
+        vroof = {"kernel": u.VLAD_KERNEL_DESCRIPTION,
+                 "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                 "traffic": vtraffic, "traffic_source": vsrc,
                  "algorithmic_bytes_per_launch_group": v_bytes / v_n,
-                 "avg_launch_ms": v_ms / v_n, "share_of_step": v_ms / ms_total}
-    shares = {c: round(prof[c][0] / ms_total, 4) for c in prof if prof[c][1]}
+                 "avg_launch_ms": v_ms / v_n, "share_of_step": v_ms / ms_prof}
+    shares = {c: round(prof[c][0] / ms_prof, 4) for c in prof if prof[c][1]}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
-            "dtype": "f32-equivalent (tcgen05 %s 3-term split, fp32 accumulate)" % ("fp16" if args.precision == "f16x3" else "tf32"),
+            "dtype": "f32-equivalent (tcgen05 %s 3-term split, fp32 accumulate)" % ("fp16" if f16 else "tf32"),
             "data": "synthetic",
             "config": {"workload": wl["name"], "per_gpu_batch": B, "global_batch": B * world,
                        "weights": "random-init (upstream recipe), no checkpoint offline",
-                       "parallelism": f"dp{world} (images sharded, no collective in the step)",
-                       "precision": args.precision,
+                       "parallelism": (f"dp{world}: images sharded; one ncclAllGather of the step's [{B},{Dv}] fp32 "
+                                       f"descriptors per rank into the replicated retrieval database, asynchronous, "
+                                       f"overlapping the next step's ViT" if world > 1 else
+                                       "dp1: the descriptor all-gather degenerates to the copy into the database buffer"),
+                       "precision": ext.precision,
                        "cache": "inputs larger than L2: weights (hi+lo) streamed every step"},
             "vit_tflops_algorithmic": flops_img * value / 1e12,
             "roofline": roof, "roofline_vlad": vroof, "time_shares": shares,
+            "collective": {"name": "ncclAllGather (torch.distributed all_gather_into_tensor)" if world > 1 else "none (N=1: device copy)",
+                           "bytes_per_rank_per_step": B * Dv * 4, "recv_bytes_per_rank_per_step": (world - 1) * B * Dv * 4,
+                           "alone_us": coll_us, "alone_busbw_GBs": coll_gbs, "nvlink_peak_GBs_per_dir": NVLINK_GBS_PER_DIR,
+                           "in_timed_region": True, "overlapped": world > 1, "checks": chk},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * img_host.numel() * 4,
-                    "d2h_bytes_per_step": world * B * K * D * 4, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": world * B * Dv * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks}
+    if sd_host is not None:
+        line["parity"] = pipeline_parity(wl, sd_host, img_host, vlad, desc, ext, u)
+        del sd_host
     if world == 1 and not args.no_cpu_baseline:
         n_ref = max(args.ref_images, 4)        # ~14 s of timed CPU work at c2 (0.85-0.9 img/s on the box's 16 usable cores)
         ips, ms, cores = cpu_reference(wl, n_ref, 3, 1)
         line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{n_ref} images x 3 steps of the same workload, batch 1 per image, "
                                           "all blocks + hook, CPU VLAD with [N,K,D] residuals"}
+        if not args.no_gpu_reference:
+            del ext
+            _lib.workspaces.clear()
+            torch.cuda.empty_cache()
+            n_g = 16
+            ips_g, vit_ms = gpu_reference(wl, n_g)
+            line["reference_gpu"] = {"value": ips_g, "unit": UNIT, "vit_ms_per_image": vit_ms,
+                                     "what": "the reference GPU PyTorch path on this GPU: restated hub model .cuda() fp32 "
+                                             "(TF32 off), batch 1, all blocks + hook, .cpu() per image, CPU VLAD.generate "
+                                             "with [N,K,D] residuals (scripts/dino_v2_vlad.py:164-188,233-237); torch/cuBLAS "
+                                             "kernels only", "sample": f"{n_g} images",
+                                     "e2e_over_reference_gpu": e2e_value / ips_g}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    R.finish()
+
+
+def pipeline_parity(wl, sd_host, img_host, vlad, desc, ext, u, n=2):
+    """bench.py checks what it timed: the first `n` images of the timed batch through the CPU oracle (restated hub model
+    with the SAME weights, reference VLAD arithmetic with the SAME vocabulary) against the features / descriptors the
+    timed configuration produced.  Relative inf-norm errors (north_star tolerance 1e-4)."""
+    import torch
+    from oracle import anyloc_oracle as ao
+    from oracle import dinov2_restated as dr
+    torch.set_num_threads(usable_cores())
+    with torch.device("meta"):
+        model = dr.DinoVisionTransformer(wl["model"], depth_override=wl["layer"] + 1)
+    model.load_state_dict(sd_host, strict=False, assign=True)
+    model.eval()
+    ref_f = ao.extract_features(model, img_host[:n].clone(), wl["layer"], wl["facet"])
+    got_f = ext(img_host[:n].to(ext.device)).cpu()
+    centers = vlad.c_centers.cpu()
+    err_f = float((got_f - ref_f).abs().max() / ref_f.abs().max())
+    # descriptors: reference arithmetic on the reference features, labels forced to the GPU's outside the fp64-ambiguous
+    # set is unnecessary here -- a flipped label would show up as an O(1) error
+    ref_v = torch.stack([ao.vlad_generate(f, centers) for f in ref_f])
+    got_v = desc[:n].cpu()
+    err_v = float((got_v - ref_v).abs().max() / ref_v.abs().max())
+    # label agreement on the reference features (exact outside near-ties)
+    lab_ref = torch.stack([ao.vlad_labels(f, centers) for f in ref_f])
+    lab_got = torch.stack([ao.vlad_labels(f, centers) for f in got_f])
+    return {"images": n, "features_rel_err": err_f, "descriptors_rel_err": err_v,
+            "labels_differ": int((lab_ref != lab_got).sum()), "labels_total": int(lab_ref.numel()),
+            "tolerance": 1e-4, "ok": bool(err_f < 1e-4),
+            "note": "descriptor error includes label flips of near-tied patches between fp32 feature sets that differ by "
+                    "features_rel_err (each flip moves one patch between two clusters)"}
+
+
+# ------------------------------------------------------------------ retrieval (c3 / c4)
+def run_retrieval(args, wl):
+    R = Ranks()
+    torch, dist, dev, world, rank = R.torch, R.dist, R.dev, R.world, R.rank
+    from anyloc_b200 import _lib, dist as adist, utilities as u
+    n_loc, n_q, Dv, k = wl["n_db_per_rank"], wl["n_q"], wl["Dv"], wl["k"]
+    if args.small:
+        n_loc, n_q = n_loc // 10, n_q // 10
+    n_db = n_loc * world
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    db_local = torch.nn.functional.normalize(torch.randn(n_loc, Dv, device=dev, generator=g), dim=1)
+    qs, qe = adist.shard_range(n_q)
+    nq_loc = qe - qs
+    src = torch.randperm(n_loc, device=dev, generator=g)[:nq_loc]
+    qu_local = db_local[src] + 0.1 * torch.nn.functional.normalize(torch.randn(nq_loc, Dv, device=dev, generator=g), dim=1)
+    truth_local = src + rank * n_loc
+    top_k = [1, k]
+
+    def step_gather_db(i):
+        """BASELINE config 4's pattern: all-gather the database descriptors, index them, every rank answers its own
+        query shard, the [n_q, k] results are gathered."""
+        db_all = adist.all_gather_descriptors(db_local)
+        index = u.FlatIndex(Dv, "cosine", True)
+        index.add(db_all)
+        d, ix = index.search(qu_local, k)
+        return adist.all_gather_rows(d), adist.all_gather_rows(ix)
+
+    index_local = u.FlatIndex(Dv, "cosine", True)
+    index_local.add(db_local)
+
+    def step_search_only(i):
+        return index_local.search(qu_local, k)
+
+    def step_gather_queries(i):
+        """database stays sharded (index built once, resident): all-gather the queries, local top-k with global
+        offsets, all-gather + merge the candidates"""
+        return adist.sharded_top_k(db_local, qu_local, k, strategy="gather_queries",
+                                   search=lambda db, qu, kk, method, norm: index_local.search(qu, kk))
+
+    step = step_gather_db
+    for i in range(args.warmup):
+        step(i)
+    sampler = ClockSampler(R.local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms_total = R.timed(step, args.steps)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    for i in range(2):
+        step_gather_queries(i)
+    ms_gq = R.timed(step_gather_queries, args.steps)
+    ms_search = R.timed(step_search_only, args.steps)
+    _lib.profile_enable(True)
+    n_prof = min(args.steps, 3)
+    R.timed(step, n_prof)
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    coll_us, coll_gbs = collective_alone(R, (n_loc, Dv), iters=3)
+
+    # correctness: the noisy copy's source row is the top-1; both strategies agree; fp64 scores on this rank's queries
+    d_db, i_db = step_gather_db(0)
+    d_gq, i_gq = step_gather_queries(0)
+    truth = adist.all_gather_rows(truth_local)
+    ok_top1 = R.all_true(torch.equal(i_db[:, 0], truth))
+    ok_same = R.all_true(torch.equal(i_db, i_gq))
+    db_all = adist.all_gather_descriptors(db_local)
+    n_chk = min(nq_loc, 32)
+    sc = (qu_local[:n_chk].double() / qu_local[:n_chk].double().norm(dim=1, keepdim=True)) @ db_all.double().T
+    rd, ri = torch.sort(sc, dim=1, descending=True, stable=True)
+    ok_fp64 = R.all_true(torch.equal(ri[:, :k], i_db[qs:qs + n_chk]))
+    dist_err = float((rd[:, :k] - d_db[qs:qs + n_chk].double()).abs().max())
+
+    # e2e through the reference-facing call with HOST tensors (N=1 only: get_top_k_recall has no multi-GPU form)
+    e2e = None
+    if world == 1:
+        db_h, qu_h = db_local.cpu().pin_memory(), qu_local.cpu().pin_memory()
+        import numpy as np
+        gt = np.empty(n_q, dtype=object)
+        for j, t in enumerate(truth_local.tolist()):
+            gt[j] = np.array([t])
+        u.get_top_k_recall(top_k, db_h, qu_h, gt)
+        n_e2e = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            dd, ii, rec = u.get_top_k_recall(top_k, db_h, qu_h, gt)
+        dt = (time.perf_counter() - t0) / n_e2e
+        e2e = {"value": n_q / dt, "unit": "queries/s", "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": (n_db + n_q) * Dv * 4, "d2h_bytes_per_step": n_q * k * 12,
+               "recall@1": rec[1], "call": "get_top_k_recall(top_k, db, qu, gt_pos) with host tensors (index.add + search)"}
+    if rank != 0:
+        R.finish()
+        return
+    peaks = measured_peaks()
+    ms_step = ms_total / args.steps
+    g_ms, g_n, g_fl = prof["gemm_tc"]
+    roof = None
+    if g_n:
+        ach = g_fl / (g_ms / 1e3) / 1e12
+        roof = {"kernel": u.TOPK_KERNEL_DESCRIPTION, "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"],
+                "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"], "traffic": ncu_traffic("gemm_tc3", "topk")[0],
+                "algorithmic_flops_per_launch": g_fl / g_n, "avg_launch_ms": g_ms / g_n, "launches": g_n,
+                "contract_ceiling": 1.0 / 3.0}
+    line = {"metric": "queries/sec cosine top-%d retrieval over a %d-image database of %d-D VLAD descriptors" % (k, n_db, Dv),
+            "value": n_q * args.steps / (ms_total / 1e3), "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32-equivalent (tcgen05 fp16-pair 3-term split on unit rows, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": wl["name"], "n_db_total": n_db, "n_db_per_gpu": n_loc, "n_q": n_q, "Dv": Dv, "k": k,
+                       "step": "all-gather of the database descriptors (N>1) + index build (normalise + fp16-pair split) "
+                               "+ search of this rank's query shard + gather of the [n_q,k] results",
+                       "parallelism": f"database and queries sharded over {world} GPU(s); strategy gather_db (BASELINE config 4)",
+                       "cache": "database larger than L2"},
+            "roofline": roof,
+            "alternatives": {"gather_queries_ms_per_step": ms_gq / args.steps,
+                             "search_only_local_shard_ms": ms_search / args.steps,
+                             "note": "gather_queries keeps the database sharded with a resident index (all-gathers the queries "
+                                     "and the [n_q,k] candidates instead): identical results"},
+            "collective": {"name": "ncclAllGather of [n_db_per_gpu, Dv] fp32" if world > 1 else "none",
+                           "bytes_per_rank_per_step": n_loc * Dv * 4, "alone_us": coll_us, "alone_busbw_GBs": coll_gbs,
+                           "nvlink_peak_GBs_per_dir": NVLINK_GBS_PER_DIR},
+            "parity": {"top1_is_source_row": ok_top1, "strategies_identical": ok_same,
+                       "top%d_equals_fp64_first_%d_queries_per_rank" % (k, n_chk): ok_fp64, "max_abs_dist_err_vs_fp64": dist_err},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "time_shares": {c: round(prof[c][0] / (ms_step * n_prof), 4) for c in prof if prof[c][1]}}
+    print(json.dumps(line), flush=True)
+    R.finish()
 
 
 def main():
@@ -337,15 +713,20 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "tc3", "simt"])
     ap.add_argument("--ref-images", type=int, default=2, help="images per CPU-reference step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--small", action="store_true", help="retrieval workloads at 1/10 size (smoke runs)")
     ap.add_argument("--vocab", default="fit", choices=["fit", "random"])
-    ap.add_argument("--precision", default="f16x3", choices=["f16x3", "tf32x3"],
+    ap.add_argument("--precision", default="f16x3", choices=["f16x3", "tf32x3", "auto"],
                     help="operand pair format of the tensor-core GEMMs (both fp32-equivalent; see DESIGN.md)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference_arm(args, wl)
+    elif wl["kind"] == "pipeline":
+        run_pipeline(args, wl)
     else:
-        run_ours(args, wl)
+        run_retrieval(args, wl)
 
 
 if __name__ == "__main__":

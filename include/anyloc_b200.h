@@ -114,6 +114,17 @@ int anyloc_vlad_generate_prepared(const float* feats, const int32_t* n_valid, co
 int anyloc_vlad_generate_soft(const float* feats, const int32_t* n_valid, const float* centers,
                               int B, int N, int D, int K, float soft_temp, int norm_descs, int intra_norm,
                               float* vlad, float* assign, void* ws, size_t ws_bytes, void* stream);
+/* Residual tensor of VLAD.generate_res_vec (utilities.py:928-972): out[q,k,:] = x^_q - c_k for ALL (patch, centre)
+ * pairs, [N,K,D] fp32 (x^ = F.normalize(x) when norm_descs).  The reference builds every descriptor from this tensor
+ * and caches it per image (`<cache_id>_r.pt`); here it is only materialised when a caller asks for it. */
+int anyloc_vlad_residuals(const float* feats, const float* centers, int N, int D, int K, int norm_descs,
+                          float* out, void* stream);
+/* Descriptor of ONE image from a residual tensor [N,K,D] plus either the hard labels [N] int32 (utilities.py:853-861)
+ * or the soft assignment [N,K] (:879-887) -- the reference's cache path (`_r.pt` + `_l.pt` / `_s.pt`, :843-852,
+ * :864-878), which needs no features.  Pass exactly one of labels / assign.  vlad [K*D]. */
+size_t anyloc_vlad_from_residuals_workspace_bytes(int D, int K);
+int anyloc_vlad_from_residuals(const float* resid, const int32_t* labels, const float* assign, int N, int D, int K,
+                               int intra_norm, float* vlad, void* ws, size_t ws_bytes, void* stream);
 /* labels only (fpk.KMeans.predict, utilities.py:849; also one Lloyd assignment step of VLAD.fit :786) */
 int anyloc_vlad_assign(const float* feats, const float* centers, int R, int D, int K, int dist_mode,
                        int32_t* labels, void* ws, size_t ws_bytes, void* stream);
@@ -132,6 +143,21 @@ int anyloc_kmeans_update(const float* x, const int32_t* labels, const float* old
 size_t anyloc_topk_workspace_bytes(int n_db, int n_q, int Dv, int k);
 int anyloc_topk(const float* db, const float* qu, int n_db, int n_q, int Dv, int k, int metric,
                 int normalize, float* dist, int64_t* idx, void* ws, size_t ws_bytes, void* stream);
+
+/* Prepared database -- what `index.add(db)` leaves behind in faiss (utilities.py:449): the rows normalised (optional)
+ * and stored as the (hi, lo) operand pairs the score GEMM consumes, plus |y|^2 per row (L2 metric).  Unit rows
+ * (normalize != 0, Dv % 8 == 0) are kept as fp16 pairs of 4096*y (half the bytes, 2x tensor rate), other rows as tf32
+ * pairs.  The blob is caller-owned (anyloc_index_bytes for `capacity` rows); rows can be added in chunks at any
+ * row_offset (e.g. as descriptor batches arrive from the all-gather); a search over the first n_db rows is
+ * anyloc_topk minus the per-call database pass.  `normalize` must be the same value in all calls on one blob.
+ * anyloc_index_search: workspace from anyloc_index_search_workspace_bytes (query pairs + the [n_q, n_db] scores). */
+size_t anyloc_index_bytes(int64_t capacity, int Dv, int normalize);
+int anyloc_index_add(void* index, size_t index_bytes, int64_t capacity, int64_t row_offset, const float* rows,
+                     int n_rows, int Dv, int normalize, void* stream);
+size_t anyloc_index_search_workspace_bytes(int64_t n_db, int n_q, int Dv, int normalize);
+int anyloc_index_search(const void* index, size_t index_bytes, int64_t capacity, int64_t n_db, const float* qu,
+                        int n_q, int Dv, int k, int metric, int normalize, float* dist, int64_t* idx, void* ws,
+                        size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------- ViT
  * Replaces DinoV2ExtractFeatures.__call__ (utilities.py:263-285) and the hub model's forward

@@ -192,8 +192,39 @@ def make_preprocess():
     print("preprocess.npz")
 
 
+def make_build_vlads():
+    """The reference's UNMODIFIED driver -- `build_vlads` of scripts/dino_v2_vlad.py:124-303 -- over its own
+    utilities.py on the synthetic dataset of tests/dropin_harness.py (hard and soft assignment), then its own
+    get_top_k_recall.  tests/test_dropin_gpu.py replays the dataset through the shim on the GPU against these."""
+    from tests import dropin_harness as H
+    script = H.load_script(ref)
+    out = {}
+    for tag, soft in (("hard", False), ("soft", True)):
+        ds = H.SyntheticVprDataset()
+        model_factory = lambda name: dr.perturb(dr.build(name, seed=0, depth_override=3), seed=3)
+        with ri.hub_patched(model_factory):
+            np.random.seed(42)
+            largs = H.make_largs(script, "/tmp/_anyloc_golden_cache", "dinov2_vits14", 2, "value", 4, False, soft)
+            db, qu = script.build_vlads(largs, ds, verbose=False)
+            # the vocabulary the run fitted (same seed -> same k-means): refit outside to record it
+            np.random.seed(42)
+            v = ref.VLAD(4, vlad_mode="soft" if soft else "hard")
+            dino = ref.DinoV2ExtractFeatures("dinov2_vits14", 2, "value", device="cpu")
+            from torchvision import transforms as T
+            feats = torch.cat([dino(T.CenterCrop((56, 70))(ds[i][0])[None]) for i in range(ds.database_num)])
+            v.fit(feats.reshape(-1, feats.shape[-1]))
+        assert torch.equal(v.generate_multi(feats), db)
+        d, i, rec = ref.get_top_k_recall([1, 2, 3], db, qu, ds.soft_positives_per_query)
+        out[f"{tag}/db_vlads"], out[f"{tag}/qu_vlads"] = db.numpy(), qu.numpy()
+        out[f"{tag}/c_centers"] = v.c_centers.numpy()
+        out[f"{tag}/dist"], out[f"{tag}/idx"] = np.asarray(d), np.asarray(i)
+        out[f"{tag}/recalls"] = np.array([rec[1], rec[2], rec[3]])
+    np.savez_compressed(os.path.join(OUT, "build_vlads.npz"), **out)
+    print("build_vlads.npz")
+
+
 if __name__ == "__main__":
     makers = {"vlad": make_vlad, "vlad_soft": make_vlad_soft, "fit": make_fit, "topk": make_topk,
-              "extract": make_extract, "preprocess": make_preprocess}
+              "extract": make_extract, "preprocess": make_preprocess, "build_vlads": make_build_vlads}
     for name in (sys.argv[1:] or list(makers)):      # `make_golden.py vlad_soft` regenerates one file
         makers[name]()
