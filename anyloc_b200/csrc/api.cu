@@ -37,15 +37,15 @@ ProfScope::ProfScope(int cat, cudaStream_t stream, double work) : slot(-1), st(s
 ProfScope::~ProfScope() { if (slot >= 0) cudaEventRecord(g_prof[slot].b, st); }
 
 int device_sm_count() {
-  static int cached = -1;
-  if (cached < 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else return 148;
-  }
-  return cached;
+  // per device ordinal: one process may drive several (possibly non-identical / MIG) devices
+  static std::atomic<int> cached[64];
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  n = cached[dev].load(std::memory_order_relaxed);
+  if (n > 0) return n;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  cached[dev].store(n, std::memory_order_relaxed);
+  return n;
 }
 
 // engines (defined in gemm_simt.cu / gemm_tc.cu)
@@ -69,6 +69,7 @@ int attention_tc_launch(const float*, const float*, const float*, const float*, 
 int attention_tc_standalone(const float*, const float*, int, int, int, int, void*, void*, bool, float*, cudaStream_t);
 int attention_vt_pitch(int T);
 int attention16_vt_pitch(int T);
+bool attention16_vmn();
 int attention_tc16_launch(const void*, const void*, const void*, const void*, int, int, int, int, void*, void*, bool,
                           cudaStream_t);
 int attention_tc16_standalone(const float*, const float*, int, int, int, int, void*, void*, bool, cudaStream_t);
@@ -166,9 +167,11 @@ extern "C" int anyloc_layernorm_split(const float* x, const float* w, const floa
   return launch_layernorm(x, w, b, M, D, eps, y_hi, y_lo, out_dtype == ANYLOC_PAIR_F16, (cudaStream_t)stream);
 }
 
+// qkv_f16: qkv_{hi,lo} already hold fp16 pairs of 8*x for all three thirds (the ViT's qkv epilogue wrote them); with
+// vt_hi == nullptr the fp16 attention kernel then reads V row-major from that buffer (MN-major operand).
 static int attention_dispatch(const float* qkv_hi, const float* qkv_lo, const float* vt_hi, const float* vt_lo,
                               int B, int T, int D, int heads, void* o_hi, void* o_lo, bool out_f16, int engine,
-                              cudaStream_t st) {
+                              cudaStream_t st, bool qkv_f16 = false) {
   ProfScope ps(PC_ATTENTION, st, 4.0 * B * (double)T * T * D);
   const bool tc_ok = qkv_lo != nullptr && (D % 4) == 0 &&
                      (reinterpret_cast<uintptr_t>(qkv_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(qkv_lo) & 15) == 0;
@@ -179,7 +182,7 @@ static int attention_dispatch(const float* qkv_hi, const float* qkv_lo, const fl
   if (engine == ANYLOC_GEMM_SIMT || !tc_ok)
     return attention_launch(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, out_f16, st);
   if (out_f16) {     // fp16-pair precision: operands are fp16 pairs too (inside the ViT the qkv epilogue wrote them)
-    if (vt_hi) return attention_tc16_launch(qkv_hi, qkv_lo, vt_hi, vt_lo, B, T, D, heads, o_hi, o_lo, true, st);
+    if (vt_hi || qkv_f16) return attention_tc16_launch(qkv_hi, qkv_lo, vt_hi, vt_lo, B, T, D, heads, o_hi, o_lo, true, st);
     return attention_tc16_standalone(qkv_hi, qkv_lo, B, T, D, heads, o_hi, o_lo, true, st);
   }
   if (vt_hi) return attention_tc_launch(qkv_hi, qkv_lo, vt_hi, vt_lo, B, T, D, heads, o_hi, o_lo, out_f16, nullptr, st);
@@ -249,10 +252,14 @@ static int vit_block(const AnylocVitCfg* c, const AnylocVitBlock& wb, const VitB
   const bool f16_attn = tc_attn && f16;       // fp16 operands for the fp16-pair precision
   e_qkv.qkv_T = T; e_qkv.qkv_Tp = f16_attn ? attention16_vt_pitch(T) : attention_vt_pitch(T); e_qkv.qkv_D = D;
   e_qkv.qkv_f16 = f16_attn;
-  e_qkv.alpha = wb.qkv_alpha;          // q,k,v always leave as tf32 pairs (attention input)
+  e_qkv.alpha = wb.qkv_alpha;
+  // fp16-pair precision with the MN-major V operand: q, k AND v leave the GEMM row-major as fp16 pairs of 8*x -- the
+  // plain split epilogue (fully staged, 16-byte stores); no transposed V^T copy exists
+  const bool vmn = f16_attn && attention16_vmn();
+  if (vmn) { e_qkv.mode = ANYLOC_EPI_BIAS_SPLIT; e_qkv.out_f16 = 1; }
   if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.qkv_w_hi, wb.qkv_w_lo, D, M, 3 * D, D, e_qkv, engine, f16, st))) return rc;
-  if ((rc = attention_dispatch(bf.qkv, bf.qkv_lo, tc_attn ? bf.vt_hi : nullptr, tc_attn ? bf.vt_lo : nullptr, B, T, D,
-                               c->num_heads, bf.y_hi, bf.y_lo, f16, engine, st))) return rc;
+  if ((rc = attention_dispatch(bf.qkv, bf.qkv_lo, (tc_attn && !vmn) ? bf.vt_hi : nullptr, (tc_attn && !vmn) ? bf.vt_lo : nullptr,
+                               B, T, D, c->num_heads, bf.y_hi, bf.y_lo, f16, engine, st, vmn))) return rc;
   EpiParams e_proj{ANYLOC_EPI_LS_RESID, wb.proj_b, wb.ls1, bf.x, bf.x, nullptr, D};
   e_proj.alpha = wb.proj_alpha;
   if ((rc = gemm_dispatch(bf.y_hi, bf.y_lo, D, wb.proj_w_hi, wb.proj_w_lo, D, M, D, D, e_proj, engine, f16, st))) return rc;
@@ -289,7 +296,7 @@ extern "C" int anyloc_vit_extract(const AnylocVitCfg* cfg, const AnylocVitWeight
     return ANYLOC_ERR_WORKSPACE;
   }
   int rc;
-  if (gemm_engine != ANYLOC_GEMM_SIMT &&
+  if (gemm_engine != ANYLOC_GEMM_SIMT && !(cfg->pair_dtype == ANYLOC_PAIR_F16 && attention16_vmn()) &&
       (cfg->pair_dtype == ANYLOC_PAIR_F16 ? attention16_vt_pitch(T) != T : attention_vt_pitch(T) != T)) {
     // pad columns [T, Tp) of the transposed-V buffers are read by TMA but never written: keep them finite (zero)
     ANYLOC_CHECK_CUDA(cudaMemsetAsync(bf.vt_hi, 0, bf.vt_elems * sizeof(float), st));

@@ -148,7 +148,11 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {      // a -> l
 // warps whose 32 keys or 32 query rows lie entirely beyond T skip scale / max / ex2 / pair split (they keep taking part
 // in the barriers and publish zero probabilities), and the P.V of the last key block issues only the k-steps that hold
 // valid keys.  SKIP = false compiles to exactly the kernel measured in round 1.
-template <bool SKIP>
+// VMN: V is read straight from the qkv buffer (row-major [token][dim] fp16 pairs, the layout the qkv GEMM's plain split
+// epilogue writes) as an MN-MAJOR B operand of the P.V UMMAs -- a [128 keys x 64 dims] TMA box is exactly the canonical
+// MN-major SWIZZLE_128B layout (64 dims = one 128-byte atom row per key, 8-key groups 1024 B apart), each K=16 step
+// advances 16 keys = 2048 B.  No per-head transposed V^T copy, no 2-byte transposed stores in the GEMM epilogue.
+template <bool SKIP, bool VMN>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid_constant__ CUtensorMap tm_lo_qk,
                       const __grid_constant__ CUtensorMap tm_hi_vt, const __grid_constant__ CUtensorMap tm_lo_vt,
@@ -244,10 +248,15 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
           const uint32_t fb = smem_u32(v_full + stage);
           mbar_expect_tx(fb, VSTAGE);
           const uint32_t sb = smem_u32(sV + stage * VSTAGE);
-          tma_load_2d(sb + 0 * V_BOX, &tm_hi_vt, fb, j * BKV, vrow);
-          tma_load_2d(sb + 1 * V_BOX, &tm_hi_vt, fb, j * BKV + 64, vrow);
-          tma_load_2d(sb + 2 * V_BOX, &tm_lo_vt, fb, j * BKV, vrow);
-          tma_load_2d(sb + 3 * V_BOX, &tm_lo_vt, fb, j * BKV + 64, vrow);
+          if constexpr (VMN) {         // [128 keys x 64 dims] of the v third, hi then lo (tm_*_vt are the qkv maps here)
+            tma_load_2d(sb, &tm_hi_vt, fb, 2 * D + h * HD, b * T + j * BKV);
+            tma_load_2d(sb + K_HALF, &tm_lo_vt, fb, 2 * D + h * HD, b * T + j * BKV);
+          } else {
+            tma_load_2d(sb + 0 * V_BOX, &tm_hi_vt, fb, j * BKV, vrow);
+            tma_load_2d(sb + 1 * V_BOX, &tm_hi_vt, fb, j * BKV + 64, vrow);
+            tma_load_2d(sb + 2 * V_BOX, &tm_lo_vt, fb, j * BKV, vrow);
+            tma_load_2d(sb + 3 * V_BOX, &tm_lo_vt, fb, j * BKV + 64, vrow);
+          }
         }
       }
     }
@@ -255,7 +264,8 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
     if (lane == 0) {
       // ------------------------------------------------ MMA issuer (kind::f16: a/b format 0 = F16, c format 1 = F32)
       constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t)(BKV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
-      constexpr uint32_t idesc_pv = (1u << 4) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      // bit 16 = b_major: 1 = MN-major (VMN: V [key][dim], dims contiguous)
+      constexpr uint32_t idesc_pv = (1u << 4) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24) | (VMN ? (1u << 16) : 0u);
       const uint32_t q_base = smem_u32(sQ);
       auto issue_s = [&](int gb) {
         const int st = gb % STAGES;
@@ -305,8 +315,9 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k) {                // 8 k-steps of 16 keys
             if (SKIP && k >= ksteps) break;
-            const uint32_t voff = (uint32_t)((k >> 2) * V_BOX + (k & 3) * 32);
-            const uint64_t v_hi = desc_kmajor(vb + voff), v_lo = desc_kmajor(vb + 2 * V_BOX + voff);
+            // V^T K-major: 64-key boxes, 32 B per k-step inside the atom; V MN-major: 16 keys x 128 B per k-step
+            const uint32_t voff = VMN ? (uint32_t)(k * 2048) : (uint32_t)((k >> 2) * V_BOX + (k & 3) * 32);
+            const uint64_t v_hi = desc_kmajor(vb + voff), v_lo = desc_kmajor(vb + (VMN ? K_HALF : 2 * V_BOX) + voff);
             // keys [16k,16k+16) live in the 32-column group of softmax part k/2: hi at +8*(k&1), lo at +16+8*(k&1)
             const uint32_t p_hi = pbuf + (uint32_t)((k >> 1) * 32 + (k & 1) * 8), p_lo = p_hi + 16;
             umma_ts(d, p_hi, v_hi, idesc_pv, k != 0);
@@ -400,6 +411,11 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tm_hi_qk, const __grid
         TSTAMP(5);
         tc_fence_before();
         __syncwarp();
+        // Warps without query rows do no work per block, so nothing paces them: they must not arrive for block gb before
+        // phase gb-1 of p_full has completed, or their early arrivals would complete that phase in place of the live
+        // warps' (the P.V of block gb-1 would then read P before it is written).  Live warps are paced by their own
+        // softmax work and by the o_full wait below.
+        if (SKIP && dead_rows && gb > 0) mbar_wait(smem_u32(p_full), (uint32_t)((gb - 1) & 1));
         if (lane == 0) mbar_arrive(smem_u32(p_full));
         TSTAMP(6);
         // fold in O_{j-1} (RN) and rescale to the new running maximum
@@ -475,13 +491,14 @@ qkv_to_f16_kernel(const float* __restrict__ qkv_hi, const float* __restrict__ qk
   const int t = blockIdx.x * 128 + threadIdx.x, h = blockIdx.y, b = blockIdx.z;
   if (t >= T) return;
   const size_t rowoff = ((size_t)b * T + t) * 3 * D;
-  for (int part = 0; part < 2; ++part) {
+  for (int part = 0; part < (vt_hi ? 2 : 3); ++part) {          // vt_hi == nullptr: v stays row-major like q, k (VMN)
     const size_t src = rowoff + (size_t)part * D + (size_t)h * HD;
     for (int d = 0; d < HD; ++d) {
       __half hh, ll; split_f16((qkv_hi[src + d] + qkv_lo[src + d]) * kActScale, hh, ll);
       q16_hi[src + d] = hh; q16_lo[src + d] = ll;
     }
   }
+  if (!vt_hi) return;
   const size_t src = rowoff + 2 * (size_t)D + (size_t)h * HD;
   const size_t dst = ((size_t)b * D + (size_t)h * HD) * Tp + t;
   for (int d = 0; d < HD; ++d) {
@@ -523,7 +540,15 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
 
 int attention16_vt_pitch(int T) { return (T + 7) & ~7; }     // fp16 rows: multiple of 16 bytes
 
-// qk16_{hi,lo}: fp16 [B*T, 3D] (q | k thirds of 8*x); vt16_{hi,lo}: fp16 [B*D, Tp], pad columns zero.
+// ANYLOC_ATTN_VMN (default 1): V row-major in the qkv buffer, MN-major P.V operand; 0 = the per-head transposed V^T copy.
+bool attention16_vmn() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ANYLOC_ATTN_VMN"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
+// qk16_{hi,lo}: fp16 [B*T, 3D] (q | k | v thirds of 8*x).  vt16_{hi,lo}: fp16 [B*D, Tp] per-head transposed V, pad columns
+// zero -- or nullptr: V is taken from the v third of qk16 (VMN kernel).
 static float* g_attn16_dbg = nullptr;      // set by the (non-ABI) debug entry below
 int attention_tc16_launch(const void* qk_hi, const void* qk_lo, const void* vt_hi, const void* vt_lo, int B, int T,
                           int D, int heads, void* o_hi, void* o_lo, bool out_f16, cudaStream_t st) {
@@ -532,24 +557,30 @@ int attention_tc16_launch(const void* qk_hi, const void* qk_lo, const void* vt_h
   CUtensorMap hqk, lqk, hvt, lvt;
   int rc;
   const int Tp = attention16_vt_pitch(T);
+  const bool vmn = vt_hi == nullptr;
   if ((rc = make_map(&hqk, qk_hi, (int64_t)B * T, 3 * (int64_t)D, BQ))) return rc;
   if ((rc = make_map(&lqk, qk_lo, (int64_t)B * T, 3 * (int64_t)D, BQ))) return rc;
-  if ((rc = make_map(&hvt, vt_hi, (int64_t)B * D, Tp, HD))) return rc;
-  if ((rc = make_map(&lvt, vt_lo, (int64_t)B * D, Tp, HD))) return rc;
+  if (vmn) { hvt = hqk; lvt = lqk; }
+  else {
+    if ((rc = make_map(&hvt, vt_hi, (int64_t)B * D, Tp, HD))) return rc;
+    if ((rc = make_map(&lvt, vt_lo, (int64_t)B * D, Tp, HD))) return rc;
+  }
   static unsigned long long attr_seen = 0;
   if (first_use_on_this_device(&attr_seen)) {
-    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc16_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc16_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc16_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc16_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   }
   static int skip_env = -1;             // ANYLOC_ATTN_SKIP=1: the tail-skipping variant (see the kernel's header); default off
   if (skip_env < 0) { const char* e = getenv("ANYLOC_ATTN_SKIP"); skip_env = e ? atoi(e) : 0; }
   const int total = cdiv(T, BQ) * heads * B;
-  if (skip_env)
-    attention_tc16_kernel<true><<<std::min(total, device_sm_count()), THREADS, SMEM_BYTES, st>>>(hqk, lqk, hvt, lvt, B, T, D,
-                                                                                               o_hi, o_lo, out_f16 ? 1 : 0, g_attn16_dbg);
-  else
-    attention_tc16_kernel<false><<<std::min(total, device_sm_count()), THREADS, SMEM_BYTES, st>>>(hqk, lqk, hvt, lvt, B, T, D,
-                                                                                                o_hi, o_lo, out_f16 ? 1 : 0, g_attn16_dbg);
+  const int grid = std::min(total, device_sm_count());
+#define ANYLOC_ATTN16_LAUNCH(S_, V_) \
+  attention_tc16_kernel<S_, V_><<<grid, THREADS, SMEM_BYTES, st>>>(hqk, lqk, hvt, lvt, B, T, D, o_hi, o_lo, out_f16 ? 1 : 0, g_attn16_dbg)
+  if (skip_env) { if (vmn) ANYLOC_ATTN16_LAUNCH(true, true); else ANYLOC_ATTN16_LAUNCH(true, false); }
+  else { if (vmn) ANYLOC_ATTN16_LAUNCH(false, true); else ANYLOC_ATTN16_LAUNCH(false, false); }
+#undef ANYLOC_ATTN16_LAUNCH
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }
@@ -558,11 +589,12 @@ int attention_tc16_launch(const void* qk_hi, const void* qk_lo, const void* vt_h
 int attention_tc16_standalone(const float* qkv_hi, const float* qkv_lo, int B, int T, int D, int heads, void* o_hi,
                               void* o_lo, bool out_f16, cudaStream_t st) {
   const int Tp = attention16_vt_pitch(T);
-  const size_t nq = (size_t)B * T * 3 * D, nv = (size_t)B * D * Tp;
+  const bool vmn = attention16_vmn();
+  const size_t nq = (size_t)B * T * 3 * D, nv = vmn ? 0 : (size_t)B * D * Tp;
   __half* buf = nullptr;
   ANYLOC_CHECK_CUDA(cudaMallocAsync((void**)&buf, (2 * nq + 2 * nv) * sizeof(__half), st));
   ANYLOC_CHECK_CUDA(cudaMemsetAsync(buf, 0, (2 * nq + 2 * nv) * sizeof(__half), st));
-  __half *q_hi = buf, *q_lo = buf + nq, *v_hi = buf + 2 * nq, *v_lo = buf + 2 * nq + nv;
+  __half *q_hi = buf, *q_lo = buf + nq, *v_hi = vmn ? nullptr : buf + 2 * nq, *v_lo = vmn ? nullptr : buf + 2 * nq + nv;
   atc16::qkv_to_f16_kernel<<<dim3(cdiv(T, 128), heads, B), 128, 0, st>>>(qkv_hi, qkv_lo, T, Tp, D, q_hi, q_lo, v_hi, v_lo);
   ANYLOC_CHECK_LAUNCH();
   int rc = attention_tc16_launch(q_hi, q_lo, v_hi, v_lo, B, T, D, heads, o_hi, o_lo, out_f16, st);

@@ -97,14 +97,15 @@ __device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi2, uin
 
 int device_sm_count();
 // true the first time it is called on the CURRENT device for this flag word: cudaFuncSetAttribute is per device, so a
-// process that drives several GPUs must repeat it on each of them (one bit per device ordinal)
+// process that drives several GPUs must repeat it on each of them (one bit per device ordinal; atomic because two host
+// threads may race on the word).  A failing cudaFuncSetAttribute is reported to the caller by ANYLOC_CHECK_CUDA; the
+// launch that follows a failed attribute set fails loudly as well (dynamic shared memory over the default limit).
 static inline bool first_use_on_this_device(unsigned long long* seen) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
   const unsigned long long bit = 1ull << dev;
-  if (*seen & bit) return false;
-  *seen |= bit;
-  return true;
+  const unsigned long long old = __atomic_fetch_or(seen, bit, __ATOMIC_RELAXED);
+  return (old & bit) == 0;
 }
 void count_launch();
 

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <vector>
 #include "epilogue.cuh"
+#include "tc_common.cuh"
 
 namespace anyloc {
 
@@ -422,6 +423,7 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
     for (int i = s + lane; i < e; i += 32)
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xs + ooff[i]), "r"(rowbytes) : "memory");
   };
+  const uint64_t pol_stream = tc::l2_policy_stream();      // last reader of the features: evict_first
   int q = grab();
   prefetch_task(q);
   while (q < ntasks) {
@@ -440,7 +442,7 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
       for (; i + U <= e; i += U) {
         float4 v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(xb + ooff[i + u]));
+        for (int u = 0; u < U; ++u) v[u] = tc::ldg_hint_v4(xb + ooff[i + u], pol_stream);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const float sc = inv_s[i + u];
@@ -450,7 +452,7 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
       if (i < e) {                                           // tail: < U rows, same order
         float4 v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) if (i + u < e) v[u] = __ldg(reinterpret_cast<const float4*>(xb + ooff[i + u]));
+        for (int u = 0; u < U; ++u) if (i + u < e) v[u] = tc::ldg_hint_v4(xb + ooff[i + u], pol_stream);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (i + u < e) {

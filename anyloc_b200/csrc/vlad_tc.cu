@@ -42,6 +42,7 @@ struct AssignParams {
   int32_t* amb_count; int32_t* amb_rows; uint32_t* amb_mask;
   int32_t* zero_ptr; int zero_n;     // cleared here for a LATER launch on the stream (accumulate tickets), nullable
   int stages; int stage_bytes; int n_mma; int burst;
+  float l2_keep;     // fraction of the feature lines marked evict_last in L2 (0 = no hint); the accumulate pass re-reads them
   int diag;      // timing experiments only (tools/, results invalid): bit 0 = row-norm math off, bit 1 = MMAs off
 };
 
@@ -97,6 +98,7 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       // burst * 128 contiguous bytes of every row back to back, which the DRAM controller can serve from one open
       // page (a lone 128-byte access per row every few hundred ns re-opens the page each time).
       const uint32_t tx_bytes = (uint32_t)(A_BYTES + p.n_mma * 128);
+      const uint64_t pol_x = l2_policy_keep(p.l2_keep), pol_c = l2_policy_keep(1.0f);
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = tile * BM;
@@ -111,8 +113,9 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             const uint32_t fb = smem_u32(full_bar + stage);
             mbar_expect_tx(fb, tx_bytes);
             const uint32_t sbase = smem_u32(smem + stage * p.stage_bytes);
-            tma_load_2d(sbase, &tm_x, fb, (kb0 + j) * 32, m0);
-            tma_load_2d(sbase + A_BYTES, &tm_c, fb, (kb0 + j) * 32, 0);
+            if (p.l2_keep > 0.f) tma_load_2d_hint(sbase, &tm_x, fb, (kb0 + j) * 32, m0, pol_x);
+            else tma_load_2d(sbase, &tm_x, fb, (kb0 + j) * 32, m0);
+            tma_load_2d_hint(sbase + A_BYTES, &tm_c, fb, (kb0 + j) * 32, 0, pol_c);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -369,6 +372,12 @@ int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_
   if (stages_env >= 2) p.stages = std::min(p.stages, stages_env);
   p.diag = diag_env;
   p.burst = std::max(1, std::min(burst_env, p.stages / 2));
+  // L2 residency for the second pass (accumulate): keep what fits in ~60 % of the 126 MB L2.  ANYLOC_VLAD_L2KEEP_MB
+  // overrides the budget (0 disables the hints).
+  static int keep_mb = -1;
+  if (keep_mb < 0) { const char* e = getenv("ANYLOC_VLAD_L2KEEP_MB"); keep_mb = e ? atoi(e) : 76; }
+  const double feat_mb = (double)R * D * 4.0 / 1e6;
+  p.l2_keep = keep_mb > 0 ? (float)std::min(1.0, keep_mb / feat_mb) : 0.f;
   const size_t smem = (size_t)p.stages * p.stage_bytes + fixed;
   const int tiles = (int)((R + BM - 1) / BM);
   const int grid = std::min(tiles, device_sm_count());

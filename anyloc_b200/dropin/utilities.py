@@ -11,4 +11,4 @@ if _repo not in _sys.path:
 from anyloc_b200.utilities import *  # noqa: F401,F403,E402
 from anyloc_b200.utilities import (  # noqa: F401,E402
     VLAD, DinoV2ExtractFeatures, get_top_k_recall, seed_everything, reduce_pca, CustomDataset, to_np,
-    top_k_search, _DINO_V2_MODELS, _DINO_FACETS)
+    top_k_search, to_pil_list, pad_img, concat_desc_dists_clusters, FlatIndex, _DINO_V2_MODELS, _DINO_FACETS)

@@ -64,6 +64,44 @@ def to_np(x, ret_type=float) -> np.ndarray:
     return arr.astype(ret_type)
 
 
+def to_pil_list(x):
+    """utilities.py:99-129: an image / batch ([B,C,H,W], [B,H,W,C], [C,H,W] or [H,W,C]) -> list of PIL images, each
+    min-max normalised to 0..255.  Host-side helper (visualisation), not on the accelerated path."""
+    from PIL import Image
+    if type(x) == Image.Image or (type(x) == list and type(x[0]) == Image.Image):
+        return x
+    x = to_np(x)
+    if len(x.shape) == 3:
+        x = x[np.newaxis, ...]
+    out = []
+    for img in x:
+        if img.shape[0] in [1, 3]:
+            img = img.transpose(1, 2, 0)
+        norm = (img - img.min()) / (img.max() - img.min())
+        out.append(Image.fromarray((norm * 255).astype(np.uint8)))
+    return out
+
+
+def pad_img(img: np.ndarray, padding: int, color: tuple = (0, 0, 0)) -> np.ndarray:
+    """utilities.py:474-500: [H,W,3] -> [H+2P, W+2P, 3] with an RGB border.  Host-side helper."""
+    if type(color) == list:
+        color = tuple(color)
+    assert len(color) == 3, "Color should be (R, G, B) value"
+    ret = np.ones((img.shape[0] + 2 * padding, img.shape[1] + 2 * padding, 3), np.uint8) * np.array(color)
+    ret[padding:-padding, padding:-padding] = img
+    return ret.astype(img.dtype)
+
+
+def concat_desc_dists_clusters(cluster_centers: torch.Tensor, descs: torch.Tensor) -> torch.Tensor:
+    """utilities.py:590-619: per descriptor, the unit residuals to every centre, concatenated and L2-normalised
+    ([n, k*d]).  Plain tensor algebra on the caller's device, as in the reference (not on the hot path)."""
+    assert type(cluster_centers) == type(descs) == torch.Tensor
+    d = descs[:, None, :] - cluster_centers[None, ...]
+    d = d / d.norm(dim=-1, keepdim=True)
+    cat = d.reshape(d.shape[0], -1)
+    return cat / cat.norm(dim=-1, keepdim=True)
+
+
 def seed_everything(seed=42):
     """utilities.py:505-519."""
     random.seed(seed)
@@ -75,29 +113,105 @@ def seed_everything(seed=42):
     print(f"Seed set to: {seed} (type: {type(seed)})")
 
 
+def _gemm_nt_dev(a, b, bias=None):
+    """C = a @ b.T (+ bias) in fp32-equivalent precision on the tcgen05 engine (anyloc_gemm_nt, tf32 (hi,lo) pairs);
+    a [M,K], b [N,K] device fp32, K padded to a multiple of 4 with zeros."""
+    lib = _lib.load()
+    pad = (-a.shape[1]) % 4
+    if pad:
+        a, b = torch.nn.functional.pad(a, (0, pad)), torch.nn.functional.pad(b, (0, pad))
+    a, b = a.contiguous(), b.contiguous()
+    M, K = a.shape
+    N = b.shape[0]
+    out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    with torch.cuda.device(a.device):
+        pairs = []
+        for t in (a, b):
+            hi, lo = torch.empty_like(t), torch.empty_like(t)
+            _lib.check(lib.anyloc_split_tf32(_lib.ptr(t), _lib.ptr(hi), _lib.ptr(lo), t.numel(), _lib.stream_ptr()),
+                       "anyloc_split_tf32")
+            pairs += [hi, lo]
+        rc = lib.anyloc_gemm_nt(_lib.ptr(pairs[0]), _lib.ptr(pairs[1]), K, _lib.ptr(pairs[2]), _lib.ptr(pairs[3]), K,
+                                M, N, K, _lib.PAIR["tf32"], C.c_float(1.0), _lib.EPI["bias"], _lib.ptr(bias), None, None,
+                                _lib.ptr(out), None, N, _lib.PAIR["tf32"], _lib.ENGINE["auto"], _lib.stream_ptr())
+    _lib.check(rc, "anyloc_gemm_nt")
+    return out
+
+
+class _PcaDev:
+    """`sklearn.decomposition.PCA(k, svd_solver="full", whiten=...)` as reduce_pca uses it (utilities.py:560-586), on
+    the GPU: the fit is a one-off fp64 eigen-decomposition of the smaller Gram / covariance matrix (torch.linalg.eigh,
+    i.e. cuSOLVER: plumbing), the projections -- the part that touches every descriptor -- run as GEMMs on this
+    library's tcgen05 engine.  Component signs follow sklearn's `svd_flip(u_based_decision=False)`."""
+
+    def __init__(self, n_components, whiten=False):
+        self.n_components, self.whiten = int(n_components), bool(whiten)
+
+    def fit(self, x):
+        n, d = x.shape
+        k = self.n_components
+        if not 0 <= k <= min(n, d):
+            raise ValueError(f"n_components={k} must be between 0 and min(n_samples, n_features)={min(n, d)} with "
+                             "svd_solver='full'")
+        self.mean_ = x.mean(dim=0)
+        xd = (x - self.mean_).double()
+        if n <= d:
+            ev, u = torch.linalg.eigh(xd @ xd.T)
+            ev, u = ev.flip(0).clamp_min(0), u.flip(1)
+            s = ev.sqrt()
+            vt = (u[:, :k].T @ xd) / s[:k, None].clamp_min(1e-300)
+        else:
+            ev, v = torch.linalg.eigh(xd.T @ xd)
+            ev, v = ev.flip(0).clamp_min(0), v.flip(1)
+            s = ev.sqrt()
+            vt = v[:, :k].T.contiguous()
+        sign = torch.sign(torch.gather(vt, 1, vt.abs().argmax(dim=1, keepdim=True)))
+        sign[sign == 0] = 1
+        self.components_ = (vt * sign).float().contiguous()
+        self.singular_values_ = s[:k].float()
+        self.explained_variance_ = (s[:k] ** 2 / (n - 1)).float()
+        self.all_singular_values_ = s
+        return self
+
+    def transform(self, x):
+        y = _gemm_nt_dev(x - self.mean_, self.components_)
+        if self.whiten:
+            scale = self.explained_variance_.sqrt()
+            scale[scale < torch.finfo(scale.dtype).eps] = torch.finfo(scale.dtype).eps
+            y = y / scale
+        return y
+
+
 def reduce_pca(train_descs: np.ndarray, test_descs: np.ndarray, lower_dim: int, low_factor: float = 0.0,
                fallback: int = 256, svd_solver: str = "full", whitening: bool = False) \
         -> Tuple[np.ndarray, np.ndarray]:
-    """PCA projection fitted on the training set (utilities.py:522-586); host-side sklearn, not
-    part of the accelerated path."""
-    from sklearn.decomposition import PCA
+    """PCA projection fitted on the training set (utilities.py:522-586; scripts/dino_v2_vlad.py:357-369 reduces the
+    database / query VLADs with it).  Same arguments and return types (numpy in -> numpy out, torch tensors accepted);
+    the arithmetic runs on the GPU -- see _PcaDev.  `svd_solver` is accepted for signature compatibility: the result
+    is the exact ("full") decomposition."""
     assert 0 <= low_factor <= 1
+    as_np = type(train_descs) == np.ndarray
+    dev = _lib.require_cuda(None)
+    tr, te = _as_device_f32(train_descs, dev), _as_device_f32(test_descs, dev)
+
+    def ret(a, b):
+        return (a.cpu().numpy(), b.cpu().numpy()) if as_np else (a.cpu(), b.cpu())
+
     if low_factor == 0.0:
-        pca = PCA(lower_dim, svd_solver=svd_solver, whiten=whitening)
-        return pca.fit_transform(train_descs), pca.transform(test_descs)
-    n_samples, n_components = train_descs.shape
+        pca = _PcaDev(lower_dim, whiten=whitening).fit(tr)
+        return ret(pca.transform(tr), pca.transform(te))
+    n_samples, n_components = tr.shape
     if n_samples < n_components:
         print(f"Too few samples, fallback to {fallback}d first")
-        both = np.concatenate((train_descs.copy(), test_descs.copy()))
-        both = PCA(fallback, svd_solver=svd_solver).fit_transform(both)
-        train_descs, test_descs = both[:n_samples], both[n_samples:]
+        both = torch.cat((tr, te))
+        both = _PcaDev(fallback).fit(both).transform(both)
+        tr, te = both[:n_samples].contiguous(), both[n_samples:].contiguous()
     n_low = int(low_factor * lower_dim)
     n_top = lower_dim - n_low
     print(f"Up: {n_top}, Down: {n_low}")
-    pca = PCA(train_descs.shape[1], svd_solver=svd_solver)
-    pca.fit(train_descs)
-    basis = np.concatenate((pca.components_[:n_top], pca.components_[-n_low:]))
-    return (train_descs - pca.mean_) @ basis.T, (test_descs - pca.mean_) @ basis.T
+    pca = _PcaDev(tr.shape[1]).fit(tr)
+    basis = torch.cat((pca.components_[:n_top], pca.components_[-n_low:])).contiguous()
+    return ret(_gemm_nt_dev(tr - pca.mean_, basis), _gemm_nt_dev(te - pca.mean_, basis))
 
 
 # ------------------------------------------------------------------ image pre-processing (extension)
@@ -112,12 +226,19 @@ def center_crop_box(h: int, w: int, patch: int = 14) -> Tuple[int, int, int, int
     return int(round((h - h_new) / 2.0)), int(round((w - w_new) / 2.0)), h_new, w_new
 
 
+_INTERP = {"bilinear": 0, "bicubic": 1}
+
+
 def preprocess_images(imgs: Union[np.ndarray, torch.Tensor], mean=IMAGENET_MEAN, std=IMAGENET_STD,
-                      patch: int = 14, device: Union[str, torch.device, None] = None) -> torch.Tensor:
+                      patch: int = 14, device: Union[str, torch.device, None] = None,
+                      resize: Union[Tuple[int, int], None] = None, interpolation: str = "bilinear") -> torch.Tensor:
     """uint8 RGB images [B,H,W,3] (or one [H,W,3]) -> the extractor's input [B,3,H',W'] on the GPU: the reference's
-    `base_transform` (ToTensor + Normalize, dvgl_benchmark/datasets_ws.py:20-23) and its centre crop to a multiple
-    of the patch size (scripts/dino_v2_vlad.py:174-176) in one kernel; bit-identical to the torchvision pipeline,
-    a quarter of the host->device bytes of sending normalised fp32 images."""
+    `base_transform` (ToTensor + Normalize, dvgl_benchmark/datasets_ws.py:20-23), optionally the dataset loader's
+    `T.functional.resize(img, resize)` (:233-235, `resize=(480, 640)` is the reference default, configs.py:141; or the
+    demo's bicubic down-scaling, demo/anyloc_vlad_generate.py:165-177) and the centre crop to a multiple of the patch
+    size (scripts/dino_v2_vlad.py:174-176) in ONE kernel.  Without `resize` the result is bit-identical to the
+    torchvision pipeline; with it, antialiased bilinear / bicubic resampling as torchvision applies to tensors (fp32
+    rounding differences only).  A quarter of the host->device bytes of sending normalised fp32 images."""
     if type(imgs) == np.ndarray:
         imgs = torch.from_numpy(imgs)
     if imgs.dtype != torch.uint8:
@@ -126,18 +247,26 @@ def preprocess_images(imgs: Union[np.ndarray, torch.Tensor], mean=IMAGENET_MEAN,
         imgs = imgs[None]
     if imgs.dim() != 4 or imgs.shape[-1] != 3:
         raise ValueError(f"preprocess_images expects [B,H,W,3], got {tuple(imgs.shape)}")
+    if interpolation not in _INTERP:
+        raise ValueError(f"interpolation must be one of {sorted(_INTERP)}, got {interpolation!r}")
     dev = _lib.require_cuda(imgs.device if imgs.is_cuda else (torch.device(device) if device is not None else None))
     x = imgs.to(dev, non_blocking=True).contiguous()
     B, H, W, _ = x.shape
-    top, left, hc, wc = center_crop_box(H, W, patch)
+    hr, wr = (H, W) if resize is None else (int(resize[0]), int(resize[1]))
+    top, left, hc, wc = center_crop_box(hr, wr, patch)
     if hc == 0 or wc == 0:
-        raise ValueError(f"image {H}x{W} is smaller than one {patch}x{patch} patch")
+        raise ValueError(f"image {hr}x{wr} is smaller than one {patch}x{patch} patch")
     out = torch.empty(B, 3, hc, wc, device=dev, dtype=torch.float32)
     m3 = (C.c_float * 3)(*[float(v) for v in mean])
     s3 = (C.c_float * 3)(*[float(v) for v in std])
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().anyloc_preprocess_u8(_lib.ptr(x), B, H, W, top, left, hc, wc, m3, s3, _lib.ptr(out),
-                                                    _lib.stream_ptr()), "anyloc_preprocess_u8")
+        if resize is None:
+            _lib.check(_lib.load().anyloc_preprocess_u8(_lib.ptr(x), B, H, W, top, left, hc, wc, m3, s3, _lib.ptr(out),
+                                                        _lib.stream_ptr()), "anyloc_preprocess_u8")
+        else:
+            _lib.check(_lib.load().anyloc_preprocess_resize_u8(_lib.ptr(x), B, H, W, hr, wr, _INTERP[interpolation], top,
+                                                               left, hc, wc, m3, s3, _lib.ptr(out), _lib.stream_ptr()),
+                       "anyloc_preprocess_resize_u8")
     return out
 
 

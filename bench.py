@@ -560,19 +560,22 @@ def pipeline_parity(wl, sd_host, img_host, vlad, desc, ext, u, n=2):
     got_f = ext(img_host[:n].to(ext.device)).cpu()
     centers = vlad.c_centers.cpu()
     err_f = float((got_f - ref_f).abs().max() / ref_f.abs().max())
-    # descriptors: reference arithmetic on the reference features, labels forced to the GPU's outside the fp64-ambiguous
-    # set is unnecessary here -- a flipped label would show up as an O(1) error
-    ref_v = torch.stack([ao.vlad_generate(f, centers) for f in ref_f])
     got_v = desc[:n].cpu()
+    # (1) the VLAD kernels alone: reference arithmetic on the SAME (GPU) features
+    same_v = torch.stack([ao.vlad_generate(f, centers) for f in got_f])
+    err_v_same = float((got_v - same_v).abs().max() / same_v.abs().max())
+    # (2) end to end: reference arithmetic on the reference features.  With the vocabulary fitted on this very batch the
+    # residual sums cancel heavily (sum over a cluster's members of x^ - c_k is ~0 by construction), so the feature
+    # error is amplified by the conditioning of the descriptor itself; reported, not gated.
+    ref_v = torch.stack([ao.vlad_generate(f, centers) for f in ref_f])
     err_v = float((got_v - ref_v).abs().max() / ref_v.abs().max())
-    # label agreement on the reference features (exact outside near-ties)
     lab_ref = torch.stack([ao.vlad_labels(f, centers) for f in ref_f])
     lab_got = torch.stack([ao.vlad_labels(f, centers) for f in got_f])
-    return {"images": n, "features_rel_err": err_f, "descriptors_rel_err": err_v,
-            "labels_differ": int((lab_ref != lab_got).sum()), "labels_total": int(lab_ref.numel()),
-            "tolerance": 1e-4, "ok": bool(err_f < 1e-4),
-            "note": "descriptor error includes label flips of near-tied patches between fp32 feature sets that differ by "
-                    "features_rel_err (each flip moves one patch between two clusters)"}
+    return {"images": n, "features_rel_err": err_f, "descriptors_rel_err_same_features": err_v_same,
+            "descriptors_rel_err_end_to_end": err_v, "labels_differ": int((lab_ref != lab_got).sum()),
+            "labels_total": int(lab_ref.numel()), "tolerance": 1e-4, "ok": bool(err_f < 1e-4 and err_v_same < 1e-4),
+            "note": "end-to-end descriptor error = feature error x conditioning of the descriptor (vocabulary fitted on the "
+                    "batch itself: residual sums nearly cancel); gated: features and the VLAD kernels on equal features"}
 
 
 # ------------------------------------------------------------------ retrieval (c3 / c4)

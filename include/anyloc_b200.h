@@ -244,6 +244,14 @@ int anyloc_pool(const float* feats, const int32_t* n_valid, int B, int N, int D,
  * img [B,H,W,3] uint8 (device), mean3/std3 HOST arrays of 3 floats, out [B,3,Hc,Wc] fp32 (device). */
 int anyloc_preprocess_u8(const uint8_t* img, int B, int H, int W, int top, int left, int Hc, int Wc,
                          const float* mean3, const float* std3, float* out, void* stream);
+/* The same with the dataset loader's resize in between (dvgl_benchmark/datasets_ws.py:222-239
+ * `T.functional.resize(base_transform(img), [480, 640])`; demo/anyloc_vlad_generate.py:165-177 bicubic down-scaling of
+ * over-sized images): ToTensor + Normalize, ANTIALIASED resize to Hr x Wr (interpolation 0 = bilinear, 1 = bicubic --
+ * torchvision's tensor defaults, i.e. torch interpolate(align_corners=False, antialias=True)), then the crop window
+ * [top, top+Hc) x [left, left+Wc) of the resized image.  out [B,3,Hc,Wc]. */
+int anyloc_preprocess_resize_u8(const uint8_t* img, int B, int H, int W, int Hr, int Wr, int interpolation, int top,
+                                int left, int Hc, int Wc, const float* mean3, const float* std3, float* out,
+                                void* stream);
 
 #ifdef __cplusplus
 }

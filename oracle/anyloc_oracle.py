@@ -61,12 +61,18 @@ def extract_features_full_forward(model, img, layer, facet="value", use_cls=Fals
 
 
 # --------------------------------------------------------------------- pre-processing
-def preprocess(img_u8, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), patch=14):
+def preprocess(img_u8, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), patch=14, resize=None,
+               interpolation="bilinear"):
     """`base_transform` (dvgl_benchmark/datasets_ws.py:20-23: ToTensor = HWC uint8 -> CHW float / 255, Normalize =
-    (x - mean) / std) then `T.CenterCrop(((h // 14) * 14, (w // 14) * 14))` (scripts/dino_v2_vlad.py:174-176;
-    torchvision puts the window at int(round((h - h_new) / 2.0))).  img_u8 [H,W,3] uint8 -> [3,h_new,w_new]."""
+    (x - mean) / std), optionally `T.functional.resize(img, resize)` (:233-235; on a float tensor torchvision calls
+    torch interpolate(mode, align_corners=False, antialias=True) -- `interpolation="bicubic"` is the demo's
+    down-scaling, demo/anyloc_vlad_generate.py:165-177), then `T.CenterCrop(((h // 14) * 14, (w // 14) * 14))`
+    (scripts/dino_v2_vlad.py:174-176; torchvision puts the window at int(round((h - h_new) / 2.0))).
+    img_u8 [H,W,3] uint8 -> [3,h_new,w_new]."""
     x = torch.as_tensor(img_u8).permute(2, 0, 1).to(torch.float32).div(255)
     x = (x - torch.tensor(mean, dtype=torch.float32)[:, None, None]) / torch.tensor(std, dtype=torch.float32)[:, None, None]
+    if resize is not None:
+        x = F.interpolate(x[None], size=tuple(resize), mode=interpolation, align_corners=False, antialias=True)[0]
     h, w = x.shape[1:]
     hn, wn = (h // patch) * patch, (w // patch) * patch
     top, left = int(round((h - hn) / 2.0)), int(round((w - wn) / 2.0))
@@ -259,3 +265,25 @@ def clustered_features(n, d, k, seed=0, kappa_noise=0.35, centre_norm=0.8):
     x = F.normalize(mu[lab] + kappa_noise / d ** 0.5 * torch.randn(n, d, generator=g), dim=1)
     centres = centre_norm * mu * (1.0 + 0.1 * torch.rand(k, 1, generator=g))
     return x, centres, lab
+
+
+# ---------------------------------------------------------------- PCA (descriptor dimensionality reduction)
+def reduce_pca(train_descs, test_descs, lower_dim, low_factor=0.0, fallback=256, svd_solver="full", whitening=False):
+    """utilities.py:522-586, restated on the same sklearn calls (sklearn.decomposition.PCA; pinned against the verbatim
+    import by tests/test_oracle_cpu.py::test_reduce_pca_matches_reference)."""
+    from sklearn.decomposition import PCA
+    assert 0 <= low_factor <= 1
+    if low_factor == 0.0:                                                    # :560-563
+        pca = PCA(lower_dim, svd_solver=svd_solver, whiten=whitening)
+        return pca.fit_transform(train_descs), pca.transform(test_descs)
+    n_samples, n_components = train_descs.shape                              # :565
+    if n_samples < n_components:                                             # :566-574
+        both = np.concatenate((train_descs.copy(), test_descs.copy()))
+        both = PCA(fallback, svd_solver=svd_solver).fit_transform(both)
+        train_descs, test_descs = both[:n_samples], both[n_samples:]
+    n_low = int(low_factor * lower_dim)                                      # :575-576
+    n_top = lower_dim - n_low
+    pca = PCA(train_descs.shape[1], svd_solver=svd_solver)                   # :578-580
+    pca.fit(train_descs)
+    basis = np.concatenate((pca.components_[:n_top], pca.components_[-n_low:]))   # :581-582
+    return (train_descs - pca.mean_) @ basis.T, (test_descs - pca.mean_) @ basis.T   # :583-584

@@ -190,6 +190,21 @@ def make_preprocess():
         out[f"{tag}/out"] = res.numpy()
     np.savez_compressed(os.path.join(OUT, "preprocess.npz"), **out)
     print("preprocess.npz")
+    # with the dataset loader's resize (dvgl_benchmark/datasets_ws.py:233-235, `T.functional.resize(img, self.resize)` on
+    # the normalised tensor) / the demo's bicubic down-scaling (demo/anyloc_vlad_generate.py:165-177), by torchvision
+    out = {}
+    for tag, (h, w), size, mode in (("bilinear_97x131_to_60x80", (97, 131), (60, 80), T.InterpolationMode.BILINEAR),
+                                    ("bilinear_40x52_to_60x80", (40, 52), (60, 80), T.InterpolationMode.BILINEAR),
+                                    ("bicubic_150x90_to_70x42", (150, 90), (70, 42), T.InterpolationMode.BICUBIC),
+                                    ("bicubic_33x47_to_58x83", (33, 47), (58, 83), T.InterpolationMode.BICUBIC)):
+        img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        t = T.functional.resize(base_transform(Image.fromarray(img, "RGB")), list(size), interpolation=mode)
+        res = T.CenterCrop(((size[0] // 14) * 14, (size[1] // 14) * 14))(t)
+        out[f"{tag}/img"] = img
+        out[f"{tag}/out"] = res.numpy()
+        out[f"{tag}/size"] = np.array(size)
+    np.savez_compressed(os.path.join(OUT, "preprocess_resize.npz"), **out)
+    print("preprocess_resize.npz")
 
 
 def make_build_vlads():

@@ -32,7 +32,7 @@ def test_library_contains_sm100a_code(lib):
 def test_mirror_api_surface():
     from anyloc_b200 import utilities as u
     for name in ("VLAD", "DinoV2ExtractFeatures", "get_top_k_recall", "seed_everything", "reduce_pca",
-                 "CustomDataset", "to_np"):
+                 "CustomDataset", "to_np", "to_pil_list", "pad_img", "concat_desc_dists_clusters"):
         assert hasattr(u, name)
     import inspect
     sig = inspect.signature(u.VLAD.__init__)
@@ -98,3 +98,22 @@ def test_cache_predicates_and_fit_errors(tmp_path):
     assert v.desc_dim == 16 and v.c_centers.shape == (3, 16)
     with pytest.raises(ValueError):
         u.VLAD(3).fit(None)
+
+
+def test_host_helpers_match_reference():
+    """the pass-through helpers of utilities.py (:99-129 to_pil_list, :474-500 pad_img, :590-619
+    concat_desc_dists_clusters) against the verbatim import"""
+    import numpy as np
+    from oracle import reference_import as ri
+    if not ri.available():
+        pytest.skip("reference tree not present")
+    ref = ri.load_reference_utilities()
+    from anyloc_b200 import utilities as u
+    g = torch.Generator().manual_seed(0)
+    c, x = torch.randn(5, 16, generator=g), torch.randn(9, 16, generator=g)
+    assert torch.equal(ref.concat_desc_dists_clusters(c, x), u.concat_desc_dists_clusters(c, x))
+    img = (np.random.default_rng(0).random((10, 12, 3)) * 255).astype(np.uint8)
+    assert np.array_equal(ref.pad_img(img, 2, (255, 0, 3)), u.pad_img(img, 2, [255, 0, 3]))
+    for batch in (torch.rand(2, 3, 8, 9, generator=g), torch.rand(8, 9, 3, generator=g)):
+        a, b = ref.to_pil_list(batch), u.to_pil_list(batch)
+        assert len(a) == len(b) and all(np.array_equal(np.asarray(p), np.asarray(q)) for p, q in zip(a, b))

@@ -179,3 +179,17 @@ def test_restated_vit_matches_hf_port(name, depth):
         hs = hf(pixel_values=img, output_hidden_states=True).hidden_states   # [emb, blk0, blk1, ...]
     tok = ao.extract_features(model, img, depth - 1, "token", use_cls=True, norm_descs=False)
     assert torch.allclose(tok, hs[depth], atol=2e-5, rtol=1e-5)
+
+
+def test_reduce_pca_matches_reference():
+    """oracle.reduce_pca == the reference's reduce_pca (utilities.py:522-586), both branches, bit for bit."""
+    if not ri.available():
+        pytest.skip("reference tree not present")
+    ref = ri.load_reference_utilities()
+    g = np.random.default_rng(0)
+    tr = (g.standard_normal((200, 24)) * (0.8 ** np.arange(24))).astype(np.float32)
+    te = (g.standard_normal((31, 24)) * (0.8 ** np.arange(24))).astype(np.float32)
+    for kw in (dict(whitening=False), dict(whitening=True), dict(low_factor=0.25)):
+        a = ref.reduce_pca(tr.copy(), te.copy(), 8, **kw)
+        b = ao.reduce_pca(tr.copy(), te.copy(), 8, **kw)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])

@@ -37,6 +37,29 @@ def test_preprocess_sizes(u, B, H, W):
     assert torch.equal(out2.cpu(), ref2)
 
 
+@pytest.mark.parametrize("name", sorted(load_cases("preprocess_resize.npz")))
+def test_preprocess_resize_golden(u, name):
+    """ToTensor + Normalize + torchvision's antialiased tensor resize + centre crop, golden vectors made by torchvision
+    (dvgl_benchmark/datasets_ws.py:233-235; demo/anyloc_vlad_generate.py:165-177)."""
+    c = load_cases("preprocess_resize.npz")[name]
+    mode = name.split("_")[0]
+    out = u.preprocess_images(c["img"], resize=tuple(int(v) for v in c["size"]), interpolation=mode)
+    assert out.shape == (1,) + c["out"].shape
+    err = float((out[0].cpu() - torch.from_numpy(c["out"])).abs().max())
+    assert err < 2e-5, (name, err)               # values are O(1): fp32 rounding of the weights / summation order
+
+
+@pytest.mark.parametrize("mode", ["bilinear", "bicubic"])
+@pytest.mark.parametrize("B,H,W,size", [(2, 720, 1280, (480, 640)), (1, 333, 517, (480, 640)), (2, 1200, 900, (1024, 768))])
+def test_preprocess_resize_sizes(u, mode, B, H, W, size):
+    g = torch.Generator().manual_seed(H + W)
+    img = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g)
+    out = u.preprocess_images(img, resize=size, interpolation=mode)
+    ref = torch.stack([ao.preprocess(i, resize=size, interpolation=mode) for i in img])
+    assert out.shape == ref.shape
+    assert float((out.cpu() - ref).abs().max()) < 2e-5
+
+
 def test_preprocess_feeds_extractor(u):
     """uint8 images -> preprocess_images -> extractor equals the float path on the torchvision-style input."""
     from oracle import dinov2_restated as dr
