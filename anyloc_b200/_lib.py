@@ -71,6 +71,7 @@ _SIGS = {
                                    [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "anyloc_vlad_assign": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 +
                            [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "anyloc_kmeans_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "anyloc_kmeans_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 3 +
                              [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "anyloc_topk_workspace_bytes": (C.c_size_t, [C.c_int] * 4),

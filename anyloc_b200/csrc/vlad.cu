@@ -423,7 +423,6 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
     for (int i = s + lane; i < e; i += 32)
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xs + ooff[i]), "r"(rowbytes) : "memory");
   };
-  const uint64_t pol_stream = tc::l2_policy_stream();      // last reader of the features: evict_first
   int q = grab();
   prefetch_task(q);
   while (q < ntasks) {
@@ -442,7 +441,7 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
       for (; i + U <= e; i += U) {
         float4 v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = tc::ldg_hint_v4(xb + ooff[i + u], pol_stream);
+        for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(xb + ooff[i + u]));
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const float sc = inv_s[i + u];
@@ -452,7 +451,7 @@ vlad_accumulate3_kernel(const float* __restrict__ x, const int32_t* __restrict__
       if (i < e) {                                           // tail: < U rows, same order
         float4 v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) if (i + u < e) v[u] = tc::ldg_hint_v4(xb + ooff[i + u], pol_stream);
+        for (int u = 0; u < U; ++u) if (i + u < e) v[u] = __ldg(reinterpret_cast<const float4*>(xb + ooff[i + u]));
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (i + u < e) {
@@ -841,10 +840,13 @@ vlad_normalize_kernel(float* __restrict__ vlad, const float* __restrict__ partia
 }
 
 // ------------------------------------------------------------------ k-means update
+// Deterministic: every (column slice, row chunk) CTA writes ITS partial sums / counts, the finalize kernel adds the
+// chunks in chunk order -- no floating-point atomics, so a fitted vocabulary is bit-reproducible for a fixed seed
+// (like the reference's single-threaded mask @ X).
 __global__ void kmeans_accumulate_kernel(const float* __restrict__ x, const int32_t* __restrict__ labels,
-                                         int64_t R, int D, int K, float* __restrict__ sums,
-                                         float* __restrict__ counts) {
-  // grid (D/128 slices, row-chunks); shared [K][128] partial sums, then atomics into sums
+                                         int64_t R, int D, int K, float* __restrict__ psums /* [chunks,K,D] */,
+                                         float* __restrict__ pcounts /* [chunks,K] */) {
+  // grid (D/128 slices, row-chunks); shared [K][128] partial sums
   extern __shared__ float acc[];
   const int t = threadIdx.x, col = blockIdx.x * ACC_COLS + t;
   const bool colok = col < D;
@@ -861,34 +863,42 @@ __global__ void kmeans_accumulate_kernel(const float* __restrict__ x, const int3
     if (blockIdx.x == 0 && t == 0) cnt[l] += 1.f;
   }
   __syncthreads();
+  float* ps = psums + (size_t)blockIdx.y * K * D;
   for (int k = 0; k < K; ++k)
-    if (colok && acc[k * ACC_COLS + t] != 0.f) atomicAdd(&sums[(size_t)k * D + col], acc[k * ACC_COLS + t]);
+    if (colok) ps[(size_t)k * D + col] = acc[k * ACC_COLS + t];
   if (blockIdx.x == 0)
-    for (int k = t; k < K; k += ACC_COLS) if (cnt[k] != 0.f) atomicAdd(&counts[k], cnt[k]);
+    for (int k = t; k < K; k += ACC_COLS) pcounts[(size_t)blockIdx.y * K + k] = cnt[k];
 }
 
-__global__ void kmeans_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ counts,
-                                       const float* __restrict__ old_c, int D, int K,
-                                       float* __restrict__ new_c, float* __restrict__ err) {
-  // one block; err = sum((new-old)^2)
+__global__ void __launch_bounds__(256)
+kmeans_finalize_kernel(const float* __restrict__ psums, const float* __restrict__ pcounts, int chunks,
+                       const float* __restrict__ old_c, int D, int K, float* __restrict__ new_c,
+                       float* __restrict__ perr /* [gridDim.x] */) {
+  // grid-stride over the K*D centre elements; per-block squared shift -> perr[block] (summed in order by the last kernel)
   float e = 0.f;
-  for (size_t i = threadIdx.x; i < (size_t)K * D; i += blockDim.x) {
-    int k = (int)(i / D);
-    float c = counts[k];
-    float v = c > 0.f ? sums[i] / c : 0.f;    // NaN -> 0 for empty clusters (fpk)
+  const size_t total = (size_t)K * D;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i / D);
+    float c = 0.f, sm = 0.f;
+    for (int ch = 0; ch < chunks; ++ch) { c += pcounts[(size_t)ch * K + k]; sm += psums[(size_t)ch * total + i]; }
+    const float v = c > 0.f ? sm / c : 0.f;    // NaN -> 0 for empty clusters (fpk)
     new_c[i] = v;
-    float d = v - old_c[i];
+    const float d = v - old_c[i];
     e += d * d;
   }
-  __shared__ float red[32];
+  __shared__ float red[8];
   e = warp_sum(e);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
   __syncthreads();
   if (threadIdx.x == 0) {
     float tot = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
-    err[0] = tot;
+    perr[blockIdx.x] = tot;
   }
+}
+
+__global__ void kmeans_err_kernel(const float* __restrict__ perr, int n, float* __restrict__ err) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { float t = 0.f; for (int i = 0; i < n; ++i) t += perr[i]; err[0] = t; }
 }
 
 }  // namespace anyloc
@@ -1232,25 +1242,41 @@ extern "C" int anyloc_vlad_generate_soft(const float* feats, const int32_t* n_va
   return ANYLOC_OK;
 }
 
+static int kmeans_chunks(int R, int D) {
+  const int nslices = cdiv(D, ACC_COLS);
+  return std::max(1, std::min(std::min((int)((R + 255) / 256), 4 * device_sm_count() / std::max(1, nslices)), 64));
+}
+constexpr int KMEANS_FIN_BLOCKS = 64;
+
+extern "C" size_t anyloc_kmeans_workspace_bytes(int R, int D, int K) {
+  const size_t chunks = (size_t)kmeans_chunks(R, D);
+  return align_up(chunks * K * D * 4, 256) + align_up(chunks * K * 4, 256) + align_up(KMEANS_FIN_BLOCKS * 4, 256) + 256;
+}
+
 extern "C" int anyloc_kmeans_update(const float* x, const int32_t* labels, const float* old_centers,
                                     int R, int D, int K, float* new_centers, float* err_out, void* ws,
                                     size_t ws_bytes, void* stream) {
   ANYLOC_REQUIRE(x && labels && old_centers && new_centers && err_out && ws, "kmeans_update: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = kmeans_chunks(R, D);
   Workspace w(ws, ws_bytes);
-  float* sums = w.take<float>((size_t)K * D + K);
-  if (!sums) { set_error("kmeans_update: workspace too small"); return ANYLOC_ERR_WORKSPACE; }
-  float* counts = sums + (size_t)K * D;
-  ANYLOC_CHECK_CUDA(cudaMemsetAsync(sums, 0, ((size_t)K * D + K) * 4, st));
+  float* psums = w.take<float>((size_t)chunks * K * D);
+  float* pcounts = w.take<float>((size_t)chunks * K);
+  float* perr = w.take<float>(KMEANS_FIN_BLOCKS);
+  if (!psums || !pcounts || !perr) {
+    set_error("kmeans_update: workspace too small (%zu given, %zu needed)", ws_bytes, anyloc_kmeans_workspace_bytes(R, D, K));
+    return ANYLOC_ERR_WORKSPACE;
+  }
   size_t smem = ((size_t)K * ACC_COLS + K) * 4;
   ANYLOC_REQUIRE(smem <= 220 * 1024, "kmeans_update: K=%d too large", K);
   ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(kmeans_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
   int nslices = cdiv(D, ACC_COLS);
-  int chunks = std::max(1, std::min((int)((R + 255) / 256), 4 * device_sm_count() / std::max(1, nslices)));
-  kmeans_accumulate_kernel<<<dim3(nslices, chunks), ACC_COLS, smem, st>>>(x, labels, R, D, K, sums, counts);
+  kmeans_accumulate_kernel<<<dim3(nslices, chunks), ACC_COLS, smem, st>>>(x, labels, R, D, K, psums, pcounts);
   ANYLOC_CHECK_LAUNCH();
-  kmeans_finalize_kernel<<<1, 1024, 0, st>>>(sums, counts, old_centers, D, K, new_centers, err_out);
+  kmeans_finalize_kernel<<<KMEANS_FIN_BLOCKS, 256, 0, st>>>(psums, pcounts, chunks, old_centers, D, K, new_centers, perr);
+  ANYLOC_CHECK_LAUNCH();
+  kmeans_err_kernel<<<1, 32, 0, st>>>(perr, KMEANS_FIN_BLOCKS, err_out);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }

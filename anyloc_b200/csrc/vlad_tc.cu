@@ -14,9 +14,11 @@
 //             (and of what the tensor core's tf32 truncation drops), then the tile epilogue: S~ from TMEM, candidate set
 //             {k : S~_k >= max - 2 eps} with a rigorous per-row bound eps on |S~ - S| built from those MEASURED norms
 //             (see the epilogue).  One candidate -> that IS the exact-fp32 argmax.
-//             Several -> (row, candidate mask) goes to the work list.
-// vlad_rescore_amb_kernel -- warp per work-list row: exact fp32 dot products for the candidates only (same arithmetic
-// as the v2 rescoring kernel), first-max argmax -> lowest index wins exact ties, all-zero rows get label 0.
+//             Several -> (row, candidate mask) goes to the tile's shared-memory list (double buffered).
+//   warps 8-15 exact re-scoring of the listed rows while the stream continues: warp per row, the row re-read from L2
+//             (it passed through this SM microseconds ago), exact fp32 dot products for the candidates only (the
+//             arithmetic of the v2 rescoring kernel), first-max argmax -> lowest index wins exact ties, all-zero rows
+//             get label 0.  (Round 1 ran this as a separate launch over a global work list: 12-16 us at c2, 30 us at c5.)
 #include <cuda.h>
 #include <algorithm>
 #include <stdlib.h>
@@ -28,23 +30,73 @@ using namespace tc;
 
 constexpr int BM = 128;
 constexpr int A_BYTES = BM * 128;          // 16 KB: 128 rows x 128 B
-constexpr int THREADS = 256;
+constexpr int R_WARPS = 8;                 // exact re-scoring warps (warps 8..15)
+constexpr int THREADS = 256 + R_WARPS * 32;
 constexpr int TMEM_COLS = 256;             // 2 accumulators x 128 columns
 constexpr int MAX_STAGES = 12;
 constexpr int MAX_K = 128;
-constexpr int BAR_BYTES = 256;             // (2*MAX_STAGES + 4) mbarriers + the TMEM slot
+constexpr int BAR_BYTES = 320;             // (2*MAX_STAGES + 4) mbarriers, the TMEM slot, 4 list mbarriers
 constexpr int VEC_BYTES = 3 * MAX_K * 4;   // cbias + cnorm + cdnorm
+constexpr int LIST_BYTES = 2 * (BM * 4 + BM * (MAX_K / 32) * 4) + 16;   // 2 x {ambiguous rows, candidate masks} + counters
 
 struct AssignParams {
   const int32_t* n_valid; int n_per_img; int R; int D; int K;
   const float* cbias; const float* cnorm; const float* cdnorm;
   int32_t* labels; float* inv_norm;
-  int32_t* amb_count; int32_t* amb_rows; uint32_t* amb_mask;
+  const float* x; const float* chat;  // features [R,D] and the exact fp32 c^ [K,D]: the in-kernel re-scoring reads them
+  int32_t* amb_count; int32_t* amb_rows; uint32_t* amb_mask;   // (unused since the re-scoring moved into this kernel)
   int32_t* zero_ptr; int zero_n;     // cleared here for a LATER launch on the stream (accumulate tickets), nullable
   int stages; int stage_bytes; int n_mma; int burst;
-  float l2_keep;     // fraction of the feature lines marked evict_last in L2 (0 = no hint); the accumulate pass re-reads them
+  int tile_rows;     // rows per tile (<= BM, multiple of 8), chosen on the host so that the tiles fill whole waves of the grid
   int diag;      // timing experiments only (tools/, results invalid): bit 0 = row-norm math off, bit 1 = MMAs off
 };
+
+// Exact fp32 re-scoring of ONE ambiguous row by one warp: dot products with the candidate centres only (mask), in
+// ascending k with a strict >, so the lowest index wins exact ties and all-zero rows get label 0 -- the arithmetic of the
+// v2 re-scoring pass.  The row (D <= 2048) lives in registers.
+__device__ __forceinline__ void rescore_row(const AssignParams& p, const float* s_cbias, int64_t row, const uint32_t* mask_w,
+                                            int lane) {
+  constexpr int MAXV = 16;
+  const int D4 = p.D >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(p.x + row * (int64_t)p.D);
+  float4 v[MAXV];
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int d = lane + j * 32;
+    v[j] = d < D4 ? __ldg(xr + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float best = -INFINITY; int bestk = 0;
+  for (int w = 0; w < MAX_K / 32; ++w) {
+    uint32_t mask = mask_w[w];
+    const int k0 = w * 32;
+    while (mask) {
+      int kk[4]; int nc = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (mask) { kk[q] = k0 + __ffs(mask) - 1; mask &= mask - 1; ++nc; } else kk[q] = kk[0];
+      }
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < MAXV; ++j) {
+        const int d = lane + j * 32;
+        if (d < D4) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 c = __ldg(reinterpret_cast<const float4*>(p.chat + (size_t)kk[q] * p.D) + d);
+            acc[q] = fmaf(v[j].x, c.x, acc[q]); acc[q] = fmaf(v[j].y, c.y, acc[q]);
+            acc[q] = fmaf(v[j].z, c.z, acc[q]); acc[q] = fmaf(v[j].w, c.w, acc[q]);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float sc = warp_sum(acc[q]) + s_cbias[kk[q]];
+        if (q < nc && sc > best) { best = sc; bestk = kk[q]; }
+      }
+    }
+  }
+  if (lane == 0) p.labels[row] = bestk;
+}
 
 __global__ void __launch_bounds__(THREADS, 1)
 vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_c,
@@ -60,10 +112,15 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   float* s_cbias = reinterpret_cast<float*>(bar_area + BAR_BYTES);      // [MAX_K]
   float* s_cnorm = s_cbias + MAX_K;                                     // [MAX_K]
   float* s_cdnorm = s_cnorm + MAX_K;                                    // [MAX_K]
+  uint64_t* list_full = tempty_bar + 2 + 1;                             // [2] epilogue -> re-scoring warps (after the TMEM slot word pair)
+  uint64_t* list_free = list_full + 2;                                  // [2] re-scoring warps -> epilogue
+  int32_t* amb_row = reinterpret_cast<int32_t*>(bar_area + BAR_BYTES + VEC_BYTES);    // [2][BM]
+  uint32_t* amb_msk = reinterpret_cast<uint32_t*>(amb_row + 2 * BM);                   // [2][BM][MAX_K/32]
+  int32_t* amb_n = reinterpret_cast<int32_t*>(amb_msk + 2 * BM * (MAX_K / 32));        // [2]
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int num_tiles = (p.R + BM - 1) / BM;
+  const int num_tiles = (p.R + p.tile_rows - 1) / p.tile_rows;
   const int num_k = (p.D + 31) / 32;
 
   if (warp == 0 && lane == 0) {
@@ -72,7 +129,11 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 5); }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), 4); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), 4);
+      mbar_init(smem_u32(list_full + s), 4); mbar_init(smem_u32(list_free + s), 1);
+      amb_n[s] = 0;
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -97,11 +158,10 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       // Stages are (re)filled in bursts of `burst` consecutive k-blocks: the TMA requests of one burst hit
       // burst * 128 contiguous bytes of every row back to back, which the DRAM controller can serve from one open
       // page (a lone 128-byte access per row every few hundred ns re-opens the page each time).
-      const uint32_t tx_bytes = (uint32_t)(A_BYTES + p.n_mma * 128);
-      const uint64_t pol_x = l2_policy_keep(p.l2_keep), pol_c = l2_policy_keep(1.0f);
+      const uint32_t tx_bytes = (uint32_t)(p.tile_rows * 128 + p.n_mma * 128);   // the box holds tile_rows rows
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = tile * BM;
+        const int m0 = tile * p.tile_rows;
         for (int kb0 = 0; kb0 < num_k; kb0 += p.burst) {
           const int g = min(p.burst, num_k - kb0);
           for (int j = 0; j < g; ++j) {
@@ -113,9 +173,8 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             const uint32_t fb = smem_u32(full_bar + stage);
             mbar_expect_tx(fb, tx_bytes);
             const uint32_t sbase = smem_u32(smem + stage * p.stage_bytes);
-            if (p.l2_keep > 0.f) tma_load_2d_hint(sbase, &tm_x, fb, (kb0 + j) * 32, m0, pol_x);
-            else tma_load_2d(sbase, &tm_x, fb, (kb0 + j) * 32, m0);
-            tma_load_2d_hint(sbase + A_BYTES, &tm_c, fb, (kb0 + j) * 32, 0, pol_c);
+            tma_load_2d(sbase, &tm_x, fb, (kb0 + j) * 32, m0);
+            tma_load_2d(sbase + A_BYTES, &tm_c, fb, (kb0 + j) * 32, 0);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -151,7 +210,7 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ---------------------------------------- row norms from the staged tiles + tile epilogue; thread = row
     const int q = warp & 3;                          // TMEM lane quarter == row quarter of the tile
     const int rt = q * 32 + lane;
@@ -160,7 +219,8 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     for (int k = 0; k < p.K; ++k) { cmax = fmaxf(cmax, s_cnorm[k]); dcmax = fmaxf(dcmax, s_cdnorm[k]); }
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
       // |x|^2 and |x - tf32_trunc(x)|^2 (what the tensor core drops), two partial sums each: the FMA chains of a stage
       // are half as deep, and the tile is read with ld.shared (the generic-address form costs an address translation)
       float ss0 = 0.f, ss1 = 0.f, dd0 = 0.f, dd1 = 0.f;
@@ -238,22 +298,57 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 
-      const int64_t m = (int64_t)tile * BM + rt;
-      if (m < p.R) {
+      // rows [tile_rows, BM) of the shared-memory tile are never written by TMA: their scores are garbage and ignored
+      const int64_t m = (int64_t)tile * p.tile_rows + rt;
+      bool amb = false;
+      if (rt < p.tile_rows && m < p.R) {
         bool valid = true;
         if (p.n_valid) { const int b = (int)(m / p.n_per_img), n = (int)(m - (int64_t)b * p.n_per_img); valid = n < p.n_valid[b]; }
         if (p.inv_norm) p.inv_norm[m] = 1.0f / fmaxf(xn, 1e-12f);
         if (!valid) p.labels[m] = -1;
         else if (cnt <= 1) p.labels[m] = first;          // cnt == 0 only with NaN scores: label 0 like the exact path
-        else {
-          const int idx = atomicAdd(p.amb_count, 1);
-          if (idx >= 0 && idx < p.R) {                 // (a stale counter must never turn into a stray write)
-            p.amb_rows[idx] = (int32_t)m;
-#pragma unroll
-            for (int i = 0; i < MAX_K / 32; ++i) p.amb_mask[(size_t)idx * (MAX_K / 32) + i] = mask[i];
-          }
-        }
+        else amb = true;
       }
+      // ambiguous rows -> this tile's shared-memory list (double buffered); the re-scoring warps take it from there
+      const int buf = ti & 1;
+      mbar_wait(smem_u32(list_free + buf), (uint32_t)(((ti >> 1) & 1) ^ 1));     // list `buf` consumed (tile ti - 2)
+      if (amb) {
+        const int idx = atomicAdd(&amb_n[buf], 1);                             // < BM by construction
+        amb_row[buf * BM + idx] = (int32_t)m;
+#pragma unroll
+        for (int i = 0; i < MAX_K / 32; ++i) amb_msk[(buf * BM + idx) * (MAX_K / 32) + i] = mask[i];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(list_full + buf));
+    }
+  } else if (warp >= 8) {
+    // ---------------------------------------- exact fp32 re-scoring of the tile's ambiguous rows (warp per row): the
+    // row was streamed through this SM microseconds ago, so it is re-read from L2; same arithmetic (and therefore the
+    // same labels) as the former vlad_rescore_amb_kernel: candidates in ascending k, strict >: lowest index wins
+    // exact ties, all-zero rows get label 0.
+    const int rw = warp - 8;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      if (tile + (int)gridDim.x >= num_tiles) break;      // the CTA's LAST list is re-scored by all 16 warps below
+      const int buf = ti & 1;
+      mbar_wait(smem_u32(list_full + buf), (uint32_t)((ti >> 1) & 1));
+      const int n = amb_n[buf];
+      for (int i = rw; i < n; i += R_WARPS)
+        rescore_row(p, s_cbias, amb_row[buf * BM + i], amb_msk + (buf * BM + i) * (MAX_K / 32), lane);
+      asm volatile("bar.sync 2, %0;" ::"n"(R_WARPS * 32) : "memory");       // every re-scoring warp is done with list `buf`
+      if (rw == 0 && lane == 0) { amb_n[buf] = 0; mbar_arrive(smem_u32(list_free + buf)); }
+    }
+  }
+  // ---- the CTA's last tile: nothing is left to overlap with, so ALL 16 warps re-score its list (at c2 every CTA has a
+  // single tile: 13-14 ambiguous rows per tile, one round instead of two behind eight warps)
+  {
+    const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    if (my_tiles > 0) {
+      const int tl = my_tiles - 1, buf = tl & 1;
+      mbar_wait(smem_u32(list_full + buf), (uint32_t)((tl >> 1) & 1));
+      const int n = amb_n[buf];
+      for (int i = warp; i < n; i += THREADS / 32)
+        rescore_row(p, s_cbias, amb_row[buf * BM + i], amb_msk + (buf * BM + i) * (MAX_K / 32), lane);
     }
   }
   tc_fence_before();
@@ -261,64 +356,6 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
-  }
-}
-
-// Warp per ambiguous row; the row (D <= 128 * MAXV) lives in registers.
-template <int MAXV>
-__global__ void __launch_bounds__(256)
-vlad_rescore_amb_kernel(const float* __restrict__ x, int D, const float* __restrict__ chat,
-                        const float* __restrict__ cbias, const int32_t* amb_count, const int32_t* amb_rows,
-                        const uint32_t* amb_mask, int32_t* __restrict__ labels, int R) {
-  const int lane = threadIdx.x & 31;
-  const int gw = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int nw = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
-  const int n = min(__ldcg(amb_count), R);
-  const int D4 = D >> 2;
-  for (int i = gw; i < n; i += nw) {
-    const int64_t row = __ldcg(amb_rows + i);
-    if (lane == 0 && i + nw < n) {        // the warp's next row -> L2 while this one is being re-scored
-      const int64_t nrow = __ldcg(amb_rows + i + nw);
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + nrow * (int64_t)D), "r"((uint32_t)D * 4u) : "memory");
-    }
-    const float4* xr = reinterpret_cast<const float4*>(x + row * (int64_t)D);
-    float4 v[MAXV];
-#pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
-      const int d = lane + j * 32;
-      v[j] = d < D4 ? __ldg(xr + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    float best = -INFINITY; int bestk = 0;
-    for (int w = 0; w < MAX_K / 32; ++w) {
-      uint32_t mask = __ldcg(amb_mask + (size_t)i * (MAX_K / 32) + w);
-      const int k0 = w * 32;
-      while (mask) {
-        int kk[4]; int nc = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (mask) { kk[q] = k0 + __ffs(mask) - 1; mask &= mask - 1; ++nc; } else kk[q] = kk[0];
-        }
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < MAXV; ++j) {
-          const int d = lane + j * 32;
-          if (d < D4) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 c = __ldg(reinterpret_cast<const float4*>(chat + (size_t)kk[q] * D) + d);
-              acc[q] = fmaf(v[j].x, c.x, acc[q]); acc[q] = fmaf(v[j].y, c.y, acc[q]);
-              acc[q] = fmaf(v[j].z, c.z, acc[q]); acc[q] = fmaf(v[j].w, c.w, acc[q]);
-            }
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float sc = warp_sum(acc[q]) + cbias[kk[q]];
-          if (q < nc && sc > best) { best = sc; bestk = kk[q]; }   // ascending k, strict >: lowest index wins exact ties
-        }
-      }
-    }
-    if (lane == 0) labels[row] = bestk;
   }
 }
 
@@ -345,12 +382,24 @@ int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_
   CUtensorMap mx, mc;
   int rc;
   const int n_mma = (K + 15) / 16 * 16;
-  if ((rc = tc::make_map(&mx, feats, (int)R, D, D, BM, false))) return rc;
+  // Rows per tile: the largest multiple of 8 <= 128 that minimises (waves of the persistent grid) x (rows per tile), so
+  // that the tiles fill whole waves (c2: 16 928 rows -> 146 tiles of 116 rows on 148 SMs instead of 133 of 128).
+  const int sms = device_sm_count();
+  int tile_rows = BM;
+  {
+    long long best = -1;
+    for (int tr = BM; tr >= 64; tr -= 8) {
+      const long long tiles_tr = (R + tr - 1) / tr, waves = (tiles_tr + sms - 1) / sms, cost = waves * tr;
+      if (best < 0 || cost < best) { best = cost; tile_rows = tr; }
+    }
+  }
+  if ((rc = tc::make_map(&mx, feats, (int)R, D, D, tile_rows, false))) return rc;
   if ((rc = tc::make_map(&mc, chat_tf32, K, D, D, n_mma, false))) return rc;
   AssignParams p;
   p.n_valid = n_valid; p.n_per_img = n_per_img; p.R = (int)R; p.D = D; p.K = K;
   p.cbias = cbias; p.cnorm = cnorm; p.cdnorm = cdnorm; p.labels = labels; p.inv_norm = inv_norm;
   p.amb_count = amb_count; p.amb_rows = amb_rows; p.amb_mask = amb_mask;
+  p.x = feats; p.chat = chat; p.tile_rows = tile_rows;
   p.zero_ptr = zero_ptr; p.zero_n = zero_ptr ? zero_n : 0;
   p.n_mma = n_mma;
   p.stage_bytes = A_BYTES + n_mma * 128;
@@ -360,7 +409,7 @@ int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_
   static unsigned long long attr_seen = 0;
   if (first_use_on_this_device(&attr_seen))
     ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(vlad_assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  const int fixed = 1024 + BAR_BYTES + VEC_BYTES;
+  const int fixed = 1024 + BAR_BYTES + VEC_BYTES + LIST_BYTES;
   p.stages = std::min(MAX_STAGES, (max_smem - fixed) / p.stage_bytes);
   const int num_k = (D + 31) / 32;
   p.stages = std::max(2, std::min(p.stages, std::max(2, num_k)));
@@ -372,24 +421,10 @@ int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_
   if (stages_env >= 2) p.stages = std::min(p.stages, stages_env);
   p.diag = diag_env;
   p.burst = std::max(1, std::min(burst_env, p.stages / 2));
-  // L2 residency for the second pass (accumulate): keep what fits in ~60 % of the 126 MB L2.  ANYLOC_VLAD_L2KEEP_MB
-  // overrides the budget (0 disables the hints).
-  static int keep_mb = -1;
-  if (keep_mb < 0) { const char* e = getenv("ANYLOC_VLAD_L2KEEP_MB"); keep_mb = e ? atoi(e) : 76; }
-  const double feat_mb = (double)R * D * 4.0 / 1e6;
-  p.l2_keep = keep_mb > 0 ? (float)std::min(1.0, keep_mb / feat_mb) : 0.f;
   const size_t smem = (size_t)p.stages * p.stage_bytes + fixed;
-  const int tiles = (int)((R + BM - 1) / BM);
+  const int tiles = (int)((R + tile_rows - 1) / tile_rows);
   const int grid = std::min(tiles, device_sm_count());
   vlad_assign_tc_kernel<<<grid, THREADS, smem, st>>>(mx, mc, p);
-  ANYLOC_CHECK_LAUNCH();
-  const int blocks = (int)std::min<int64_t>((R + 7) / 8, (int64_t)device_sm_count() * 4);
-  if (D <= 512)
-    vlad_rescore_amb_kernel<4><<<blocks, 256, 0, st>>>(feats, D, chat, cbias, amb_count, amb_rows, amb_mask, labels, (int)R);
-  else if (D <= 1024)
-    vlad_rescore_amb_kernel<8><<<blocks, 256, 0, st>>>(feats, D, chat, cbias, amb_count, amb_rows, amb_mask, labels, (int)R);
-  else
-    vlad_rescore_amb_kernel<16><<<blocks, 256, 0, st>>>(feats, D, chat, cbias, amb_count, amb_rows, amb_mask, labels, (int)R);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }

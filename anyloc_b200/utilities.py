@@ -415,7 +415,7 @@ class _KMeans:
         new_c = torch.empty_like(c)
         err = torch.zeros(1, device=x.device)
         with torch.cuda.device(x.device):
-            ws = _lib.workspaces.get(x.device, lib.anyloc_vlad_workspace_bytes(1, 1, D, K), "kmeans_upd")
+            ws = _lib.workspaces.get(x.device, lib.anyloc_kmeans_workspace_bytes(n, D, K), "kmeans_upd")
             _lib.check(lib.anyloc_kmeans_update(_lib.ptr(x), _lib.ptr(labels), _lib.ptr(c), n, D, K,
                                                 _lib.ptr(new_c), _lib.ptr(err), _lib.ptr(ws), ws.numel(),
                                                 _lib.stream_ptr()), "anyloc_kmeans_update")

@@ -129,7 +129,9 @@ int anyloc_vlad_from_residuals(const float* resid, const int32_t* labels, const 
 int anyloc_vlad_assign(const float* feats, const float* centers, int R, int D, int K, int dist_mode,
                        int32_t* labels, void* ws, size_t ws_bytes, void* stream);
 /* one Lloyd centroid update of fpk.KMeans.fit (utilities.py:786): new_c[k] = mean of members
- * (0 for empty clusters); err_out[0] = sum((new_c - old_c)^2).  sums_ws: K*D+K floats. */
+ * (0 for empty clusters); err_out[0] = sum((new_c - old_c)^2).  Deterministic (per-chunk partial sums added in a
+ * fixed order, no floating-point atomics).  Workspace: anyloc_kmeans_workspace_bytes(R, D, K). */
+size_t anyloc_kmeans_workspace_bytes(int R, int D, int K);
 int anyloc_kmeans_update(const float* x, const int32_t* labels, const float* old_centers, int R, int D,
                          int K, float* new_centers, float* err_out, void* ws, size_t ws_bytes,
                          void* stream);

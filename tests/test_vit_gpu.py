@@ -174,6 +174,11 @@ def test_outlier_activations_precision_contract(u):
     wild = _outlier_weights(name, depth, 3000.0)
     ref = ao.extract_features(wild, img, layer, "value")
     assert bool(torch.isfinite(ref).all())
+    # with activations of 1e4 next to O(1) ones fp32 itself is no longer 1e-4-accurate: measure both fp32 evaluations
+    # (the oracle's and the kernels') against the same model in fp64 and allow this one 3x the oracle's own error
+    ref64 = ao.extract_features(wild.double(), img.double(), layer, "value")
+    wild = wild.float()
+    tol = max(TOL, 3.0 * rel_inf(ref, ref64))
     ext = u.DinoV2ExtractFeatures(name, layer, "value", device="cuda", weights=wild.state_dict(), precision="f16x3")
     with pytest.raises(_lib.AnylocError, match="overflowed the fp16 operand range"):
         ext(img.cuda())
@@ -182,9 +187,11 @@ def test_outlier_activations_precision_contract(u):
     with pytest.raises(_lib.AnylocError):
         ext.raise_if_overflowed()
     ext = u.DinoV2ExtractFeatures(name, layer, "value", device="cuda", weights=wild.state_dict(), precision="tf32x3")
-    assert rel_inf(ext(img.cuda()).cpu(), ref) < TOL
+    err = rel_inf(ext(img.cuda()).cpu(), ref64)
+    print(f"outliers x3000: oracle fp32 vs fp64 {rel_inf(ref, ref64):.2e}, tf32x3 vs fp64 {err:.2e}")
+    assert err < tol, (err, tol)
     ext = u.DinoV2ExtractFeatures(name, layer, "value", device="cuda", weights=wild.state_dict())     # default: auto
     assert ext.precision == "f16x3"
     out = ext(img.cuda())
-    assert ext.precision == "tf32x3" and rel_inf(out.cpu(), ref) < TOL
-    assert rel_inf(ext(img.cuda()).cpu(), ref) < TOL
+    assert ext.precision == "tf32x3" and rel_inf(out.cpu(), ref64) < tol
+    assert rel_inf(ext(img.cuda()).cpu(), ref64) < tol
