@@ -148,6 +148,25 @@ extern "C" int anyloc_gemm_nt(const void* a_hi, const void* a_lo, int lda, const
                        (cudaStream_t)stream);
 }
 
+// internal (topk.cu): plain-store GEMM with a device gate; not part of the public header
+extern "C" int anyloc_gemm_nt_gated(const void* a_hi, const void* a_lo, int lda, const void* b_hi, const void* b_lo, int ldb,
+                                    int M, int N, int K, int in_dtype, float alpha, float* out, int ldo, const int* gate,
+                                    void* stream) {
+  EpiParams ep{ANYLOC_EPI_BIAS, nullptr, nullptr, nullptr, out, nullptr, ldo};
+  ep.alpha = alpha;
+  ep.gate = gate;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool f16 = in_dtype == ANYLOC_PAIR_F16;
+  if (gate) {      // conditional fallback: tcgen05 engine only (the gate lives in its kernels), nothing recorded
+    if (!gemm_tc_supported(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, f16)) {
+      set_error("gemm_nt_gated: shape outside the tcgen05 engine's contract");
+      return ANYLOC_ERR_UNSUPPORTED;
+    }
+    return gemm_tc_launch(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, f16, st);
+  }
+  return gemm_dispatch(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, ANYLOC_GEMM_AUTO, f16, st);
+}
+
 extern "C" int anyloc_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream) {
   ANYLOC_REQUIRE(x && hi && lo, "split_tf32: null pointer");
   if (n == 0) return ANYLOC_OK;

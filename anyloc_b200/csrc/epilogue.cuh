@@ -20,6 +20,7 @@ struct EpiParams {
   int qkv_f16 = 0;      // QKV_SPLIT: q,k and V^T as fp16 pairs of kActScale*x (out/out_lo/vt_* point to __half)
   float alpha = 1.0f;   // accumulator scale (1/(s_A*s_B) for fp16-pair inputs, else 1)
   int out_f16 = 0;      // SPLIT outputs as fp16 pairs of kActScale*v (out/out_lo then point to __half)
+  const int* gate = nullptr;   // device flag (nullable): tcgen05 kernels return immediately when *gate == 0 (conditional fallbacks without a host sync)
 };
 
 __device__ __forceinline__ void epi_store_split(const EpiParams& p, size_t o, float v) {

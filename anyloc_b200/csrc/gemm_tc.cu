@@ -272,6 +272,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                 int M, int N, int K, int has_a_lo, int has_b_lo, int band_n, EpiParams ep) {
   using C = Cfg<BN, LO>;
+  if (ep.gate != nullptr && *reinterpret_cast<const volatile int*>(ep.gate) == 0) return;   // uniform over the grid
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* bar_area = smem + C::STAGES * C::STAGE_BYTES;
@@ -430,9 +431,12 @@ namespace two {
 constexpr int BH_BYTES = 128 * 128;                       // half of the B tile: 128 rows x 128 B
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;    // A_hi, A_lo, Bh_hi, Bh_lo = 64 KB
 constexpr int STAGES = 3;
+constexpr int HI_STAGE_BYTES = A_BYTES + BH_BYTES;         // hi-only pass: A_hi, Bh_hi = 32 KB
+constexpr int HI_STAGES = 5;
 constexpr int EPI_TILE_BYTES = 16 * 64;                    // per epilogue warp: 16 rows x 16 fp32 (coalescing transpose)
 constexpr int EPI_VEC_BYTES = 2 * 2 * 256 * 4;              // bias + gamma slices of the tile's 256 columns, double buffered
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_VEC_BYTES + EPI_WARPS * EPI_TILE_BYTES;
+static_assert(HI_STAGES * HI_STAGE_BYTES <= STAGES * STAGE_BYTES, "the hi-only ring must fit the same allocation");
 constexpr int BN = 256;
 }  // namespace two
 
@@ -474,12 +478,21 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {       // arrives
       ::"r"(bar) : "memory");
 }
 
-template <bool F16, int MODE>
+// LO = false: hi-only single pass (A_hi . B_hi^T, one MMA per product instead of three) -- the COARSE scores of the
+// retrieval (topk.cu bounds their error rigorously and re-scores the candidates exactly).  Stages then hold
+// {A_hi, Bh_hi} = 32 KB and the ring is HI_STAGES deep.  ep.gate (nullable): the kernel returns at once when *gate == 0.
+template <bool F16, int MODE, bool LO = true>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                      const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                     int M, int N, int K, int band_n, int staged_epi, EpiParams ep) {
+                     int M, int N, int K, int band_n, int staged_epi, int chunk_kb, EpiParams ep) {
   using namespace two;
+  if (ep.gate != nullptr && *reinterpret_cast<const volatile int*>(ep.gate) == 0) return;   // uniform over the grid
+  constexpr int STAGES = LO ? two::STAGES : two::HI_STAGES;
+  constexpr int STAGE_BYTES = LO ? two::STAGE_BYTES : two::HI_STAGE_BYTES;
+  constexpr int A_LO_OFF = A_BYTES;                                      // LO only
+  constexpr int B_HI_OFF = LO ? 2 * A_BYTES : A_BYTES;
+  constexpr int B_LO_OFF = 2 * A_BYTES + BH_BYTES;                       // LO only
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* bar_area = smem + STAGES * STAGE_BYTES;
@@ -496,7 +509,7 @@ gemm_tc3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   const int num_m = (M + 255) / 256, num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   constexpr int BKE = F16 ? 64 : 32;
-  constexpr int CHUNK_KB = F16 ? CHUNK_KB_F16 : CHUNK_KB_TF32;
+  const int CHUNK_KB = chunk_kb;             // k-blocks accumulated in TMEM between two round-to-nearest drains
   const int num_k = (K + BKE - 1) / BKE;
   const int num_chunks = (num_k + CHUNK_KB - 1) / CHUNK_KB;
 
@@ -537,9 +550,9 @@ gemm_tc3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
           const uint32_t fb = mapa_rank0(fb_local);
           const uint32_t sbase = smem_u32(smem + stage * STAGE_BYTES);
           tma_load_2d_2sm(sbase, &tm_a_hi, fb, kb * BKE, m0);
-          tma_load_2d_2sm(sbase + A_BYTES, &tm_a_lo, fb, kb * BKE, m0);
-          tma_load_2d_2sm(sbase + 2 * A_BYTES, &tm_b_hi, fb, kb * BKE, n0);
-          tma_load_2d_2sm(sbase + 2 * A_BYTES + BH_BYTES, &tm_b_lo, fb, kb * BKE, n0);
+          if (LO) tma_load_2d_2sm(sbase + A_LO_OFF, &tm_a_lo, fb, kb * BKE, m0);
+          tma_load_2d_2sm(sbase + B_HI_OFF, &tm_b_hi, fb, kb * BKE, n0);
+          if (LO) tma_load_2d_2sm(sbase + B_LO_OFF, &tm_b_lo, fb, kb * BKE, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -561,14 +574,14 @@ gemm_tc3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
           mbar_wait(smem_u32(full_bar + stage), phase);
           tc_fence_after();
           const uint32_t sbase = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t a_hi = make_desc(sbase), a_lo = make_desc(sbase + A_BYTES);
-          const uint64_t b_hi = make_desc(sbase + 2 * A_BYTES), b_lo = make_desc(sbase + 2 * A_BYTES + BH_BYTES);
+          const uint64_t a_hi = make_desc(sbase), a_lo = make_desc(sbase + A_LO_OFF);
+          const uint64_t b_hi = make_desc(sbase + B_HI_OFF), b_lo = make_desc(sbase + B_LO_OFF);
 #pragma unroll
           for (int k = 0; k < KSTEPS; ++k) {
             const uint64_t adv = (uint64_t)((k * 32) >> 4);
             umma2<F16>(d_tmem, a_hi + adv, b_hi + adv, idesc, (in_chunk | k) != 0);
-            umma2<F16>(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-            umma2<F16>(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+            if (LO) umma2<F16>(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+            if (LO) umma2<F16>(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
           }
           umma_commit_2sm(smem_u32(empty_bar + stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -717,6 +730,10 @@ static int launch_2cta(const void* a_hi, const void* a_lo, int lda, const void* 
   static int staged_epi = -1;          // ANYLOC_GEMM_STAGED_EPI=0: direct (lane = row) stores, for A/B measurements
   if (staged_epi < 0) { const char* e = getenv("ANYLOC_GEMM_STAGED_EPI"); staged_epi = e ? atoi(e) : 1; }
   const int bn = std::min(band_n, cdiv(N, two::BN));
+  // ANYLOC_GEMM_CHUNK: k-blocks per TMEM chunk (A/B knob; default 4 fp16 / 2 tf32 k-blocks = 48 / 24 MMAs per drain)
+  static int chunk_env = -1;
+  if (chunk_env < 0) { const char* e = getenv("ANYLOC_GEMM_CHUNK"); chunk_env = e ? atoi(e) : 0; }
+  const int chunk = chunk_env > 0 ? chunk_env : (F16 ? CHUNK_KB_F16 : CHUNK_KB_TF32);
   // one instantiation per epilogue mode (compact per-tile code); -1 = the diagnostic "discard" variant
 #define ANYLOC_LAUNCH_2CTA(MODE_)                                                                                   \
   case MODE_: {                                                                                                     \
@@ -726,7 +743,7 @@ static int launch_2cta(const void* a_hi, const void* a_lo, int lda, const void* 
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, two::SMEM_BYTES));        \
     }                                                                                                               \
     gemm_tc3_2cta_kernel<F16, MODE_><<<2 * pairs, THREADS, two::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, \
-                                                                                  K, bn, staged_epi, ep);          \
+                                                                                  K, bn, staged_epi, chunk, ep);   \
   } break;
   switch (ep.mode) {
     ANYLOC_LAUNCH_2CTA(-1)
@@ -739,6 +756,27 @@ static int launch_2cta(const void* a_hi, const void* a_lo, int lda, const void* 
     default: set_error("gemm_tc: unknown epilogue mode %d", ep.mode); return ANYLOC_ERR_ARG;
   }
 #undef ANYLOC_LAUNCH_2CTA
+  ANYLOC_CHECK_LAUNCH();
+  return ANYLOC_OK;
+}
+
+// hi-only 2-CTA pass (fp16 operands, plain store epilogue): coarse retrieval scores
+static int launch_2cta_hi(const void* a_hi, int lda, const void* b_hi, int ldb, int M, int N, int K, const EpiParams& ep,
+                          int band_n, cudaStream_t st) {
+  using namespace tc;
+  CUtensorMap ma, mb;
+  int rc;
+  if ((rc = make_map(&ma, a_hi, M, K, lda, 128, true))) return rc;
+  if ((rc = make_map(&mb, b_hi, N, K, ldb, 128, true))) return rc;
+  const int tiles = cdiv(M, 256) * cdiv(N, two::BN);
+  const int pairs = std::min(tiles, device_sm_count() / 2);
+  static unsigned long long attr_seen = 0;
+  if (first_use_on_this_device(&attr_seen))
+    ANYLOC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_2cta_kernel<true, ANYLOC_EPI_BIAS, false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, two::SMEM_BYTES));
+  // 32 k-blocks (128 MMAs) per TMEM chunk: the coarse pass does not need the tight round-to-nearest accumulation
+  gemm_tc3_2cta_kernel<true, ANYLOC_EPI_BIAS, false><<<2 * pairs, THREADS, two::SMEM_BYTES, st>>>(
+      ma, ma, mb, mb, M, N, K, std::min(band_n, cdiv(N, two::BN)), 1, 32, ep);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }
@@ -790,6 +828,8 @@ int gemm_tc_launch(const void* a_hi, const void* a_lo, int lda, const void* b_hi
     return f16 ? launch_2cta<true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, band_n, st)
                : launch_2cta<false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, band_n, st);
   }
+  if (two_cta && f16 && !lo && M >= 512 && N >= 256 && ep.mode == ANYLOC_EPI_BIAS)
+    return launch_2cta_hi(a_hi, lda, b_hi, ldb, M, N, K, ep, band_n, st);
   if (f16) return lo ? launch_impl<true, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st)
                      : launch_impl<true, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st);
   return lo ? launch_impl<false, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, ep, st)

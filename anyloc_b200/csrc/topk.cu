@@ -4,6 +4,12 @@
 #include <stdlib.h>
 #include "common.cuh"
 
+// internal (api.cu): the plain-store 3-term GEMM with an optional device gate (*gate == 0 -> the kernels return at once);
+// when gated, no algorithmic work is recorded (the coarse pass already accounted for the product)
+extern "C" int anyloc_gemm_nt_gated(const void* a_hi, const void* a_lo, int lda, const void* b_hi, const void* b_lo, int ldb,
+                                    int M, int N, int K, int in_dtype, float alpha, float* out, int ldo, const int* gate,
+                                    void* stream);
+
 namespace anyloc {
 
 // fp16-pair scale of unit-norm rows: |s y| <= 4096 < 65504, and s*y - hi stays far above the fp16 subnormal step for
@@ -15,7 +21,8 @@ constexpr float kRetrievalScale = 4096.0f;
 template <bool F16>
 __global__ void __launch_bounds__(256)
 normalize_rows_split_kernel(const float* __restrict__ x, int D, int do_norm, void* __restrict__ hi_v,
-                            void* __restrict__ lo_v, float* __restrict__ sq) {
+                            void* __restrict__ lo_v, float* __restrict__ sq, float* __restrict__ dn /* nullable, F16 only */,
+                            int* __restrict__ dn_max_bits /* nullable */) {
   const size_t row = blockIdx.x;
   const float4* xr = reinterpret_cast<const float4*>(x + row * D);
   const int D4 = D >> 2;
@@ -36,16 +43,20 @@ normalize_rows_split_kernel(const float* __restrict__ x, int D, int do_norm, voi
   float4* l4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(lo_v) + row * D);
   uint2* h2 = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(hi_v) + row * D);   // 4 halves = 8 bytes
   uint2* l2 = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(lo_v) + row * D);
-  float ss2 = 0.f;
+  float ss2 = 0.f, dd2 = 0.f;
   for (int d = threadIdx.x; d < D4; d += blockDim.x) {
     float4 v = __ldg(xr + d);
     if (do_norm) { v.x = v.x / nrm; v.y = v.y / nrm; v.z = v.z / nrm; v.w = v.w / nrm; }
     ss2 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     if constexpr (F16) {
       uint2 h, l;
-      split_f16x2(v.x * kRetrievalScale, v.y * kRetrievalScale, h.x, l.x);
-      split_f16x2(v.z * kRetrievalScale, v.w * kRetrievalScale, h.y, l.y);
+      const float a0 = v.x * kRetrievalScale, a1 = v.y * kRetrievalScale, a2 = v.z * kRetrievalScale, a3 = v.w * kRetrievalScale;
+      split_f16x2(a0, a1, h.x, l.x);
+      split_f16x2(a2, a3, h.y, l.y);
       h2[d] = h; l2[d] = l;
+      // what a hi-only product drops of this row: s*y - hi (exact in fp32: hi is s*y rounded to 11 significant bits)
+      const float e0 = a0 - veltkamp_hi11(a0), e1 = a1 - veltkamp_hi11(a1), e2 = a2 - veltkamp_hi11(a2), e3 = a3 - veltkamp_hi11(a3);
+      dd2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
     } else {
       float4 h, l;
       split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
@@ -59,6 +70,20 @@ normalize_rows_split_kernel(const float* __restrict__ x, int D, int do_norm, voi
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss2;
     __syncthreads();
     if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += red[w]; sq[row] = t; }
+  }
+  if (F16 && dn) {
+    // |s*y - hi| / s, rounded UP (1 + 2^-10), plus the fp16 subnormal slack sqrt(D) * 2^-25 / s (elements of |s*y| < 2^-14
+    // are rounded to the 2^-24 grid) -- a rigorous bound on what the hi-only (coarse) score ignores of this row
+    dd2 = warp_sum(dd2);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dd2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f; for (int w = 0; w < 8; ++w) t += red[w];
+      const float b = (sqrtf(t) * 1.001f + sqrtf((float)D) * 2.98e-8f) / kRetrievalScale;
+      dn[row] = b;
+      if (dn_max_bits) atomicMax(dn_max_bits, __float_as_int(b));      // positive floats order like their bit patterns
+    }
   }
 }
 
@@ -102,7 +127,8 @@ __device__ __forceinline__ void block_argbest(float& best, int& besti, float* bv
 __global__ void __launch_bounds__(1024)
 topk_select2_kernel(const float* __restrict__ scores, int n_db, int64_t ld, int k, int metric,
                     const float* __restrict__ qq, const float* __restrict__ dd,
-                    float* __restrict__ dist, int64_t* __restrict__ idx) {
+                    float* __restrict__ dist, int64_t* __restrict__ idx, const int* __restrict__ gate /* nullable */) {
+  if (gate != nullptr && *reinterpret_cast<const volatile int*>(gate) == 0) return;
   const int q = blockIdx.x;
   const float* s = scores + (size_t)q * ld;
   const bool l2 = metric == ANYLOC_METRIC_L2;
@@ -184,6 +210,121 @@ topk_select2_kernel(const float* __restrict__ scores, int n_db, int64_t ld, int 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Coarse retrieval (inner product on an fp16-pair index).  One hi-only tensor-core pass gives S~ = hi_q . hi_d / s^2 with
+//   |S~ - S| <= eps_q = (dn_q + DN + dn_q DN) (1 + 2^-10) + 3e-5
+// (dn_* = |s y - hi| / s per row, measured when the pairs were written; DN = max over the database; Cauchy-Schwarz per
+// dropped term, |y| <= 1 + 1e-6; 3e-5 covers the fp32 accumulation: <= 128 truncating steps per TMEM chunk + 24
+// round-to-nearest chunk adds).  With tau = the k-th best S~ of a query, every member of its exact top-k has
+// S~ >= tau - 2 eps_q, so those candidates (usually k .. 3k of 10^4-10^5 rows) are re-scored EXACTLY from the (hi,lo)
+// pairs in fp32 and the k best of them -- score descending, lowest index first -- are the answer: identical to the
+// 3-term path up to fp32 rounding of the scores, at a third of the tensor-core work.  A query with more than CAND_MAX
+// candidates raises a device flag that switches on the 3-term fallback (launched behind it, gated, no host sync).
+constexpr int CAND_MAX = 256;
+
+__global__ void __launch_bounds__(1024)
+topk_candidates_kernel(const float* __restrict__ scores, int n_db, int64_t ld, int k, const float* __restrict__ dn_q,
+                       const int* __restrict__ dn_max_bits, int32_t* __restrict__ cand /* [n_q, CAND_MAX] */,
+                       int32_t* __restrict__ cand_n /* [n_q] */, int* __restrict__ overflow) {
+  const int q = blockIdx.x;
+  const float* s = scores + (size_t)q * ld;
+  __shared__ float bv[33];
+  __shared__ int bi[33];
+  __shared__ int ci[SEL_CAP];
+  __shared__ int count;
+  if (threadIdx.x == 0) count = 0;
+  float mine = -INFINITY; int minei = 0x7fffffff;
+  for (int j = threadIdx.x; j < n_db; j += blockDim.x) {
+    const float v = s[j];
+    if (better(v, j, mine, minei)) { mine = v; minei = j; }
+  }
+  float tau = -INFINITY;
+  {
+    float v = mine; int vi = minei;
+    for (int r = 0; r < k; ++r) {
+      float b = v; int bidx = vi;
+      block_argbest(b, bidx, bv, bi);
+      if (bidx == 0x7fffffff) { tau = -INFINITY; break; }
+      tau = b;
+      if (vi == bidx) { v = -INFINITY; vi = 0x7fffffff; }
+    }
+  }
+  const float DN = __int_as_float(*dn_max_bits), dq = dn_q[q];
+  const float eps = (dq + DN + dq * DN) * 1.001f + 3.0e-5f;
+  const float thr = tau - 2.0f * eps;
+  __syncthreads();
+  for (int j = threadIdx.x; j < n_db; j += blockDim.x) {
+    if (s[j] >= thr) {
+      const int slot = atomicAdd(&count, 1);
+      if (slot < SEL_CAP) ci[slot] = j;
+    }
+  }
+  __syncthreads();
+  const int n_c = count;
+  if (n_c > CAND_MAX) {
+    if (threadIdx.x == 0) { cand_n[q] = 0; atomicExch(overflow, 1); }
+    return;
+  }
+  for (int c = threadIdx.x; c < n_c; c += blockDim.x) cand[(size_t)q * CAND_MAX + c] = ci[c];
+  if (threadIdx.x == 0) cand_n[q] = n_c;
+}
+
+// CTA per query: exact fp32 scores of its candidates from the fp16 (hi,lo) pairs, then the k best of them.
+__device__ __forceinline__ float2 h2f(uint32_t u) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+__global__ void __launch_bounds__(256)
+topk_rescore_kernel(const __half* __restrict__ db_hi, const __half* __restrict__ db_lo, const __half* __restrict__ qu_hi,
+                    const __half* __restrict__ qu_lo, int Dv, int k, const int32_t* __restrict__ cand,
+                    const int32_t* __restrict__ cand_n, const int* __restrict__ overflow, float* __restrict__ dist,
+                    int64_t* __restrict__ idx) {
+  if (*reinterpret_cast<const volatile int*>(overflow) != 0) return;       // the 3-term fallback answers every query
+  const int q = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __shared__ float cv[CAND_MAX];
+  __shared__ int ci[CAND_MAX];
+  __shared__ float bv[33];
+  __shared__ int bi[33];
+  const int n_c = cand_n[q];
+  const uint4* qh = reinterpret_cast<const uint4*>(qu_hi + (size_t)q * Dv);
+  const uint4* ql = reinterpret_cast<const uint4*>(qu_lo + (size_t)q * Dv);
+  const int steps = Dv >> 3;                 // 8 halves (16 bytes) per lane and step
+  for (int c = w; c < n_c; c += 8) {
+    const int j = cand[(size_t)q * CAND_MAX + c];
+    const uint4* dh = reinterpret_cast<const uint4*>(db_hi + (size_t)j * Dv);
+    const uint4* dl = reinterpret_cast<const uint4*>(db_lo + (size_t)j * Dv);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int t = lane; t < steps; t += 32) {
+      const uint4 xh = __ldg(qh + t), xl = __ldg(ql + t), yh = __ldg(dh + t), yl = __ldg(dl + t);
+      const uint32_t xhw[4] = {xh.x, xh.y, xh.z, xh.w}, xlw[4] = {xl.x, xl.y, xl.z, xl.w};
+      const uint32_t yhw[4] = {yh.x, yh.y, yh.z, yh.w}, ylw[4] = {yl.x, yl.y, yl.z, yl.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = h2f(xhw[e]), b = h2f(xlw[e]), c2 = h2f(yhw[e]), d2 = h2f(ylw[e]);
+        const float x0 = a.x + b.x, x1 = a.y + b.y, y0 = c2.x + d2.x, y1 = c2.y + d2.y;     // exact: 22 significant bits
+        if (e & 1) { a2 = fmaf(x0, y0, a2); a3 = fmaf(x1, y1, a3); }
+        else       { a0 = fmaf(x0, y0, a0); a1 = fmaf(x1, y1, a1); }
+      }
+    }
+    const float tot = warp_sum((a0 + a1) + (a2 + a3));
+    if (lane == 0) { cv[c] = tot * (1.0f / (kRetrievalScale * kRetrievalScale)); ci[c] = j; }
+  }
+  __syncthreads();
+  for (int r = 0; r < k; ++r) {
+    float b = -INFINITY; int bidx = 0x7fffffff; int bslot = -1;
+    for (int c = threadIdx.x; c < n_c; c += blockDim.x)
+      if (better(cv[c], ci[c], b, bidx)) { b = cv[c]; bidx = ci[c]; bslot = c; }
+    float wb = b; int wi = bidx;
+    block_argbest(wb, wi, bv, bi);
+    if (bslot >= 0 && wi == bidx && wi != 0x7fffffff) { cv[bslot] = -INFINITY; ci[bslot] = 0x7fffffff; }
+    if (threadIdx.x == 0) {
+      dist[(size_t)q * k + r] = wi != 0x7fffffff ? wb : -INFINITY;
+      idx[(size_t)q * k + r] = wi != 0x7fffffff ? wi : -1;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace anyloc
 
 using namespace anyloc;
@@ -191,7 +332,8 @@ using namespace anyloc;
 
 // ---- prepared database ("index"): what faiss' index.add(db) leaves behind (utilities.py:449).
 // Layout of the caller-owned blob for `capacity` rows of Dv columns:
-//   hi [capacity, Dv] | lo [capacity, Dv] | sq [capacity] fp32 (|y|^2 per row, the L2 metric needs it)
+//   hi [capacity, Dv] | lo [capacity, Dv] | sq [capacity] fp32 (|y|^2 per row, the L2 metric needs it) |
+//   dn [capacity] fp32 (|s y - hi| / s per row: what a hi-only product ignores; fp16 layout only) | header (256 B: max dn)
 // with hi/lo either fp16 pairs of 4096*y (unit rows: normalize != 0, Dv % 8 == 0 -- the 2x faster kind::f16 tensor
 // path) or tf32 pairs of y (rows of unknown range).  ANYLOC_TOPK_F16=0 forces the tf32 pairs (A/B).
 static bool index_uses_f16(int Dv, int normalize) {
@@ -199,20 +341,32 @@ static bool index_uses_f16(int Dv, int normalize) {
   if (f16_env < 0) { const char* e = getenv("ANYLOC_TOPK_F16"); f16_env = e ? atoi(e) : 1; }
   return f16_env && normalize && (Dv % 8) == 0;
 }
-struct IndexView { void* hi; void* lo; float* sq; bool f16; };
+struct IndexView { void* hi; void* lo; float* sq; float* dn; int* hdr; bool f16; size_t pair_bytes_per_row; };
 static bool carve_index(void* blob, size_t bytes, int64_t capacity, int Dv, int normalize, IndexView* v) {
   v->f16 = index_uses_f16(Dv, normalize);
   const size_t esz = v->f16 ? 2 : 4;
+  v->pair_bytes_per_row = (size_t)Dv * esz;
   Workspace w(blob, bytes);
   v->hi = w.take<char>((size_t)capacity * Dv * esz);
   v->lo = w.take<char>((size_t)capacity * Dv * esz);
   v->sq = w.take<float>((size_t)capacity);
-  return v->hi && v->lo && v->sq;
+  v->dn = w.take<float>((size_t)capacity);
+  v->hdr = w.take<int>(64);
+  return v->hi && v->lo && v->sq && v->dn && v->hdr;
 }
 
 extern "C" size_t anyloc_index_bytes(int64_t capacity, int Dv, int normalize) {
   const size_t esz = index_uses_f16(Dv, normalize) ? 2 : 4;
-  return 2 * align_up((size_t)capacity * Dv * esz, 256) + align_up((size_t)capacity * 4, 256) + 256;
+  return 2 * align_up((size_t)capacity * Dv * esz, 256) + 2 * align_up((size_t)capacity * 4, 256) + 256 + 256;
+}
+
+// A fresh blob must be initialised once (clears the header) before the first anyloc_index_add.
+extern "C" int anyloc_index_init(void* index, size_t index_bytes, int64_t capacity, int Dv, int normalize, void* stream) {
+  ANYLOC_REQUIRE(index, "index_init: null pointer");
+  IndexView v;
+  if (!carve_index(index, index_bytes, capacity, Dv, normalize, &v)) { set_error("index_init: blob too small"); return ANYLOC_ERR_WORKSPACE; }
+  ANYLOC_CHECK_CUDA(cudaMemsetAsync(v.hdr, 0, 256, (cudaStream_t)stream));
+  return ANYLOC_OK;
 }
 
 extern "C" int anyloc_index_add(void* index, size_t index_bytes, int64_t capacity, int64_t row_offset, const float* rows,
@@ -232,19 +386,40 @@ extern "C" int anyloc_index_add(void* index, size_t index_bytes, int64_t capacit
   const size_t off = (size_t)row_offset * Dv;
   if (v.f16)
     normalize_rows_split_kernel<true><<<n_rows, 256, 0, st>>>(rows, Dv, normalize, (__half*)v.hi + off, (__half*)v.lo + off,
-                                                              v.sq + row_offset);
+                                                              v.sq + row_offset, v.dn + row_offset, v.hdr);
   else
     normalize_rows_split_kernel<false><<<n_rows, 256, 0, st>>>(rows, Dv, normalize, (float*)v.hi + off, (float*)v.lo + off,
-                                                               v.sq + row_offset);
+                                                               v.sq + row_offset, nullptr, nullptr);
   ANYLOC_CHECK_LAUNCH();
   return ANYLOC_OK;
 }
 
-// workspace of one search: query pairs + |q|^2 + the [n_q, n_db] score matrix
+// Growth: the first n_rows rows of every section (and the header) of `src` -> `dst` (a larger blob of the same Dv / normalize).
+extern "C" int anyloc_index_copy(void* dst, size_t dst_bytes, int64_t dst_capacity, const void* src, size_t src_bytes,
+                                 int64_t src_capacity, int64_t n_rows, int Dv, int normalize, void* stream) {
+  ANYLOC_REQUIRE(dst && src && n_rows >= 0 && n_rows <= src_capacity && n_rows <= dst_capacity, "index_copy: bad arguments");
+  IndexView d, s;
+  if (!carve_index(dst, dst_bytes, dst_capacity, Dv, normalize, &d) ||
+      !carve_index(const_cast<void*>(src), src_bytes, src_capacity, Dv, normalize, &s)) {
+    set_error("index_copy: blob too small");
+    return ANYLOC_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t pb = (size_t)n_rows * d.pair_bytes_per_row;
+  ANYLOC_CHECK_CUDA(cudaMemcpyAsync(d.hi, s.hi, pb, cudaMemcpyDeviceToDevice, st));
+  ANYLOC_CHECK_CUDA(cudaMemcpyAsync(d.lo, s.lo, pb, cudaMemcpyDeviceToDevice, st));
+  ANYLOC_CHECK_CUDA(cudaMemcpyAsync(d.sq, s.sq, (size_t)n_rows * 4, cudaMemcpyDeviceToDevice, st));
+  ANYLOC_CHECK_CUDA(cudaMemcpyAsync(d.dn, s.dn, (size_t)n_rows * 4, cudaMemcpyDeviceToDevice, st));
+  ANYLOC_CHECK_CUDA(cudaMemcpyAsync(d.hdr, s.hdr, 256, cudaMemcpyDeviceToDevice, st));
+  return ANYLOC_OK;
+}
+
+// workspace of one search: query pairs + |q|^2 + dn_q + the [n_q, n_db] score matrix + candidate lists + flags
 extern "C" size_t anyloc_index_search_workspace_bytes(int64_t n_db, int n_q, int Dv, int normalize) {
   const size_t esz = index_uses_f16(Dv, normalize) ? 2 : 4;
-  return 2 * align_up((size_t)n_q * Dv * esz, 256) + align_up((size_t)n_q * 4, 256) +
-         align_up((size_t)n_q * (size_t)n_db * 4, 256) + 1024;
+  return 2 * align_up((size_t)n_q * Dv * esz, 256) + 2 * align_up((size_t)n_q * 4, 256) +
+         align_up((size_t)n_q * (size_t)n_db * 4, 256) + align_up((size_t)n_q * CAND_MAX * 4, 256) +
+         align_up((size_t)n_q * 4, 256) + 256 + 1024;
 }
 
 extern "C" int anyloc_index_search(const void* index, size_t index_bytes, int64_t capacity, int64_t n_db, const float* qu,
@@ -267,8 +442,12 @@ extern "C" int anyloc_index_search(const void* index, size_t index_bytes, int64_
   void* qu_hi = w.take<char>((size_t)n_q * Dv * esz);
   void* qu_lo = w.take<char>((size_t)n_q * Dv * esz);
   float* qq = w.take<float>(n_q);
+  float* dnq = w.take<float>(n_q);
   float* scores = w.take<float>((size_t)n_q * (size_t)n_db);
-  if (!qu_hi || !qu_lo || !qq || !scores) {
+  int32_t* cand = w.take<int32_t>((size_t)n_q * CAND_MAX);
+  int32_t* cand_n = w.take<int32_t>(n_q);
+  int* flags = w.take<int>(64);
+  if (!qu_hi || !qu_lo || !qq || !dnq || !scores || !cand || !cand_n || !flags) {
     set_error("index_search: workspace too small (%zu given, %zu needed)", ws_bytes,
               anyloc_index_search_workspace_bytes(n_db, n_q, Dv, normalize));
     return ANYLOC_ERR_WORKSPACE;
@@ -276,18 +455,38 @@ extern "C" int anyloc_index_search(const void* index, size_t index_bytes, int64_
   int rc;
   {
     ProfScope ps(PC_TOPK, st, (v.f16 ? 8.0 : 12.0) * (double)n_q * Dv);
-    if (v.f16) normalize_rows_split_kernel<true><<<n_q, 256, 0, st>>>(qu, Dv, normalize, qu_hi, qu_lo, qq);
-    else normalize_rows_split_kernel<false><<<n_q, 256, 0, st>>>(qu, Dv, normalize, qu_hi, qu_lo, qq);
+    if (v.f16) normalize_rows_split_kernel<true><<<n_q, 256, 0, st>>>(qu, Dv, normalize, qu_hi, qu_lo, qq, dnq, nullptr);
+    else normalize_rows_split_kernel<false><<<n_q, 256, 0, st>>>(qu, Dv, normalize, qu_hi, qu_lo, qq, nullptr, nullptr);
     ANYLOC_CHECK_LAUNCH();
   }
-  // score GEMM on the tcgen05 engine (gemm_dispatch records it under PC_GEMM_TC with 2*n_q*n_db*Dv FLOPs)
-  rc = anyloc_gemm_nt(qu_hi, qu_lo, Dv, v.hi, v.lo, Dv, n_q, (int)n_db, Dv, v.f16 ? ANYLOC_PAIR_F16 : ANYLOC_PAIR_TF32,
-                      v.f16 ? 1.0f / (kRetrievalScale * kRetrievalScale) : 1.0f, ANYLOC_EPI_BIAS, nullptr, nullptr, nullptr,
-                      scores, nullptr, (int)n_db, ANYLOC_PAIR_TF32, ANYLOC_GEMM_AUTO, stream);
+  const float alpha = v.f16 ? 1.0f / (kRetrievalScale * kRetrievalScale) : 1.0f;
+  const int pair = v.f16 ? ANYLOC_PAIR_F16 : ANYLOC_PAIR_TF32;
+  // ---- coarse pass + exact re-scoring of the candidates (inner product, fp16 index); ANYLOC_TOPK_COARSE=0 disables
+  static int coarse_env = -1;
+  if (coarse_env < 0) { const char* e = getenv("ANYLOC_TOPK_COARSE"); coarse_env = e ? atoi(e) : 1; }
+  const bool coarse = coarse_env && v.f16 && metric == ANYLOC_METRIC_IP && k <= 64 && n_db >= 1024 && n_q >= 32;
+  const int* gate = nullptr;
+  if (coarse) {
+    ANYLOC_CHECK_CUDA(cudaMemsetAsync(flags, 0, 256, st));
+    // hi-only GEMM: a_lo = b_lo = nullptr selects the single-pass kernels of the tcgen05 engine (recorded under PC_GEMM_TC
+    // with the FULL 2*n_q*n_db*Dv algorithmic FLOPs: the coarse pass + re-scoring replace the whole product)
+    rc = anyloc_gemm_nt(qu_hi, nullptr, Dv, v.hi, nullptr, Dv, n_q, (int)n_db, Dv, pair, alpha, ANYLOC_EPI_BIAS, nullptr,
+                        nullptr, nullptr, scores, nullptr, (int)n_db, ANYLOC_PAIR_TF32, ANYLOC_GEMM_TC3, stream);
+    if (rc) return rc;
+    ProfScope ps(PC_TOPK, st, 8.0 * (double)n_q * (double)n_db);
+    topk_candidates_kernel<<<n_q, 1024, 0, st>>>(scores, (int)n_db, n_db, k, dnq, v.hdr, cand, cand_n, flags);
+    ANYLOC_CHECK_LAUNCH();
+    topk_rescore_kernel<<<n_q, 256, 0, st>>>((const __half*)v.hi, (const __half*)v.lo, (const __half*)qu_hi,
+                                             (const __half*)qu_lo, Dv, k, cand, cand_n, flags, dist, idx);
+    ANYLOC_CHECK_LAUNCH();
+    gate = flags;            // the exact path below only runs (on the device) if a candidate list overflowed
+  }
+  // ---- exact path: 3-term score GEMM on the tcgen05 engine (gemm_dispatch records it under PC_GEMM_TC) + selection
+  rc = anyloc_gemm_nt_gated(qu_hi, qu_lo, Dv, v.hi, v.lo, Dv, n_q, (int)n_db, Dv, pair, alpha, scores, (int)n_db, gate, stream);
   if (rc) return rc;
   {
-    ProfScope ps(PC_TOPK, st, 8.0 * (double)n_q * (double)n_db);
-    topk_select2_kernel<<<n_q, 1024, 0, st>>>(scores, (int)n_db, n_db, k, metric, qq, v.sq, dist, idx);
+    ProfScope ps(PC_TOPK, st, gate ? 0.0 : 8.0 * (double)n_q * (double)n_db);
+    topk_select2_kernel<<<n_q, 1024, 0, st>>>(scores, (int)n_db, n_db, k, metric, qq, v.sq, dist, idx, gate);
     ANYLOC_CHECK_LAUNCH();
   }
   return ANYLOC_OK;
@@ -316,8 +515,9 @@ extern "C" int anyloc_topk(const float* db, const float* qu, int n_db, int n_q, 
     set_error("topk: workspace too small (%zu given, %zu needed)", ws_bytes, need);
     return ANYLOC_ERR_WORKSPACE;
   }
-  int rc = anyloc_index_add(ws, ib, n_db, 0, db, n_db, Dv, normalize, stream);
+  int rc = anyloc_index_init(ws, ib, n_db, Dv, normalize, stream);
   if (rc) return rc;
+  if ((rc = anyloc_index_add(ws, ib, n_db, 0, db, n_db, Dv, normalize, stream))) return rc;
   char* rest = (char*)ws + align_up(ib, 256);
   return anyloc_index_search(ws, ib, n_db, n_db, qu, n_q, Dv, k, metric, normalize, dist, idx, rest,
                              ws_bytes - align_up(ib, 256), stream);

@@ -114,6 +114,7 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   float* s_cdnorm = s_cnorm + MAX_K;                                    // [MAX_K]
   uint64_t* list_full = tempty_bar + 2 + 1;                             // [2] epilogue -> re-scoring warps (after the TMEM slot word pair)
   uint64_t* list_free = list_full + 2;                                  // [2] re-scoring warps -> epilogue
+  uint64_t* last_full = list_free + 2;                                  // [1] the CTA's LAST list is complete (single phase)
   int32_t* amb_row = reinterpret_cast<int32_t*>(bar_area + BAR_BYTES + VEC_BYTES);    // [2][BM]
   uint32_t* amb_msk = reinterpret_cast<uint32_t*>(amb_row + 2 * BM);                   // [2][BM][MAX_K/32]
   int32_t* amb_n = reinterpret_cast<int32_t*>(amb_msk + 2 * BM * (MAX_K / 32));        // [2]
@@ -134,6 +135,7 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       mbar_init(smem_u32(list_full + s), 4); mbar_init(smem_u32(list_free + s), 1);
       amb_n[s] = 0;
     }
+    mbar_init(smem_u32(last_full), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -319,7 +321,9 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         for (int i = 0; i < MAX_K / 32; ++i) amb_msk[(buf * BM + idx) * (MAX_K / 32) + i] = mask[i];
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(list_full + buf));
+      // the last list goes to ALL warps through its own single-phase barrier: warps without a role reach the tail at
+      // once and have not followed the phases of list_full (a parity wait there would alias an earlier phase)
+      if (lane == 0) mbar_arrive(smem_u32(tile + (int)gridDim.x >= num_tiles ? last_full : list_full + buf));
     }
   } else if (warp >= 8) {
     // ---------------------------------------- exact fp32 re-scoring of the tile's ambiguous rows (warp per row): the
@@ -345,7 +349,7 @@ vlad_assign_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     if (my_tiles > 0) {
       const int tl = my_tiles - 1, buf = tl & 1;
-      mbar_wait(smem_u32(list_full + buf), (uint32_t)((tl >> 1) & 1));
+      mbar_wait(smem_u32(last_full), 0u);
       const int n = amb_n[buf];
       for (int i = warp; i < n; i += THREADS / 32)
         rescore_row(p, s_cbias, amb_row[buf * BM + i], amb_msk + (buf * BM + i) * (MAX_K / 32), lane);

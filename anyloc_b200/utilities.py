@@ -452,9 +452,10 @@ class _KMeans:
         self.fit_predict(X, centroids)
 
 
-VLAD_KERNEL_DESCRIPTION = ("VLAD v3: vlad_assign_tc_kernel (TMA + tcgen05 coarse scores + row norms) -> "
-                           "vlad_rescore_amb_kernel (ambiguous rows only) -> vlad_accumulate3_kernel (+ fused "
-                           "normalisation); prepared vocabulary, 3 launches")
+VLAD_KERNEL_DESCRIPTION = ("VLAD v3.1: vlad_assign_tc_kernel (TMA stream + tcgen05 coarse scores + row norms + exact "
+                           "re-scoring of the ambiguous rows by dedicated warps, wave-balanced tiles) -> "
+                           "vlad_accumulate3_kernel (label-sorted residual sums + fused normalisation); prepared "
+                           "vocabulary, 2 launches")
 
 
 class VLAD:
@@ -791,9 +792,10 @@ def pool_descriptors(patch_descs: torch.Tensor, method: str = "gem", gem_p: floa
 
 
 # ------------------------------------------------------------------ retrieval
-TOPK_KERNEL_DESCRIPTION = ("retrieval score GEMM: gemm_tc3_2cta_kernel<true, BIAS> (tcgen05 cta_group::2, fp16 pairs of the "
-                           "unit rows, 3-term split, fp32 RN chunk accumulation) over a prepared database index, then "
-                           "topk_select2_kernel (one pass + candidate list)")
+TOPK_KERNEL_DESCRIPTION = ("retrieval: gemm_tc3_2cta_kernel<true, BIAS, hi-only> (tcgen05 cta_group::2, ONE fp16 pass = coarse "
+                           "scores with a rigorous per-query error bound) over a prepared database index -> "
+                           "topk_candidates_kernel -> topk_rescore_kernel (exact fp32 re-scoring of the candidates from the "
+                           "(hi,lo) pairs + k-best); 3-term GEMM + topk_select2_kernel as the device-gated fallback")
 
 
 class FlatIndex:
@@ -814,18 +816,16 @@ class FlatIndex:
 
     def _reserve(self, capacity, dev):
         lib = _lib.load()
-        blob = torch.empty(lib.anyloc_index_bytes(capacity, self.dp, int(self.norm_descs)), dtype=torch.uint8, device=dev)
-        if self.ntotal:         # growth: re-pack the used rows of the three sections into the larger blob
-            for (o_old, per_row), (o_new, _) in zip(self._sections(self.capacity), self._sections(capacity)):
-                blob[o_new:o_new + per_row * self.ntotal].copy_(self._blob[o_old:o_old + per_row * self.ntotal])
+        norm = int(self.norm_descs)
+        blob = torch.empty(lib.anyloc_index_bytes(capacity, self.dp, norm), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.anyloc_index_init(_lib.ptr(blob), blob.numel(), capacity, self.dp, norm, _lib.stream_ptr()),
+                       "anyloc_index_init")
+            if self.ntotal:         # growth: the used rows of every section move into the larger blob
+                _lib.check(lib.anyloc_index_copy(_lib.ptr(blob), blob.numel(), capacity, _lib.ptr(self._blob),
+                                                 self._blob.numel(), self.capacity, self.ntotal, self.dp, norm,
+                                                 _lib.stream_ptr()), "anyloc_index_copy")
         self._blob, self.capacity, self._dev = blob, capacity, dev
-
-    def _sections(self, cap):
-        """(byte offset, bytes per row) of the hi, lo and |y|^2 sections of a blob of `cap` rows (csrc/topk.cu)."""
-        f16 = self.norm_descs and self.dp % 8 == 0 and os.environ.get("ANYLOC_TOPK_F16", "1") != "0"
-        per_row = self.dp * (2 if f16 else 4)
-        pair = (cap * per_row + 255) // 256 * 256
-        return [(0, per_row), (pair, per_row), (2 * pair, 4)]
 
     def add(self, x: Union[np.ndarray, torch.Tensor]):
         on_dev = isinstance(x, torch.Tensor) and x.is_cuda

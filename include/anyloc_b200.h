@@ -152,8 +152,16 @@ int anyloc_topk(const float* db, const float* qu, int n_db, int n_q, int Dv, int
  * pairs.  The blob is caller-owned (anyloc_index_bytes for `capacity` rows); rows can be added in chunks at any
  * row_offset (e.g. as descriptor batches arrive from the all-gather); a search over the first n_db rows is
  * anyloc_topk minus the per-call database pass.  `normalize` must be the same value in all calls on one blob.
- * anyloc_index_search: workspace from anyloc_index_search_workspace_bytes (query pairs + the [n_q, n_db] scores). */
+ * anyloc_index_search: workspace from anyloc_index_search_workspace_bytes (query pairs + the [n_q, n_db] scores +
+ * candidate lists).  Inner-product searches over an fp16-pair index run a hi-only (coarse) tensor-core pass with a
+ * rigorous per-query error bound, re-score the candidates that could belong to the top-k exactly in fp32 and fall back
+ * to the full 3-term product on the device when a candidate list overflows: same results, a third of the MMAs. */
 size_t anyloc_index_bytes(int64_t capacity, int Dv, int normalize);
+/* a fresh blob is initialised once before the first add; anyloc_index_copy moves the first n_rows rows into a larger
+ * blob (growth) */
+int anyloc_index_init(void* index, size_t index_bytes, int64_t capacity, int Dv, int normalize, void* stream);
+int anyloc_index_copy(void* dst, size_t dst_bytes, int64_t dst_capacity, const void* src, size_t src_bytes,
+                      int64_t src_capacity, int64_t n_rows, int Dv, int normalize, void* stream);
 int anyloc_index_add(void* index, size_t index_bytes, int64_t capacity, int64_t row_offset, const float* rows,
                      int n_rows, int Dv, int normalize, void* stream);
 size_t anyloc_index_search_workspace_bytes(int64_t n_db, int n_q, int Dv, int normalize);

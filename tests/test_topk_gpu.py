@@ -73,3 +73,44 @@ def test_topk_config3_shape_properties(u):
     assert bool((dist[:, :-1] >= dist[:, 1:]).all())
     ref = (torch.nn.functional.normalize(qu).double() @ db.double().T).topk(5, dim=1)
     assert torch.equal(idx, ref.indices) and rel_inf(dist.cpu(), ref.values.cpu()) < 1e-5
+
+
+def _check_vs_fp64(db, qu, dist, idx, k):
+    d64, i64 = ao.top_k(db.cpu(), qu.cpu(), k + 1, "cosine", dtype=torch.float64)
+    dist, idx = dist.cpu(), idx.cpu()
+    for q in range(qu.shape[0]):
+        gaps = (d64[q, 1:] - d64[q, :-1]).abs()
+        if not bool((gaps[:k] < 1e-6).any()):
+            assert torch.equal(idx[q], i64[q, :k]), (q, idx[q], i64[q, :k])
+    assert rel_inf(dist, d64[:, :k]) < 1e-4
+
+
+def test_topk_coarse_pass_and_fallback(u):
+    """The inner-product search on an fp16-pair index: hi-only tensor-core pass (2-CTA kernel at >= 512 queries) + exact
+    re-scoring of the candidates, and the device-gated 3-term fallback when a candidate list overflows (here: 400
+    identical database rows next to the query -> 400 candidates > CAND_MAX; ties must still come out lowest index first)."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    db = torch.randn(4096, 256, device="cuda", generator=g)
+    qu = db[torch.randint(0, 4096, (640,), device="cuda", generator=g)] + 0.7 * torch.randn(640, 256, device="cuda", generator=g)
+    dist, idx = u.top_k_search(db, qu, 10)
+    _check_vs_fp64(db, qu, dist, idx, 10)
+    # clustered database: many near-equal scores around the k-th best
+    centre = torch.randn(1, 256, device="cuda", generator=g)
+    db2 = centre + 0.02 * torch.randn(3000, 256, device="cuda", generator=g)
+    qu2 = centre + 0.02 * torch.randn(64, 256, device="cuda", generator=g)
+    dist, idx = u.top_k_search(db2, qu2, 5)
+    _check_vs_fp64(db2, qu2, dist, idx, 5)
+    # overflow -> fallback
+    db3 = db.clone()
+    db3[100:500] = db3[100]
+    qu3 = db3[100][None] + 0.05 * torch.randn(40, 256, device="cuda", generator=g)
+    dist, idx = u.top_k_search(db3, qu3, 8)
+    assert torch.equal(idx.cpu(), torch.arange(100, 108).expand(40, 8))
+    assert bool((dist[:, :1] == dist[:, 1:]).all())
+    # growth of a FlatIndex keeps what the coarse pass needs (per-row norms, header)
+    ix = u.FlatIndex(256, "cosine", True, device="cuda")
+    for c0 in range(0, 4096, 1000):
+        ix.add(db[c0:c0 + 1000])
+    d2, i2 = ix.search(qu, 10)
+    d1, i1 = u.top_k_search(db, qu, 10)
+    assert torch.equal(i1, i2) and torch.equal(d1, d2)

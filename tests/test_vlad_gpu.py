@@ -120,6 +120,28 @@ def test_vlad_c5_shape_properties(u):
     assert rel_inf(out[0].cpu(), ref) < TOL
 
 
+@pytest.mark.parametrize("B,N,D,K", [(48, 1369, 256, 128), (64, 1369, 1024, 128), (200, 529, 64, 16)])
+def test_vlad_many_tiles_per_cta(u, B, N, D, K):
+    """More 128-row tiles than SMs (the full BASELINE config 5 batch: 87 616 rows = 4-5 tiles per persistent CTA): the
+    per-tile hand-over of ambiguous rows to the re-scoring warps, their double-buffered lists and the all-warp tail on
+    each CTA's last tile.  Labels exact outside the fp64-ambiguous set on two images, descriptors against the oracle,
+    batch == single image (bitwise)."""
+    g = torch.Generator(device="cuda").manual_seed(B + D)
+    x = torch.nn.functional.normalize(torch.randn(B, N, D, device="cuda", generator=g), dim=-1)
+    centers = 0.6 * x.reshape(-1, D)[torch.randperm(B * N, device="cuda", generator=g)[:K]].contiguous()
+    v = make_vlad(u, K, centers.cpu())
+    out = v.generate_multi(x)
+    assert torch.allclose(out.norm(dim=1), torch.ones(B, device="cuda"), atol=1e-5)
+    lab_all = v.kmeans.predict(x.reshape(-1, D)).reshape(B, N)
+    assert int(lab_all.min()) >= 0 and int(lab_all.max()) < K
+    for b in (0, B - 1):
+        gap, lab64 = ao.label_margins(x[b].cpu(), centers.cpu())
+        assert torch.equal(lab_all[b].cpu()[gap > 1e-5], lab64[gap > 1e-5])
+        ref = ao.vlad_generate(x[b].cpu(), centers.cpu(), labels=lab_all[b].cpu(), dtype=torch.float64)
+        assert rel_inf(out[b].cpu(), ref) < TOL
+        assert torch.equal(v.generate(x[b]), out[b])
+
+
 def test_vlad_switches_and_errors(u):
     x, centers, _ = ao.clustered_features(64, 64, 4, seed=2)
     for kw in ({"intra_norm": False}, {"norm_descs": False}, {"dist_mode": "euclidean"}):
