@@ -43,7 +43,9 @@ template <int BN, bool LO = true> struct Cfg {
   static constexpr int TMEM_COLS = 2 * BN;          // 512 or 256: power of two
 };
 constexpr int CHUNK_KB_TF32 = 2;          // k-blocks (128 B of K each) accumulated in the tensor core before an RN
-constexpr int CHUNK_KB_F16 = 4;           // drain: 24 / 48 MMAs per chunk -> RZ bias ~4e-7 / ~8e-7 relative
+constexpr int CHUNK_KB_F16 = 4;           // drain: 24 / 48 MMAs per chunk -> RZ bias ~4e-7 / ~8e-7 relative (1-CTA kernel)
+constexpr int CHUNK_KB_F16_2CTA = 8;      // the ViT's 2-CTA fp16 kernel: 96 MMAs per chunk -- measured at c2 (31 blocks): features 1.1e-5
+                                          // from the oracle instead of 6.1e-6 (tolerance 1e-4) for +1.4 % throughput: half the TMEM drains
 constexpr int EPI_WARPS = 16;             // 4 TMEM lane quarters x 4 column quarters
 constexpr int THREADS = 128 + EPI_WARPS * 32;
 
@@ -733,7 +735,7 @@ static int launch_2cta(const void* a_hi, const void* a_lo, int lda, const void* 
   // ANYLOC_GEMM_CHUNK: k-blocks per TMEM chunk (A/B knob; default 4 fp16 / 2 tf32 k-blocks = 48 / 24 MMAs per drain)
   static int chunk_env = -1;
   if (chunk_env < 0) { const char* e = getenv("ANYLOC_GEMM_CHUNK"); chunk_env = e ? atoi(e) : 0; }
-  const int chunk = chunk_env > 0 ? chunk_env : (F16 ? CHUNK_KB_F16 : CHUNK_KB_TF32);
+  const int chunk = chunk_env > 0 ? chunk_env : (F16 ? CHUNK_KB_F16_2CTA : CHUNK_KB_TF32);
   // one instantiation per epilogue mode (compact per-tile code); -1 = the diagnostic "discard" variant
 #define ANYLOC_LAUNCH_2CTA(MODE_)                                                                                   \
   case MODE_: {                                                                                                     \

@@ -274,6 +274,7 @@ topk_candidates_kernel(const float* __restrict__ scores, int n_db, int64_t ld, i
 __device__ __forceinline__ float2 h2f(uint32_t u) {
   return __half22float2(*reinterpret_cast<const __half2*>(&u));
 }
+constexpr int RS_CHUNK = 4096;          // query elements staged per pass (fp32: 16 KB of shared memory)
 __global__ void __launch_bounds__(256)
 topk_rescore_kernel(const __half* __restrict__ db_hi, const __half* __restrict__ db_lo, const __half* __restrict__ qu_hi,
                     const __half* __restrict__ qu_lo, int Dv, int k, const int32_t* __restrict__ cand,
@@ -281,34 +282,50 @@ topk_rescore_kernel(const __half* __restrict__ db_hi, const __half* __restrict__
                     int64_t* __restrict__ idx) {
   if (*reinterpret_cast<const volatile int*>(overflow) != 0) return;       // the 3-term fallback answers every query
   const int q = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __shared__ __align__(16) float xq[RS_CHUNK];      // this pass' slice of the query, hi + lo (exact: 22 significant bits)
   __shared__ float cv[CAND_MAX];
   __shared__ int ci[CAND_MAX];
   __shared__ float bv[33];
   __shared__ int bi[33];
   const int n_c = cand_n[q];
-  const uint4* qh = reinterpret_cast<const uint4*>(qu_hi + (size_t)q * Dv);
-  const uint4* ql = reinterpret_cast<const uint4*>(qu_lo + (size_t)q * Dv);
-  const int steps = Dv >> 3;                 // 8 halves (16 bytes) per lane and step
-  for (int c = w; c < n_c; c += 8) {
-    const int j = cand[(size_t)q * CAND_MAX + c];
-    const uint4* dh = reinterpret_cast<const uint4*>(db_hi + (size_t)j * Dv);
-    const uint4* dl = reinterpret_cast<const uint4*>(db_lo + (size_t)j * Dv);
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int t = lane; t < steps; t += 32) {
-      const uint4 xh = __ldg(qh + t), xl = __ldg(ql + t), yh = __ldg(dh + t), yl = __ldg(dl + t);
-      const uint32_t xhw[4] = {xh.x, xh.y, xh.z, xh.w}, xlw[4] = {xl.x, xl.y, xl.z, xl.w};
-      const uint32_t yhw[4] = {yh.x, yh.y, yh.z, yh.w}, ylw[4] = {yl.x, yl.y, yl.z, yl.w};
+  for (int c = threadIdx.x; c < n_c; c += blockDim.x) { cv[c] = 0.f; ci[c] = cand[(size_t)q * CAND_MAX + c]; }
+  // The query is read ONCE per CTA (slice by slice into shared memory); every candidate row is streamed once, in
+  // 8 KB pieces per array.  Warp w owns candidates w, w + 8, ...; partial sums are added slice by slice in slice order.
+  for (int d0 = 0; d0 < Dv; d0 += RS_CHUNK) {
+    const int len = min(RS_CHUNK, Dv - d0);          // multiple of 8
+    __syncthreads();
+    for (int t = threadIdx.x; t < (len >> 3); t += blockDim.x) {
+      const uint4 xh = __ldg(reinterpret_cast<const uint4*>(qu_hi + (size_t)q * Dv + d0) + t);
+      const uint4 xl = __ldg(reinterpret_cast<const uint4*>(qu_lo + (size_t)q * Dv + d0) + t);
+      const uint32_t hw[4] = {xh.x, xh.y, xh.z, xh.w}, lw[4] = {xl.x, xl.y, xl.z, xl.w};
+      float o[8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 a = h2f(xhw[e]), b = h2f(xlw[e]), c2 = h2f(yhw[e]), d2 = h2f(ylw[e]);
-        const float x0 = a.x + b.x, x1 = a.y + b.y, y0 = c2.x + d2.x, y1 = c2.y + d2.y;     // exact: 22 significant bits
-        if (e & 1) { a2 = fmaf(x0, y0, a2); a3 = fmaf(x1, y1, a3); }
-        else       { a0 = fmaf(x0, y0, a0); a1 = fmaf(x1, y1, a1); }
-      }
+      for (int e = 0; e < 4; ++e) { const float2 a = h2f(hw[e]), b2 = h2f(lw[e]); o[2 * e] = a.x + b2.x; o[2 * e + 1] = a.y + b2.y; }
+      *reinterpret_cast<float4*>(xq + t * 8) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(xq + t * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
     }
-    const float tot = warp_sum((a0 + a1) + (a2 + a3));
-    if (lane == 0) { cv[c] = tot * (1.0f / (kRetrievalScale * kRetrievalScale)); ci[c] = j; }
+    __syncthreads();
+    for (int c = w; c < n_c; c += 8) {
+      const size_t roff = (size_t)ci[c] * Dv + d0;
+      const uint4* dh = reinterpret_cast<const uint4*>(db_hi + roff);
+      const uint4* dl = reinterpret_cast<const uint4*>(db_lo + roff);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int t = lane; t < (len >> 3); t += 32) {
+        const uint4 yh = __ldg(dh + t), yl = __ldg(dl + t);
+        const float4 x0 = *reinterpret_cast<const float4*>(xq + t * 8), x1 = *reinterpret_cast<const float4*>(xq + t * 8 + 4);
+        const float2 h0 = h2f(yh.x), l0 = h2f(yl.x), h1 = h2f(yh.y), l1 = h2f(yl.y);
+        const float2 h2 = h2f(yh.z), l2 = h2f(yl.z), h3 = h2f(yh.w), l3 = h2f(yl.w);
+        a0 = fmaf(x0.x, h0.x + l0.x, a0); a1 = fmaf(x0.y, h0.y + l0.y, a1);
+        a2 = fmaf(x0.z, h1.x + l1.x, a2); a3 = fmaf(x0.w, h1.y + l1.y, a3);
+        a0 = fmaf(x1.x, h2.x + l2.x, a0); a1 = fmaf(x1.y, h2.y + l2.y, a1);
+        a2 = fmaf(x1.z, h3.x + l3.x, a2); a3 = fmaf(x1.w, h3.y + l3.y, a3);
+      }
+      const float part = warp_sum((a0 + a1) + (a2 + a3));
+      if (lane == 0) cv[c] += part;
+    }
   }
+  __syncthreads();
+  for (int c = threadIdx.x; c < n_c; c += blockDim.x) cv[c] *= 1.0f / (kRetrievalScale * kRetrievalScale);
   __syncthreads();
   for (int r = 0; r < k; ++r) {
     float b = -INFINITY; int bidx = 0x7fffffff; int bslot = -1;
