@@ -827,6 +827,17 @@ class FlatIndex:
                                                  _lib.stream_ptr()), "anyloc_index_copy")
         self._blob, self.capacity, self._dev = blob, capacity, dev
 
+    def reset(self):
+        """faiss `index.reset()`: forget the rows, keep the allocation."""
+        if self._blob is not None and self.ntotal:
+            self.ntotal = 0
+            self._reserve_header_only()
+
+    def _reserve_header_only(self):
+        with torch.cuda.device(self._dev):
+            _lib.check(_lib.load().anyloc_index_init(_lib.ptr(self._blob), self._blob.numel(), self.capacity, self.dp,
+                                                     int(self.norm_descs), _lib.stream_ptr()), "anyloc_index_init")
+
     def add(self, x: Union[np.ndarray, torch.Tensor]):
         on_dev = isinstance(x, torch.Tensor) and x.is_cuda
         dev = _lib.require_cuda(x.device if on_dev else self._dev)

@@ -388,11 +388,19 @@ def run_pipeline(args, wl):
         gather(desc, i)
         return desc
 
+    e2e_marks = []          # (before H2D, after H2D, after compute + gather launch, after D2H) events per e2e step
+
     def step_e2e(i):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
         x = img_host.to(dev, non_blocking=True)                    # H2D of this step's inputs
+        ev[1].record()
         desc = vlad.generate_multi(ext(x))
         gather(desc, i)
+        ev[2].record()
         out_host[i & 1].copy_(desc, non_blocking=True)             # D2H of the result
+        ev[3].record()
+        e2e_marks.append(ev)
 
     def loop(fn):
         def body(i):
@@ -417,7 +425,9 @@ def run_pipeline(args, wl):
     for i in range(max(1, args.warmup // 2)):
         step_e2e(i)
     drain()
+    e2e_marks.clear()
     ms_e2e = R.timed(loop(step_e2e), args.steps)
+    e2e_phase = [sum(m[j].elapsed_time(m[j + 1]) for m in e2e_marks) / len(e2e_marks) for j in range(3)]
 
     # separate instrumented pass (a cudaEvent pair per launch group): time shares and the kernels' live durations
     n_prof = min(args.steps, 3)
@@ -526,7 +536,8 @@ def run_pipeline(args, wl):
                            "alone_us": coll_us, "alone_busbw_GBs": coll_gbs, "nvlink_peak_GBs_per_dir": NVLINK_GBS_PER_DIR,
                            "in_timed_region": True, "overlapped": world > 1, "checks": chk},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * img_host.numel() * 4,
-                    "d2h_bytes_per_step": world * B * Dv * 4, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": world * B * Dv * 4, "ms_per_step": ms_e2e / args.steps,
+                    "rank0_phase_ms": {"h2d": e2e_phase[0], "compute_and_gather_launch": e2e_phase[1], "d2h": e2e_phase[2]}},
             "gpu_launches": launches, "clocks": clocks}
     if sd_host is not None:
         line["parity"] = pipeline_parity(wl, sd_host, img_host, vlad, desc, ext, u)
@@ -605,13 +616,25 @@ def run_retrieval(args, wl):
     truth_local = src + rank * n_loc
     top_k = [1, k]
 
+    # persistent buffers of the gather_db step (a service keeps them; allocating 2 x 20 GB per step would time cudaMalloc)
+    db_all_buf = torch.empty(n_db, Dv, device=dev) if world > 1 else db_local
+    index_all = u.FlatIndex(Dv, "cosine", True, capacity=n_db, device=dev)
+    d_all, i_all = torch.empty(n_q, k, device=dev), torch.empty(n_q, k, device=dev, dtype=torch.int64)
+
     def step_gather_db(i):
         """BASELINE config 4's pattern: all-gather the database descriptors, index them, every rank answers its own
-        query shard, the [n_q, k] results are gathered."""
-        db_all = adist.all_gather_descriptors(db_local)
-        index = u.FlatIndex(Dv, "cosine", True)
-        index.add(db_all)
-        d, ix = index.search(qu_local, k)
+        query shard, the [n_q, k] results are gathered.  (Equal shards: n_db_per_rank rows and n_q / world queries.)"""
+        if world > 1:
+            dist.all_gather_into_tensor(db_all_buf, db_local)            # THE collective: [n_loc, Dv] fp32 per rank
+        index_all.reset()
+        index_all.add(db_all_buf)
+        d, ix = index_all.search(qu_local, k)
+        if world == 1:
+            return d, ix
+        if n_q % world == 0:
+            dist.all_gather_into_tensor(d_all, d.contiguous())
+            dist.all_gather_into_tensor(i_all, ix.contiguous())
+            return d_all, i_all
         return adist.all_gather_rows(d), adist.all_gather_rows(ix)
 
     index_local = u.FlatIndex(Dv, "cosine", True)
@@ -665,7 +688,7 @@ def run_retrieval(args, wl):
     truth = adist.all_gather_rows(truth_local)
     ok_top1 = R.all_true(torch.equal(i_db[:, 0], truth))
     ok_same = R.all_true(torch.equal(i_db, i_gq))
-    db_all = adist.all_gather_descriptors(db_local)
+    db_all = db_all_buf                               # filled by step_gather_db above
     n_chk = nq_loc                                   # every query of this rank, database converted chunk by chunk
     qd = qu_local.double()
     qd = qd / qd.norm(dim=1, keepdim=True)
