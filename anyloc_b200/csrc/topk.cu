@@ -2,6 +2,7 @@
 // IndexFlatL2 exact search).  normalise rows -> score GEMM (fp32-equivalent) -> k-best per query,
 // best first, lowest database index first among equal scores.
 #include <stdlib.h>
+#include <algorithm>
 #include "common.cuh"
 
 // internal (api.cu): the plain-store 3-term GEMM with an optional device gate (*gate == 0 -> the kernels return at once);
@@ -22,8 +23,12 @@ template <bool F16>
 __global__ void __launch_bounds__(256)
 normalize_rows_split_kernel(const float* __restrict__ x, int D, int do_norm, void* __restrict__ hi_v,
                             void* __restrict__ lo_v, float* __restrict__ sq, float* __restrict__ dn /* nullable, F16 only */,
-                            int* __restrict__ dn_max_bits /* nullable */) {
-  const size_t row = blockIdx.x;
+                            int* __restrict__ dn_max_bits /* nullable */, int n_rows) {
+  // grid-stride over the rows with a grid of ~3 CTAs per SM: a row (196 KB at Dv = 49152) is read twice (norm pass,
+  // split pass) and the second read must still find it in L2 -- with one CTA per row ~1200 rows (230 MB) were in
+  // flight and both passes went to DRAM (ncu, round 2: 3.93 GB read for a 1.97 GB database)
+  for (size_t row = blockIdx.x; row < (size_t)n_rows; row += gridDim.x) {
+  __syncthreads();
   const float4* xr = reinterpret_cast<const float4*>(x + row * D);
   const int D4 = D >> 2;
   float ss = 0.f;
@@ -85,6 +90,99 @@ normalize_rows_split_kernel(const float* __restrict__ x, int D, int do_norm, voi
       if (dn_max_bits) atomicMax(dn_max_bits, __float_as_int(b));      // positive floats order like their bit patterns
     }
   }
+  }
+}
+
+// Single-pass form for rows that fit the registers of a 1024-thread CTA (D <= 16 * 4096 floats): the row is loaded ONCE
+// (NV float4 per thread, the whole row in flight), reduced, normalised, split and stored -- 4 B read + 4 B (fp16 pairs) or
+// 8 B (tf32 pairs) written per element, instead of reading the row twice.  Same arithmetic, except that |x|^2 is summed in
+// the order of this thread layout (fp32 rounding of the norm only).
+template <bool F16, int NV>
+__global__ void __launch_bounds__(1024, 1)
+normalize_rows_split_reg_kernel(const float* __restrict__ x, int D, int do_norm, void* __restrict__ hi_v,
+                                void* __restrict__ lo_v, float* __restrict__ sq, float* __restrict__ dn,
+                                int* __restrict__ dn_max_bits, int n_rows) {
+  const int D4 = D >> 2;
+  __shared__ float red[32];
+  __shared__ float s_tot;
+  for (size_t row = blockIdx.x; row < (size_t)n_rows; row += gridDim.x) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    float4 v[NV];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int d = threadIdx.x + j * 1024;
+      v[j] = d < D4 ? __ldg(xr + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+    ss = warp_sum(ss);
+    __syncthreads();                                   // red / s_tot of the previous row have been consumed
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < 32; ++w) t += red[w]; s_tot = t; }
+    __syncthreads();
+    const float nrm = fmaxf(sqrtf(s_tot), 1e-12f);
+    float ss2 = 0.f, dd2 = 0.f;
+    uint2* h2 = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(hi_v) + row * D);
+    uint2* l2 = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(lo_v) + row * D);
+    float4* h4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(hi_v) + row * D);
+    float4* l4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(lo_v) + row * D);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int d = threadIdx.x + j * 1024;
+      if (d >= D4) continue;
+      float4 y = v[j];
+      if (do_norm) { y.x = y.x / nrm; y.y = y.y / nrm; y.z = y.z / nrm; y.w = y.w / nrm; }
+      ss2 += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
+      if constexpr (F16) {
+        uint2 h, l;
+        const float a0 = y.x * kRetrievalScale, a1 = y.y * kRetrievalScale, a2 = y.z * kRetrievalScale, a3 = y.w * kRetrievalScale;
+        split_f16x2(a0, a1, h.x, l.x);
+        split_f16x2(a2, a3, h.y, l.y);
+        h2[d] = h; l2[d] = l;
+        const float e0 = a0 - veltkamp_hi11(a0), e1 = a1 - veltkamp_hi11(a1), e2 = a2 - veltkamp_hi11(a2), e3 = a3 - veltkamp_hi11(a3);
+        dd2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+      } else {
+        float4 h, l;
+        split_tf32(y.x, h.x, l.x); split_tf32(y.y, h.y, l.y); split_tf32(y.z, h.z, l.z); split_tf32(y.w, h.w, l.w);
+        h4[d] = h; l4[d] = l;
+      }
+    }
+    ss2 = warp_sum(ss2); dd2 = warp_sum(dd2);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss2;
+    __syncthreads();
+    if (threadIdx.x == 0 && sq) { float t = 0.f; for (int w = 0; w < 32; ++w) t += red[w]; sq[row] = t; }
+    if (F16 && dn) {
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dd2;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float t = 0.f; for (int w = 0; w < 32; ++w) t += red[w];
+        const float b = (sqrtf(t) * 1.001f + sqrtf((float)D) * 2.98e-8f) / kRetrievalScale;
+        dn[row] = b;
+        if (dn_max_bits) atomicMax(dn_max_bits, __float_as_int(b));
+      }
+    }
+  }
+}
+
+// host dispatch of the two forms
+template <bool F16>
+static cudaError_t launch_normalize_rows(const float* x, int n_rows, int D, int do_norm, void* hi, void* lo, float* sq, float* dn,
+                                         int* dn_max_bits, cudaStream_t st) {
+  const int D4 = D >> 2, sms = device_sm_count();
+  if (D4 > 2 * 1024 && D4 <= 16 * 1024) {            // long rows: the single-pass register form, one CTA per SM
+    const int grid = std::min(n_rows, sms);
+    if (D4 <= 4 * 1024) normalize_rows_split_reg_kernel<F16, 4><<<grid, 1024, 0, st>>>(x, D, do_norm, hi, lo, sq, dn, dn_max_bits, n_rows);
+    else if (D4 <= 8 * 1024) normalize_rows_split_reg_kernel<F16, 8><<<grid, 1024, 0, st>>>(x, D, do_norm, hi, lo, sq, dn, dn_max_bits, n_rows);
+    else if (D4 <= 12 * 1024) normalize_rows_split_reg_kernel<F16, 12><<<grid, 1024, 0, st>>>(x, D, do_norm, hi, lo, sq, dn, dn_max_bits, n_rows);
+    else normalize_rows_split_reg_kernel<F16, 16><<<grid, 1024, 0, st>>>(x, D, do_norm, hi, lo, sq, dn, dn_max_bits, n_rows);
+  } else {
+    normalize_rows_split_kernel<F16><<<std::min(n_rows, 8 * sms), 256, 0, st>>>(x, D, do_norm, hi, lo, sq, dn, dn_max_bits, n_rows);
+  }
+  return cudaGetLastError();
 }
 
 // k-best selection per query row, best first, lowest index first among equal scores (metric IP: larger is better;
@@ -402,12 +500,12 @@ extern "C" int anyloc_index_add(void* index, size_t index_bytes, int64_t capacit
   ProfScope ps(PC_TOPK, st, (v.f16 ? 8.0 : 12.0) * (double)n_rows * Dv);
   const size_t off = (size_t)row_offset * Dv;
   if (v.f16)
-    normalize_rows_split_kernel<true><<<n_rows, 256, 0, st>>>(rows, Dv, normalize, (__half*)v.hi + off, (__half*)v.lo + off,
-                                                              v.sq + row_offset, v.dn + row_offset, v.hdr);
+    ANYLOC_CHECK_CUDA(launch_normalize_rows<true>(rows, n_rows, Dv, normalize, (__half*)v.hi + off, (__half*)v.lo + off,
+                                                  v.sq + row_offset, v.dn + row_offset, v.hdr, st));
   else
-    normalize_rows_split_kernel<false><<<n_rows, 256, 0, st>>>(rows, Dv, normalize, (float*)v.hi + off, (float*)v.lo + off,
-                                                               v.sq + row_offset, nullptr, nullptr);
-  ANYLOC_CHECK_LAUNCH();
+    ANYLOC_CHECK_CUDA(launch_normalize_rows<false>(rows, n_rows, Dv, normalize, (float*)v.hi + off, (float*)v.lo + off,
+                                                   v.sq + row_offset, nullptr, nullptr, st));
+  count_launch();
   return ANYLOC_OK;
 }
 
@@ -472,9 +570,9 @@ extern "C" int anyloc_index_search(const void* index, size_t index_bytes, int64_
   int rc;
   {
     ProfScope ps(PC_TOPK, st, (v.f16 ? 8.0 : 12.0) * (double)n_q * Dv);
-    if (v.f16) normalize_rows_split_kernel<true><<<n_q, 256, 0, st>>>(qu, Dv, normalize, qu_hi, qu_lo, qq, dnq, nullptr);
-    else normalize_rows_split_kernel<false><<<n_q, 256, 0, st>>>(qu, Dv, normalize, qu_hi, qu_lo, qq, nullptr, nullptr);
-    ANYLOC_CHECK_LAUNCH();
+    if (v.f16) ANYLOC_CHECK_CUDA(launch_normalize_rows<true>(qu, n_q, Dv, normalize, qu_hi, qu_lo, qq, dnq, nullptr, st));
+    else ANYLOC_CHECK_CUDA(launch_normalize_rows<false>(qu, n_q, Dv, normalize, qu_hi, qu_lo, qq, nullptr, nullptr, st));
+    count_launch();
   }
   const float alpha = v.f16 ? 1.0f / (kRetrievalScale * kRetrievalScale) : 1.0f;
   const int pair = v.f16 ? ANYLOC_PAIR_F16 : ANYLOC_PAIR_TF32;

@@ -61,6 +61,36 @@ def all_gather_descriptors(local_desc: torch.Tensor) -> torch.Tensor:
     return all_gather_rows(local_desc)
 
 
+def all_gather_into_index(index, db_local: torch.Tensor, staging: Optional[torch.Tensor] = None, chunks: int = 4):
+    """The descriptor all-gather of BASELINE config 4 pipelined with the database preparation: the local shard is
+    all-gathered in `chunks` pieces (asynchronously, back to back on the NCCL stream) and every piece is prepared into
+    the index (`FlatIndex.add_at`, rank r's rows at r * n_local + offset) as soon as it has landed, so the index build of
+    piece c hides behind the transfer of piece c+1.  Equal shard sizes on every rank.  `index` must have capacity
+    world * n_local; `staging` ([world * n_local, Dv], optional) receives the raw gathered pieces (piece-major).
+    Results are identical to `index.add(all_gather_descriptors(db_local))`."""
+    world, rank = world_info()
+    n_loc, Dv = db_local.shape
+    index.reset()
+    if world == 1:
+        index.add(db_local)
+        return index
+    if staging is None:
+        staging = torch.empty(world * n_loc, Dv, device=db_local.device, dtype=db_local.dtype)
+    chunks = max(1, min(chunks, n_loc))
+    bounds = [n_loc * c // chunks for c in range(chunks + 1)]
+    works = []
+    for c in range(chunks):
+        m = bounds[c + 1] - bounds[c]
+        out = staging[world * bounds[c]: world * bounds[c + 1]]
+        works.append((dist.all_gather_into_tensor(out, db_local[bounds[c]:bounds[c + 1]].contiguous(), async_op=True),
+                      out, bounds[c], m))
+    for work, out, off, m in works:
+        work.wait()
+        for r in range(world):
+            index.add_at(out[r * m:(r + 1) * m], r * n_loc + off)
+    return index
+
+
 def merge_candidates(dist_c: torch.Tensor, idx_c: torch.Tensor, k: int, largest: bool):
     """k best of per-shard candidates [n_q, C] (distance, global index); ties -> lowest index; -1 = padding."""
     invalid = idx_c < 0

@@ -859,6 +859,22 @@ class FlatIndex:
                                                 int(self.norm_descs), _lib.stream_ptr()), "anyloc_index_add")
         self.ntotal += n
 
+    def add_at(self, x: torch.Tensor, row_offset: int):
+        """Prepare device rows `x` into rows [row_offset, row_offset + len(x)) of the (already reserved) index -- for
+        callers that receive the database out of order, e.g. chunk by chunk from an all-gather (dist.py).  `ntotal`
+        becomes the highest row written; the caller must fill every row below it before searching."""
+        n = x.shape[0]
+        if self._blob is None or row_offset < 0 or row_offset + n > self.capacity:
+            raise ValueError(f"rows [{row_offset}, {row_offset + n}) outside the reserved capacity {self.capacity}")
+        rows = _as_device_f32(x, self._dev)
+        if self.dp != self.d:
+            rows = torch.nn.functional.pad(rows, (0, self.dp - self.d))
+        with torch.cuda.device(self._dev):
+            _lib.check(_lib.load().anyloc_index_add(_lib.ptr(self._blob), self._blob.numel(), self.capacity, row_offset,
+                                                    _lib.ptr(rows), n, self.dp, int(self.norm_descs), _lib.stream_ptr()),
+                       "anyloc_index_add")
+        self.ntotal = max(self.ntotal, row_offset + n)
+
     def search(self, qu: Union[np.ndarray, torch.Tensor], k: int, n_q_chunk: int = 4096):
         if self.ntotal == 0:
             raise ValueError("search on an empty index")

@@ -91,35 +91,32 @@ def usable_cores():
     return n
 
 
-def ncu_traffic(kernel_substr, tag=None):
-    """DRAM bytes (read + write) per launch of the kernels whose name contains `kernel_substr`, from the committed
-    `ncu --set full ... --page raw --csv` exports under profiles/ (newest round first).  -> (bytes, file) or (None, None)."""
+def ncu_traffic(kernel_substrs, tag, per_call=False):
+    """DRAM bytes (read + write) of the kernels whose name contains one of `kernel_substrs`, from the committed
+    `ncu --set full ... --page raw --csv` export profiles/r*_ncu_<tag>_raw.csv (newest round first): the mean per launch, or
+    with per_call the sum over the distinct kernels of their per-launch means (a call = one launch of each).
+    -> (bytes, file) or (None, None)."""
     import csv
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*raw*.csv")), reverse=True)
-    for path in files:
-        if tag and tag not in os.path.basename(path):
-            continue
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_ncu_{tag}_raw.csv")), reverse=True):
         try:
             rows = list(csv.reader(open(path, newline="")))
+            hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+            h, units = rows[hdr], rows[hdr + 1]
+            kn, rd, wr = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
         except Exception:
             continue
-        hdr = next((i for i, r in enumerate(rows) if "Kernel Name" in r), None)
-        if hdr is None:
-            continue
-        h = rows[hdr]
-        try:
-            kn, rd, wr = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
-        except ValueError:
-            continue
-        units = rows[hdr + 1] if len(rows) > hdr + 1 else []
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-
-        def val(r, c):
-            return float(r[c].replace(",", "")) * scale.get(units[c] if c < len(units) else "byte", 1.0)
-        vals = [val(r, rd) + val(r, wr) for r in rows[hdr + 2:] if len(r) > max(kn, rd, wr) and kernel_substr in r[kn]]
-        if vals:
-            return sum(vals) / len(vals), os.path.relpath(path, ROOT)
+        per_kernel = {}
+        for r in rows[hdr + 2:]:
+            if len(r) <= max(kn, rd, wr) or not any(k in r[kn] for k in kernel_substrs):
+                continue
+            v = float(r[rd].replace(",", "")) * scale.get(units[rd], 1.0) + float(r[wr].replace(",", "")) * scale.get(units[wr], 1.0)
+            per_kernel.setdefault(r[kn].split("(")[0], []).append(v)
+        if per_kernel:
+            means = [sum(v) / len(v) for v in per_kernel.values()]
+            allv = [x for v in per_kernel.values() for x in v]
+            return (sum(means) if per_call else sum(allv) / len(allv)), os.path.relpath(path, ROOT)
     return None, None
 
 
@@ -412,6 +409,13 @@ def run_pipeline(args, wl):
     for i in range(args.warmup):
         step_device(i)
     drain()
+    if os.environ.get("ANYLOC_BENCH_PROFILE_STEP"):      # `ncu --profile-from-start off ...`: exactly one step's launches
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step_device(0)
+        drain()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     sampler = ClockSampler(R.local)
     if rank == 0:
         sampler.start()
@@ -488,8 +492,9 @@ def run_pipeline(args, wl):
         kname = ("gemm_tc3_2cta_kernel<%s> (tcgen05 cta_group::2 M256xN256, kind::%s" if two_cta else
                  "gemm_tc3_kernel<256,%s> (tcgen05 cta_group::1 M128xN256, kind::%s") % (
                      "true" if f16 else "false", "f16" if f16 else "tf32")
-        traffic, tsrc = (ncu_traffic("gemm_tc3_2cta_kernel", "gemm") if (args.workload == "c2" and f16 and two_cta)
-                         else (None, None))
+        # the four per-block GEMMs (qkv <1,1,1>, w12 <1,3,1>, proj / w3 <1,4,1>) of the committed capture of this shape
+        traffic, tsrc = (ncu_traffic(["kernel<1, 1, 1>", "kernel<1, 3, 1>", "kernel<1, 4, 1>"], "vit")
+                         if (args.workload == "c2" and f16 and two_cta) else (None, None))
         roof = {"kernel": kname + ", 3-term split, fp32 accumulate, RN chunk accumulation)",
                 "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tflops_sustained"], "traffic": traffic, "traffic_source": tsrc,
@@ -507,7 +512,7 @@ def run_pipeline(args, wl):
     vroof = None
     if v_n:
         gbs = v_bytes / (v_ms / 1e3) / 1e9
-        vtraffic, vsrc = ncu_traffic("vlad_", "vlad_" + args.workload)
+        vtraffic, vsrc = ncu_traffic(["vlad_assign_tc_kernel", "vlad_accumulate3_kernel"], "vlad_" + args.workload, per_call=True)
         vroof = {"kernel": u.VLAD_KERNEL_DESCRIPTION,
                  "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                  "traffic": vtraffic, "traffic_source": vsrc,
@@ -624,10 +629,14 @@ def run_retrieval(args, wl):
     def step_gather_db(i):
         """BASELINE config 4's pattern: all-gather the database descriptors, index them, every rank answers its own
         query shard, the [n_q, k] results are gathered.  (Equal shards: n_db_per_rank rows and n_q / world queries.)"""
-        if world > 1:
-            dist.all_gather_into_tensor(db_all_buf, db_local)            # THE collective: [n_loc, Dv] fp32 per rank
-        index_all.reset()
-        index_all.add(db_all_buf)
+        if world > 1 and args.gather_chunks > 1:
+            # THE collective ([n_loc, Dv] fp32 per rank), in pieces, each prepared into the index while the next travels
+            adist.all_gather_into_index(index_all, db_local, staging=db_all_buf, chunks=args.gather_chunks)
+        else:
+            if world > 1:
+                dist.all_gather_into_tensor(db_all_buf, db_local)
+            index_all.reset()
+            index_all.add(db_all_buf)
         d, ix = index_all.search(qu_local, k)
         if world == 1:
             return d, ix
@@ -688,7 +697,7 @@ def run_retrieval(args, wl):
     truth = adist.all_gather_rows(truth_local)
     ok_top1 = R.all_true(torch.equal(i_db[:, 0], truth))
     ok_same = R.all_true(torch.equal(i_db, i_gq))
-    db_all = db_all_buf                               # filled by step_gather_db above
+    db_all = adist.all_gather_descriptors(db_local)    # rank-major reference copy (the staging buffer is piece-major)
     n_chk = nq_loc                                   # every query of this rank, database converted chunk by chunk
     qd = qu_local.double()
     qd = qd / qd.norm(dim=1, keepdim=True)
@@ -727,7 +736,7 @@ def run_retrieval(args, wl):
     if g_n:
         ach = g_fl / (g_ms / 1e3) / 1e12
         roof = {"kernel": u.TOPK_KERNEL_DESCRIPTION, "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"],
-                "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"], "traffic": ncu_traffic("gemm_tc3", "topk")[0],
+                "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"], "traffic": ncu_traffic(["gemm_tc3_2cta_kernel<1, 0, 0>"], "topk")[0],
                 "algorithmic_flops_per_launch": g_fl / g_n, "avg_launch_ms": g_ms / g_n, "launches": g_n,
                 "contract_ceiling": 1.0 / 3.0}
     line = {"metric": "queries/sec cosine top-%d retrieval over a %d-image database of %d-D VLAD descriptors" % (k, n_db, Dv),
@@ -770,6 +779,7 @@ def main():
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--small", action="store_true", help="retrieval workloads at 1/10 size (smoke runs)")
+    ap.add_argument("--gather-chunks", type=int, default=4, help="c4: pieces of the database all-gather (1 = one collective)")
     ap.add_argument("--vocab", default="fit", choices=["fit", "random"])
     ap.add_argument("--precision", default="f16x3", choices=["f16x3", "tf32x3", "auto"],
                     help="operand pair format of the tensor-core GEMMs (both fp32-equivalent; see DESIGN.md)")

@@ -77,6 +77,14 @@ def _worker(rank, world, port, ret):
         d, i = index.search(full_qu, 5)
         rd, ri = u.top_k_search(db_chunked, full_qu, 5)
         assert torch.equal(i, ri) and torch.equal(d, rd)
+        # the pipelined form of the config-4 exchange: all-gather in pieces, each prepared into the index on arrival
+        n_eq = 12                                             # equal shards
+        loc = full_db[rank * n_eq:(rank + 1) * n_eq].contiguous()
+        ix2 = u.FlatIndex(K * D, "cosine", True, capacity=world * n_eq, device=dev)
+        adist.all_gather_into_index(ix2, loc, chunks=3)
+        d3, i3 = ix2.search(full_qu, 5)
+        rd3, ri3 = u.top_k_search(full_db[:world * n_eq].contiguous(), full_qu, 5)
+        assert torch.equal(i3, ri3) and torch.equal(d3, rd3)
         dist.barrier()
         ret[rank] = True
     finally:
