@@ -17,8 +17,8 @@ NVCC_FLAGS = [
 
 
 def sources():
-    """every csrc/*.cu except drafts (*_draft.cu: design-stage code that only has to compile, see its header)"""
-    return sorted(f for f in glob.glob(os.path.join(CSRC, "*.cu")) if not f.endswith("_draft.cu"))
+    """every csrc/*.cu"""
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
 def _headers():
