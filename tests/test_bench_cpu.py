@@ -29,3 +29,14 @@ def test_flops_model_matches_survey():
     assert abs(bench.vit_flops_per_image("dinov2_vitl14", 20, 518, 518) / 1e9 - 847.8) < 1.0
     assert abs(bench.vit_flops_per_image("dinov2_vits14", 9, 224, 224) / 1e9 - 9.29) < 0.05
     assert bench.usable_cores() >= 1
+
+
+def test_roofline_traffic_comes_from_committed_ncu_exports():
+    """bench.py's `roofline.traffic` is read from the ncu --set full exports under profiles/, not hard-coded."""
+    sys.path.insert(0, ROOT)
+    import bench
+    gemm, src = bench.ncu_traffic(["kernel<1, 1, 1>", "kernel<1, 3, 1>", "kernel<1, 4, 1>"], "vit")
+    assert src and src.startswith("profiles/") and 3e8 < gemm < 1e9          # mean of the four per-block GEMMs (MB range)
+    vlad, src = bench.ncu_traffic(["vlad_assign_tc_kernel", "vlad_accumulate3_kernel"], "vlad_c2", per_call=True)
+    assert src and 1.1e8 < vlad < 3e8                                         # >= the 110.5 MB algorithmic bytes of c2
+    assert bench.ncu_traffic(["no_such_kernel"], "vit") == (None, None)
