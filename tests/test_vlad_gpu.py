@@ -142,6 +142,20 @@ def test_vlad_many_tiles_per_cta(u, B, N, D, K):
         assert torch.equal(v.generate(x[b]), out[b])
 
 
+def test_vlad_generate_multi_host_chunks(u):
+    """The driver hands VLAD.generate_multi a CPU [n_imgs, n_patches, D] tensor (scripts/dino_v2_vlad.py:233-237: 32 GB for the
+    10k-image database of c3); large host batches are streamed in chunks -- same result as one pass, and numpy in ->
+    numpy-compatible tensor out (utilities.py:892-926)."""
+    x, centers, _ = ao.clustered_features(12 * 300, 64, 8, seed=9)
+    xb = x.reshape(12, 300, 64)
+    v = make_vlad(u, 8, centers)
+    whole = v.generate_multi(xb)
+    v._host_chunk_bytes = 5 * 300 * 64 * 4 - 1            # forces chunks of 4 images
+    chunked = v.generate_multi(xb)
+    assert not chunked.is_cuda and torch.equal(whole, chunked)
+    assert torch.equal(torch.as_tensor(v.generate_multi(xb.numpy())), whole)
+
+
 def test_vlad_switches_and_errors(u):
     x, centers, _ = ao.clustered_features(64, 64, 4, seed=2)
     for kw in ({"intra_norm": False}, {"norm_descs": False}, {"dist_mode": "euclidean"}):
