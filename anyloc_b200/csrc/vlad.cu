@@ -16,7 +16,6 @@
 #include <algorithm>
 #include <vector>
 #include "epilogue.cuh"
-#include "tc_common.cuh"
 
 namespace anyloc {
 
@@ -916,8 +915,8 @@ bool vlad_assign_tc_supported(const float* feats, const float* chat_tf32, int64_
 size_t vlad_assign_tc_ws_bytes(int64_t R);
 int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_img, int64_t R, int D, int K,
                           const float* chat, const float* chat_tf32, const float* cbias, const float* cnorm,
-                          const float* cdnorm, int32_t* labels, float* inv_norm, int32_t* amb_count, int32_t* amb_rows,
-                          uint32_t* amb_mask, cudaStream_t st, int32_t* zero_ptr = nullptr, int zero_n = 0);
+                          const float* cdnorm, int32_t* labels, float* inv_norm, cudaStream_t st, int32_t* zero_ptr = nullptr,
+                          int zero_n = 0);
 }  // namespace anyloc
 
 // ANYLOC_VLAD=2 selects the v2 pipeline (coarse GEMM + full rescoring pass + shared-memory accumulate + normalise
@@ -947,7 +946,7 @@ namespace {
 struct AssignBufs {
   float *chat, *chat_tf32, *cbias, *cnorm, *coarse;
   float* cdnorm = nullptr;                                                           // v3: |c^ - tf32(c^)| per centre
-  int32_t *amb_count = nullptr, *amb_rows = nullptr; uint32_t* amb_mask = nullptr;   // v3 work list (optional)
+  int32_t* amb_count = nullptr;                                                      // reserved word of the prepared blob (round-1 work-list counter; kept zero)
   int32_t* done = nullptr; int n_done = 0;                                           // accumulate3 tickets (optional)
 };
 
@@ -958,14 +957,13 @@ int launch_assign(const float* feats, const int32_t* n_valid, int N_per_img, int
                   cudaStream_t st, bool prepared = false) {
   if (prepared)      // c^, tf32 copy, bias, norms and a zero work-list counter already sit in ab (anyloc_vlad_prepare)
     return vlad_assign_tc_launch(feats, n_valid, N_per_img, R, D, K, ab.chat, ab.chat_tf32, ab.cbias, ab.cnorm, ab.cdnorm,
-                                 labels, inv_norm, ab.amb_count, ab.amb_rows, ab.amb_mask, st, ab.done, ab.n_done);
+                                 labels, inv_norm, st, ab.done, ab.n_done);
   vlad_centre_prep_kernel<<<K, 256, 0, st>>>(centers, K, D, dist_mode, ab.chat, ab.cbias, ab.chat_tf32, ab.cnorm,
                                              ab.cdnorm, ab.amb_count, ab.amb_count ? 1 : 0, ab.done, ab.done ? ab.n_done : 0);
   ANYLOC_CHECK_LAUNCH();
-  if (vlad_version() >= 3 && ab.amb_count && ab.amb_rows && ab.amb_mask && ab.cdnorm &&
-      vlad_assign_tc_supported(feats, ab.chat_tf32, R, D, K))
+  if (vlad_version() >= 3 && ab.amb_count && ab.cdnorm && vlad_assign_tc_supported(feats, ab.chat_tf32, R, D, K))
     return vlad_assign_tc_launch(feats, n_valid, N_per_img, R, D, K, ab.chat, ab.chat_tf32, ab.cbias, ab.cnorm, ab.cdnorm, labels,
-                                 inv_norm, ab.amb_count, ab.amb_rows, ab.amb_mask, st);
+                                 inv_norm, st);
   EpiParams ep{ANYLOC_EPI_BIAS, ab.cbias, nullptr, nullptr, ab.coarse, nullptr, K};
   const bool fast = ab.coarse != nullptr && D <= 2048 && R >= 256 && R < (1ll << 31) &&
                     gemm_tc_supported(feats, nullptr, D, ab.chat_tf32, nullptr, D, (int)R, K, D, ep, false);
@@ -1003,8 +1001,6 @@ bool take_assign_bufs(Workspace& w, int64_t R, int D, int K, AssignBufs* ab) {
   ab->coarse = w.take<float>((size_t)R * K);        // may be null when the caller's workspace is the small one
   ab->cdnorm = w.take<float>(K);
   ab->amb_count = w.take<int32_t>(64);
-  ab->amb_rows = w.take<int32_t>((size_t)R);
-  ab->amb_mask = w.take<uint32_t>((size_t)R * 4);
   return ab->chat && ab->chat_tf32 && ab->cbias && ab->cnorm;
 }
 }  // namespace
@@ -1080,7 +1076,7 @@ static int vlad_generate_impl(const float* feats, const int32_t* n_valid, const 
   if (acc3) { ab.done = w.take<int32_t>((size_t)B); ab.n_done = B; }
   // prepared vocabulary: usable when this call takes the v3 assignment + accumulate3 route
   PreparedView pv;
-  const bool use_prep = prepared && acc3 && ab.done && ab.amb_rows && ab.amb_mask && vlad_version() >= 3 &&
+  const bool use_prep = prepared && acc3 && ab.done && vlad_version() >= 3 &&
                         carve_prepared(prepared, prepared_bytes, D, K, &pv) &&
                         vlad_assign_tc_supported(feats, pv.chat_tf32, (int64_t)R, D, K);
   if (use_prep) {

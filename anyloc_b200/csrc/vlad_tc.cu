@@ -44,7 +44,6 @@ struct AssignParams {
   const float* cbias; const float* cnorm; const float* cdnorm;
   int32_t* labels; float* inv_norm;
   const float* x; const float* chat;  // features [R,D] and the exact fp32 c^ [K,D]: the in-kernel re-scoring reads them
-  int32_t* amb_count; int32_t* amb_rows; uint32_t* amb_mask;   // (unused since the re-scoring moved into this kernel)
   int32_t* zero_ptr; int zero_n;     // cleared here for a LATER launch on the stream (accumulate tickets), nullable
   int stages; int stage_bytes; int n_mma; int burst;
   int tile_rows;     // rows per tile (<= BM, multiple of 8), chosen on the host so that the tiles fill whole waves of the grid
@@ -373,15 +372,16 @@ bool vlad_assign_tc_supported(const float* feats, const float* chat_tf32, int64_
 }
 
 size_t vlad_assign_tc_ws_bytes(int64_t R) {
-  return align_up((size_t)R * 4, 256) + align_up((size_t)R * (vtc::MAX_K / 32) * 4, 256) + 256;
+  (void)R;           // the ambiguous-row lists live in shared memory since the re-scoring moved into the kernel
+  return 256;
 }
 
 // feats [R,D]; chat (exact fp32 c^), chat_tf32 (rounded copy), cbias / cnorm [K] come from vlad_centre_prep_kernel;
-// amb_count must have been zeroed earlier on the stream.  labels [R], inv_norm [R] (nullable).
+// labels [R], inv_norm [R] (nullable).
 int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_img, int64_t R, int D, int K,
                           const float* chat, const float* chat_tf32, const float* cbias, const float* cnorm,
-                          const float* cdnorm, int32_t* labels, float* inv_norm, int32_t* amb_count, int32_t* amb_rows,
-                          uint32_t* amb_mask, cudaStream_t st, int32_t* zero_ptr, int zero_n) {
+                          const float* cdnorm, int32_t* labels, float* inv_norm, cudaStream_t st, int32_t* zero_ptr,
+                          int zero_n) {
   using namespace vtc;
   CUtensorMap mx, mc;
   int rc;
@@ -402,7 +402,6 @@ int vlad_assign_tc_launch(const float* feats, const int32_t* n_valid, int n_per_
   AssignParams p;
   p.n_valid = n_valid; p.n_per_img = n_per_img; p.R = (int)R; p.D = D; p.K = K;
   p.cbias = cbias; p.cnorm = cnorm; p.cdnorm = cdnorm; p.labels = labels; p.inv_norm = inv_norm;
-  p.amb_count = amb_count; p.amb_rows = amb_rows; p.amb_mask = amb_mask;
   p.x = feats; p.chat = chat; p.tile_rows = tile_rows;
   p.zero_ptr = zero_ptr; p.zero_n = zero_ptr ? zero_n : 0;
   p.n_mma = n_mma;
