@@ -104,10 +104,27 @@ def cpu_double(state_dict_for=None):
         self._rows = getattr(self, "_rows", []) + [x]
         self.ntotal += x.shape[0]
 
+    def index_rows(self):
+        if getattr(self, "_slab", None) is not None:             # rows placed with add_at()
+            return self._slab[:self.ntotal]
+        return torch.cat(self._rows)
+
     def index_search(self, qu, k, n_q_chunk=4096):
         if self.ntotal == 0:
             raise ValueError("search on an empty index")
-        return ao.top_k(torch.cat(self._rows), torch.as_tensor(qu).float(), k, self.method, self.norm_descs)
+        return ao.top_k(index_rows(self), torch.as_tensor(qu).float(), k, self.method, self.norm_descs)
+
+    def index_add_at(self, x, row_offset):
+        x = torch.as_tensor(x).float()
+        if row_offset < 0 or row_offset + x.shape[0] > self.capacity:
+            raise ValueError("rows outside the reserved capacity")
+        if getattr(self, "_slab", None) is None:
+            self._slab = torch.zeros(self.capacity, self.d)
+        self._slab[row_offset:row_offset + x.shape[0]] = x
+        self.ntotal = max(self.ntotal, row_offset + x.shape[0])
+
+    def index_reset(self):
+        self.ntotal, self._rows, self._slab = 0, [], None
 
     patch(_lib, "require_cuda", lambda device=None: cpu)
     patch(_vit, "VitWeights", _DoubleVit)
@@ -122,6 +139,8 @@ def cpu_double(state_dict_for=None):
     patch(u.FlatIndex, "_reserve", index_reserve)
     patch(u.FlatIndex, "add", index_add)
     patch(u.FlatIndex, "search", index_search)
+    patch(u.FlatIndex, "add_at", index_add_at)
+    patch(u.FlatIndex, "reset", index_reset)
     try:
         yield
     finally:

@@ -58,6 +58,39 @@ def test_sharded_pipeline_world2(n_db, n_q):
     assert ret.get(0) and ret.get(1)
 
 
+def _worker_pipelined(rank, world, port, ret):
+    """dist.all_gather_into_index over gloo: pieces of the local shard are gathered and placed at rank * n_local + offset
+    (the product's FlatIndex runs on the CPU double here: the collective + placement logic is what is under test)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from anyloc_b200 import utilities as u
+        from tests.cpu_double import cpu_double
+        g = torch.Generator().manual_seed(3)
+        n_loc, d = 10, 48
+        db = torch.randn(world * n_loc, d, generator=g)
+        qu = db[[3, 17, 8]] + 0.1 * torch.randn(3, d, generator=g)
+        with cpu_double():
+            for chunks in (1, 3, 4, 50):
+                ix = u.FlatIndex(d, "cosine", True, capacity=world * n_loc)
+                adist.all_gather_into_index(ix, db[rank * n_loc:(rank + 1) * n_loc], chunks=chunks)
+                assert ix.ntotal == world * n_loc
+                di, ii = ix.search(qu, 4)
+                rd, ri = ao.top_k(db, qu, 4)
+                assert torch.equal(ii, ri) and torch.allclose(di, rd, atol=1e-6), chunks
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_all_gather_into_index_world2():
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_pipelined, args=(2, port, ret), nprocs=2, join=True)
+    assert ret.get(0) and ret.get(1)
+
+
 def test_shard_range_partitions():
     for n in (0, 1, 7, 8, 100000):
         for world in (1, 2, 4, 8):
