@@ -408,7 +408,8 @@ class _KMeans:
         return labels
 
     def _update(self, x, labels, c):
-        """one Lloyd centroid update (anyloc_kmeans_update) -> (new centres, sum of squared centre shifts)"""
+        """one Lloyd centroid update (anyloc_kmeans_update) -> (new centres, sum of squared centre shifts as a device
+        tensor -- or a float, from a synchronous implementation)"""
         lib = _lib.load()
         n, D = x.shape
         K = c.shape[0]
@@ -419,7 +420,7 @@ class _KMeans:
             _lib.check(lib.anyloc_kmeans_update(_lib.ptr(x), _lib.ptr(labels), _lib.ptr(c), n, D, K,
                                                 _lib.ptr(new_c), _lib.ptr(err), _lib.ptr(ws), ws.numel(),
                                                 _lib.stream_ptr()), "anyloc_kmeans_update")
-        return new_c, float(err.item())
+        return new_c, err              # err stays on the device: fit_predict reads it one iteration late
 
     def predict(self, X):
         dev = _lib.require_cuda(X.device if isinstance(X, torch.Tensor) and X.is_cuda else None)
@@ -438,12 +439,36 @@ class _KMeans:
             c = x[torch.from_numpy(init).to(dev)].contiguous()
         else:
             c = _as_device_f32(centroids, dev)
-        labels = None
-        for _ in range(self.max_iter):
-            labels = self._assign(x, c)
-            c, err = self._update(x, labels, c)
-            if err <= self.tol:
-                break
+        # Lloyd iterations without a host sync on the critical path: iteration i+1 is enqueued BEFORE the convergence
+        # test of iteration i is read (its error travels to pinned host memory behind an event), so the device never
+        # idles on the host; when iteration i turns out to have converged, the speculative iteration is simply dropped
+        # -- centres and labels are exactly those of the synchronous loop (fpk: break after the update whose shift <= tol)
+        labels, pending = None, None            # pending = (labels_i, c_{i+1}, host error, event) of the previous iteration
+        hosts = None
+        for it in range(self.max_iter):
+            labels_i = self._assign(x, c)
+            c_next, err = self._update(x, labels_i, c)
+            if not isinstance(err, torch.Tensor):                 # synchronous implementation (tests' CPU double)
+                labels, c = labels_i, c_next
+                if err <= self.tol:
+                    break
+                continue
+            if hosts is None:
+                hosts = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+            host = hosts[it & 1]
+            host.copy_(err, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            if pending is not None:
+                pending[3].synchronize()
+                if float(pending[2][0]) <= self.tol:               # the PREVIOUS iteration had converged
+                    labels, c = pending[0], pending[1]
+                    pending = None
+                    break
+            pending = (labels_i, c_next, host, ev)
+            labels, c = labels_i, c_next
+        if pending is not None:
+            pending[3].synchronize()                               # results of the last enqueued iteration are final
         self.centroids = c.cpu() if was_cpu else c
         labels = labels.to(torch.int64)
         return labels.cpu() if was_cpu else labels
