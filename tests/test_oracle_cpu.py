@@ -193,3 +193,33 @@ def test_reduce_pca_matches_reference():
         a = ref.reduce_pca(tr.copy(), te.copy(), 8, **kw)
         b = ao.reduce_pca(tr.copy(), te.copy(), 8, **kw)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_preprocess_resize_matches_torchvision_golden():
+    """oracle.preprocess(resize=...) == torchvision's ToTensor + Normalize + antialiased tensor resize + CenterCrop
+    (tests/golden/preprocess_resize.npz, made by torchvision itself), bit for bit."""
+    for name, c in load_cases("preprocess_resize.npz").items():
+        out = ao.preprocess(c["img"], resize=tuple(int(v) for v in c["size"]), interpolation=name.split("_")[0])
+        assert torch.equal(out, torch.from_numpy(c["out"])), name
+
+
+def test_oracle_reproduces_reference_driver_run():
+    """tests/golden/build_vlads.npz holds what the reference's UNMODIFIED build_vlads (scripts/dino_v2_vlad.py:124-303)
+    produced over its own utilities.py; the oracle restatements (extractor, fpk k-means, VLAD, top-k) driven the same way
+    must reproduce it -- this is what the GPU parity tests are then measured against."""
+    from tests import dropin_harness as H
+    ds = H.SyntheticVprDataset()
+    model = dr.perturb(dr.build("dinov2_vits14", seed=0, depth_override=3), seed=3)
+    imgs = torch.stack([ds[i][0][:, 2:58, 2:72] for i in range(len(ds))])        # T.CenterCrop((56, 70)) of 60 x 75
+    feats = ao.extract_features(model, imgs, 2, "value")
+    for tag, g in load_cases("build_vlads.npz").items():
+        np.random.seed(42)
+        km = fpk.KMeans(4, mode="cosine")
+        km.fit(torch.nn.functional.normalize(feats[:ds.database_num].reshape(-1, 384), dim=1))
+        assert torch.allclose(km.centroids, torch.from_numpy(g["c_centers"]), atol=1e-6)
+        gen = ao.vlad_generate if tag == "hard" else ao.vlad_generate_soft
+        vl = torch.stack([gen(f, km.centroids) for f in feats])
+        assert torch.allclose(vl[:ds.database_num], torch.from_numpy(g["db_vlads"]), atol=2e-6)
+        assert torch.allclose(vl[ds.database_num:], torch.from_numpy(g["qu_vlads"]), atol=2e-6)
+        d, i = ao.top_k(vl[:ds.database_num], vl[ds.database_num:], 3)
+        assert np.array_equal(i.numpy(), g["idx"])
