@@ -62,7 +62,7 @@ def build(force=False, verbose=False):
     if verbose:
         print("\n".join(l for l in logs if l))
     r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB] +
-                       [_obj(s) for s in sources()] + ["-lcuda"] * 0, capture_output=True, text=True)
+                       [_obj(s) for s in sources()] + ["-ldl"], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed linking libanyloc_b200.so")

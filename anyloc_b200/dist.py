@@ -61,6 +61,24 @@ def all_gather_descriptors(local_desc: torch.Tensor) -> torch.Tensor:
     return all_gather_rows(local_desc)
 
 
+def all_gather_descriptors_cabi(local_desc: torch.Tensor) -> torch.Tensor:
+    """The same collective through the C ABI (`anyloc_allgather_desc`, include/anyloc_b200.h) on the NCCL communicator
+    of the default process group: what a host that is not PyTorch would bind.  Equal shard sizes; enqueued on the
+    current stream (the caller must not have other work in flight on the communicator)."""
+    from . import _lib
+    world, _ = world_info()
+    if world == 1:
+        return local_desc
+    backend = dist.distributed_c10d._get_default_group()._get_backend(local_desc.device)
+    comm = backend._comm_ptr()
+    local_desc = local_desc.contiguous()
+    out = torch.empty((world * local_desc.shape[0], local_desc.shape[1]), device=local_desc.device, dtype=torch.float32)
+    with torch.cuda.device(local_desc.device):
+        _lib.check(_lib.load().anyloc_allgather_desc(comm, _lib.ptr(local_desc), _lib.ptr(out), local_desc.shape[0],
+                                                     local_desc.shape[1], _lib.stream_ptr()), "anyloc_allgather_desc")
+    return out
+
+
 def all_gather_into_index(index, db_local: torch.Tensor, staging: Optional[torch.Tensor] = None, chunks: int = 4):
     """The descriptor all-gather of BASELINE config 4 pipelined with the database preparation: the local shard is
     all-gathered in `chunks` pieces (asynchronously, back to back on the NCCL stream) and every piece is prepared into

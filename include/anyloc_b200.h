@@ -169,6 +169,14 @@ int anyloc_index_search(const void* index, size_t index_bytes, int64_t capacity,
                         int n_q, int Dv, int k, int metric, int normalize, float* dist, int64_t* idx, void* ws,
                         size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------- collective
+ * The one data-path collective of the pipeline (BASELINE config 4): all-gather of the [n_loc, Dv] fp32 descriptors of
+ * every rank into [world * n_loc, Dv] (rank order), enqueued on `stream`.  `nccl_comm` is an ncclComm_t owned by the
+ * caller (e.g. torch.distributed's NCCL backend); the library resolves ncclAllGather from the NCCL the process has
+ * already loaded and returns ANYLOC_ERR_UNSUPPORTED when there is none.  The caller orders this call against its own
+ * use of the communicator (one stream at a time per communicator). */
+int anyloc_allgather_desc(void* nccl_comm, const float* local, float* all, size_t n_loc, int Dv, void* stream);
+
 /* ------------------------------------------------------------------- ViT
  * Replaces DinoV2ExtractFeatures.__call__ (utilities.py:263-285) and the hub model's forward
  * it triggers (facebookresearch/dinov2 DinoVisionTransformer), with the

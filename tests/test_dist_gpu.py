@@ -85,6 +85,12 @@ def _worker(rank, world, port, ret):
         d3, i3 = ix2.search(full_qu, 5)
         rd3, ri3 = u.top_k_search(full_db[:world * n_eq].contiguous(), full_qu, 5)
         assert torch.equal(i3, ri3) and torch.equal(d3, rd3)
+        # the collective through the C ABI (anyloc_allgather_desc on the process group's ncclComm_t) == torch.distributed's
+        torch.cuda.synchronize()
+        dist.barrier()
+        via_abi = adist.all_gather_descriptors_cabi(loc)
+        torch.cuda.synchronize()
+        assert torch.equal(via_abi, full_db[:world * n_eq])
         dist.barrier()
         ret[rank] = True
     finally:
